@@ -1,0 +1,16 @@
+"""dcol_b200 — B200-native batched drop-in for DifferentiableCollisions.jl's proximity path.
+
+Import as `import dcol_b200 as dc` (repo-root shim) — the directory name carries a dot and is
+not importable directly.
+"""
+from .primitives import (  # noqa: F401
+    ATT_MRP, ATT_QUAT, AbstractPrimitive, AbstractPrimitiveMRP,
+    Polytope, Capsule, Cylinder, Cone, Sphere, Polygon, Ellipsoid,
+    PolytopeMRP, CapsuleMRP, CylinderMRP, ConeMRP, SphereMRP, PolygonMRP, EllipsoidMRP,
+    create_rect_prism, create_n_sided, mrp_from_q, q_from_mrp, dcm_from_q, dcm_from_mrp,
+)
+from .shapes import ShapeTable  # noqa: F401
+from .api import (  # noqa: F401
+    Context, default_context, proximity, proximity_gradient, proximity_jacobian, MEM_HOST, MEM_DEVICE,
+)
+from . import flops_model  # noqa: F401

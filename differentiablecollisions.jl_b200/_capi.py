@@ -1,0 +1,55 @@
+"""ctypes binding of libdcol_b200.so (the C ABI of include/dcol_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+present, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdcol_b200.so")
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+lp = C.POINTER(C.c_int64)
+
+_Q_ARGS = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+           C.c_int, C.c_double, C.c_int]
+
+# name -> (restype, argtypes); this is the complete list of symbols include/dcol_b200.h declares
+SYMBOLS = {
+    "dcol_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "dcol_destroy": (None, [C.c_void_p]),
+    "dcol_last_error": (C.c_char_p, [C.c_void_p]),
+    "dcol_version": (C.c_char_p, []),
+    "dcol_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dcol_set_shapes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "dcol_proximity": (C.c_int, _Q_ARGS + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_proximity_gradient": (C.c_int, _Q_ARGS + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_proximity_jacobian": (C.c_int, _Q_ARGS + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_launch_count": (C.c_int64, [C.c_void_p]),
+    "dcol_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). dcol_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's query API over the C ABI.
+
+Single-pair calls keep the reference's names, argument meaning and error behaviour:
+  proximity(P1, P2; pdip_tol=1e-6)            -> (alpha, x)        src/proximity.jl:3-26
+  proximity_gradient(P1, P2; pdip_tol=1e-6)   -> (alpha, grad)     src/proximity_gradient.jl:80-111
+  proximity_jacobian(P1, P2; pdip_tol=1e-6)   -> (alpha, x, J)     src/proximity.jl:168-195
+`RuntimeError("pdip failed")` mirrors `error("pdip failed")` (static_solver2.jl:188); mixed
+quaternion/MRP pairs raise TypeError (the reference has no such method, src/proximity.jl:3,15).
+
+Batched variants (`Context.proximity_batch` ...) take arrays of poses and return arrays plus the
+per-pair status, never raising for solver failures.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .primitives import ATT_MRP, ATT_QUAT, AbstractPrimitive
+from .shapes import ShapeTable
+
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    # torch tensor (device or pinned host memory)
+    return C.c_void_p(a.data_ptr())
+
+
+class Context:
+    """One CUDA device + one shape table (`dcol_ctx`).  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        rc = self._lib.dcol_create(C.byref(h), int(device))
+        if rc != 0:
+            raise RuntimeError(self._lib.dcol_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.table = ShapeTable()
+        self._table_version = -1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dcol_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"dcol error {rc}: {self._lib.dcol_last_error(self._h).decode()}")
+
+    # ---- shape table ---------------------------------------------------------------------
+    def add_shape(self, prim) -> int:
+        return self.table.add(prim)
+
+    def set_shape_arrays(self, types, offs, params):
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(self._lib.dcol_set_shapes(self._h, len(types), _ptr(types), _ptr(offs), _ptr(params), params.shape[0]))
+        self._table_version = None
+
+    def sync_shapes(self):
+        if self._table_version != self.table.version:
+            t, o, p = self.table.arrays()
+            self._check(self._lib.dcol_set_shapes(self._h, len(t), _ptr(t), _ptr(o), _ptr(p), p.shape[0]))
+            self._table_version = self.table.version
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.dcol_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- instrumentation -----------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.dcol_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.dcol_last_kernel_ms(self._h))
+
+    def measure_fp64_tflops(self) -> float:
+        return float(self._lib.dcol_measure_fp64_tflops(self._h))
+
+    # ---- raw call (host numpy arrays or device/pinned torch tensors) --------------------------
+    def query_raw(self, kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem,
+                  alpha, x, deriv, status, iters):
+        if self._table_version is not None:
+            self.sync_shapes()
+        args = [self._h, int(n), _ptr(shape1), _ptr(shape2), _ptr(r1), _ptr(att1), _ptr(r2), _ptr(att2),
+                int(att_kind), float(pdip_tol), int(mem)]
+        if kind == 0:
+            rc = self._lib.dcol_proximity(*args, _ptr(alpha), _ptr(x), _ptr(status), _ptr(iters))
+        elif kind == 1:
+            rc = self._lib.dcol_proximity_gradient(*args, _ptr(alpha), _ptr(deriv), _ptr(status), _ptr(iters))
+        else:
+            rc = self._lib.dcol_proximity_jacobian(*args, _ptr(alpha), _ptr(x), _ptr(deriv), _ptr(status), _ptr(iters))
+        self._check(rc)
+
+    # ---- batched host API ----------------------------------------------------------------------
+    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol):
+        shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
+        shape2 = np.ascontiguousarray(shape2, dtype=np.int32).reshape(-1)
+        n = shape1.shape[0]
+        na = 4 if att_kind == ATT_QUAT else 3
+        nt = 6 + 2 * na
+        r1 = np.ascontiguousarray(r1, dtype=np.float64).reshape(n, 3)
+        r2 = np.ascontiguousarray(r2, dtype=np.float64).reshape(n, 3)
+        att1 = np.ascontiguousarray(att1, dtype=np.float64).reshape(n, na)
+        att2 = np.ascontiguousarray(att2, dtype=np.float64).reshape(n, na)
+        if shape2.shape[0] != n:
+            raise ValueError("shape1 and shape2 must have the same length")
+        alpha = np.empty(n)
+        x = np.empty((n, 3)) if kind != 1 else None
+        deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
+        status = np.empty(n, dtype=np.int32)
+        iters = np.empty(n, dtype=np.int32)
+        self.query_raw(kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, MEM_HOST,
+                       alpha, x, deriv, status, iters)
+        out = {"alpha": alpha, "status": status, "iters": iters}
+        if x is not None:
+            out["x"] = x
+        if kind == 1:
+            out["grad"] = deriv
+        elif kind == 2:
+            out["J"] = np.ascontiguousarray(deriv.transpose(0, 2, 1))  # (n, 4, nt)
+        return out
+
+    def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+
+    def proximity_gradient_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        return self._batch(1, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+
+    def proximity_jacobian_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        return self._batch(2, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _single(kind, prim1, prim2, pdip_tol, ctx):
+    if not isinstance(prim1, AbstractPrimitive) or not isinstance(prim2, AbstractPrimitive):
+        raise TypeError("proximity expects two primitives")
+    if prim1.att_kind != prim2.att_kind:
+        raise TypeError("no method: both primitives must be quaternion (AbstractPrimitive) or both MRP (AbstractPrimitiveMRP)")
+    ctx = ctx or default_context()
+    s1, s2 = ctx.add_shape(prim1), ctx.add_shape(prim2)
+    out = ctx._batch(kind, [s1], [s2], prim1.r, prim1.att, prim2.r, prim2.att, prim1.att_kind, pdip_tol)
+    st = int(out["status"][0])
+    if st == 1:
+        raise RuntimeError("pdip failed")
+    if st != 0:
+        raise ArithmeticError("numerical breakdown in the conic solver")
+    return out
+
+
+def proximity(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
+    out = _single(0, prim1, prim2, pdip_tol, ctx)
+    return float(out["alpha"][0]), out["x"][0].copy()
+
+
+def proximity_gradient(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
+    out = _single(1, prim1, prim2, pdip_tol, ctx)
+    return float(out["alpha"][0]), out["grad"][0].copy()
+
+
+def proximity_jacobian(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
+    out = _single(2, prim1, prim2, pdip_tol, ctx)
+    return float(out["alpha"][0]), out["x"][0].copy(), out["J"][0].copy()

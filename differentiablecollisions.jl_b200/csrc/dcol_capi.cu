@@ -1,0 +1,535 @@
+// Host side of libdcol_b200.so: context, shape-table upload, class-pair binning
+// (device counting sort), kernel dispatch over streams, host<->device staging.
+// Entry points are declared in include/dcol_b200.h.
+#include "../../include/dcol_b200.h"
+#include "dcol_common.cuh"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace dcol {
+typedef void (*SolveFn)(QueryParams, int, int);
+SolveFn get_solve_kernel(int c1, int c2);   // dcol_kernels_*.cu
+SolveFn get_deriv_kernel(int c1, int c2);   // dcol_kernels_*.cu
+}
+using namespace dcol;
+
+namespace {
+
+constexpr int NSIDE = 8;            // side streams for concurrent class-pair bins
+constexpr int MAX_KEYS = 4096;      // counting-sort key space
+constexpr int MAX_SMEM = 227 * 1024;
+thread_local std::string g_create_err;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+  ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -2; } } while (0)
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct dcol_ctx {
+  int device = 0;
+  cudaStream_t own = nullptr, user = nullptr;
+  cudaStream_t side[NSIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {}, ev_k0 = nullptr, ev_k1 = nullptr;
+  std::string err;
+  // shape table
+  int n_shapes = 0;
+  std::vector<DevShape> h_shapes;
+  std::vector<int> key_cp;            // dense key -> class pair (c1*NCLS+c2)
+  int n_keys = 0; bool use_keymap = false;
+  int max_rows_cls[NCLS] = {};
+  DevBuf d_shapes, d_rows, d_cls, d_keymap;
+  // per-call scratch
+  DevBuf d_in, d_out, d_perm, d_hist, d_state;
+  std::vector<int> h_off;
+  int64_t launches = 0;
+  double last_ms = -1.0;
+  cudaStream_t stream() const { return user ? user : own; }
+};
+
+// ---------------------------------------------------------------------------
+// binning kernels: counting sort of pair indices by (class1, class2[, shape1, shape2])
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int pair_key(const int32_t* cls, const int32_t* keymap, int n_shapes, int s1, int s2) {
+  return keymap ? keymap[s1 * n_shapes + s2] : cls[s1] * NCLS + cls[s2];
+}
+
+__global__ void k_hist(const int32_t* __restrict__ shape1, const int32_t* __restrict__ shape2, int64_t n,
+                       const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap, int n_shapes, int n_keys,
+                       int* __restrict__ hist, int* __restrict__ bad) {
+  extern __shared__ int sh[];
+  for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s1 = shape1[i], s2 = shape2[i];
+    if ((unsigned)s1 >= (unsigned)n_shapes || (unsigned)s2 >= (unsigned)n_shapes) { atomicExch(bad, 1); continue; }
+    atomicAdd(&sh[pair_key(cls, keymap, n_shapes, s1, s2)], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_keys; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+
+// single block: exclusive scan of hist[0..n_keys) -> off[0..n_keys], cursor = off
+__global__ void k_scan(const int* __restrict__ hist, int n_keys, int* __restrict__ off, int* __restrict__ cursor) {
+  __shared__ int part[1024];
+  int per = (n_keys + blockDim.x - 1) / blockDim.x;
+  int b = threadIdx.x * per, e = min(b + per, n_keys);
+  int s = 0;
+  for (int k = b; k < e; k++) s += hist[k];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < blockDim.x; d <<= 1) {
+    int v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int k = b; k < e; k++) { off[k] = run; cursor[k] = run; run += hist[k]; }
+  if (threadIdx.x == blockDim.x - 1) off[n_keys] = part[threadIdx.x];
+}
+
+__global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __restrict__ shape2, int64_t n,
+                          const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap, int n_shapes, int n_keys,
+                          int* __restrict__ cursor, int32_t* __restrict__ perm) {
+  extern __shared__ int sh[];          // [0,n_keys) local counts, then [n_keys, 2 n_keys) global bases
+  int64_t chunk = (int64_t)blockDim.x * 8;
+  for (int64_t base = blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    int key[8], rank[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int64_t i = base + u * blockDim.x + threadIdx.x;
+      key[u] = -1;
+      if (i < n) {
+        int s1 = shape1[i], s2 = shape2[i];
+        if ((unsigned)s1 < (unsigned)n_shapes && (unsigned)s2 < (unsigned)n_shapes) {
+          key[u] = pair_key(cls, keymap, n_shapes, s1, s2);
+          rank[u] = atomicAdd(&sh[key[u]], 1);
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[n_keys + k] = sh[k] ? atomicAdd(&cursor[k], sh[k]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      int64_t i = base + u * blockDim.x + threadIdx.x;
+      if (key[u] >= 0) perm[sh[n_keys + key[u]] + rank[u]] = (int32_t)i;
+    }
+    __syncthreads();
+  }
+}
+
+// FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
+__global__ void k_dfma(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ---------------------------------------------------------------------------
+// shape table
+// ---------------------------------------------------------------------------
+static int type_to_cls(int type) {
+  switch (type) {
+    case T_POLYTOPE: return CLS_POLYTOPE;
+    case T_CAPSULE: case T_CYLINDER: return CLS_CAPCYL;
+    case T_CONE: return CLS_CONE;
+    case T_SPHERE: return CLS_SPHERE;
+    case T_ELLIPSOID: return CLS_ELL;
+    case T_POLYGON: return CLS_POLYGON;
+  }
+  return -1;
+}
+
+extern "C" {
+
+const char* dcol_version(void) { return "dcol_b200 0.1.0 (sm_100a, fp64)"; }
+
+int dcol_create(dcol_ctx** out, int device_id) {
+  if (!out) { g_create_err = "dcol_create: out is NULL"; return -1; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("dcol_create: no CUDA device available (") + cudaGetErrorString(e) +
+                   "); this library has no CPU fallback";
+    return -2;
+  }
+  if (device_id < 0 || device_id >= ndev) { g_create_err = "dcol_create: bad device id"; return -1; }
+  dcol_ctx* ctx = new dcol_ctx();
+  ctx->device = device_id;
+  auto fail = [&](const char* what, cudaError_t err) { g_create_err = std::string(what) + ": " + cudaGetErrorString(err); delete ctx; return -2; };
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess) return fail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (int i = 0; i < NSIDE; i++) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  }
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev_k1)) != cudaSuccess) return fail("cudaEventCreate", e);
+  *out = ctx;
+  return 0;
+}
+
+void dcol_destroy(dcol_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_state};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+  if (ctx->own) cudaStreamDestroy(ctx->own);
+  delete ctx;
+}
+
+const char* dcol_last_error(const dcol_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int dcol_set_stream(dcol_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return -1;
+  ctx->user = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int64_t dcol_launch_count(const dcol_ctx* ctx) { return ctx ? ctx->launches : 0; }
+double dcol_last_kernel_ms(const dcol_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
+
+int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int64_t* param_off, const double* params, int64_t n_params) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  if (n_shapes <= 0 || !type || !param_off || !params) { ctx->err = "dcol_set_shapes: bad arguments"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  std::vector<DevShape> hs(n_shapes);
+  std::vector<double> rows;
+  std::vector<int32_t> cls(n_shapes);
+  for (int c = 0; c < NCLS; c++) ctx->max_rows_cls[c] = 0;
+  for (int i = 0; i < n_shapes; i++) {
+    DevShape& S = hs[i];
+    memset(&S, 0, sizeof(S));
+    const double* p = params + param_off[i];
+    int64_t avail = n_params - param_off[i];
+    int c = type_to_cls(type[i]);
+    if (c < 0 || param_off[i] < 0 || avail < 13) { ctx->err = "dcol_set_shapes: bad shape type or offset at shape " + std::to_string(i); return -1; }
+    S.cls = c; S.type = type[i]; S.rows_off = (int64_t)rows.size();
+    const double* tail = nullptr;
+    auto row = [&](std::initializer_list<double> v) { rows.insert(rows.end(), v); };
+    switch (type[i]) {
+      case T_POLYTOPE: {          // u_i = b_i*alpha - a_i . x~        (problem_matrices.jl:79-88)
+        int n = (int)p[0];
+        if (n < 1 || avail < 1 + 4 * (int64_t)n + 12) { ctx->err = "dcol_set_shapes: bad polytope at shape " + std::to_string(i); return -1; }
+        const double* A = p + 1; const double* b = p + 1 + 3 * n;
+        for (int k = 0; k < n; k++) row({-A[3 * k], -A[3 * k + 1], -A[3 * k + 2], b[k]});
+        S.n_ort = n; tail = p + 1 + 4 * n;
+      } break;
+      case T_CAPSULE: case T_CYLINDER: {   // :30-39, :146-160
+        double R = p[0], L = p[1];
+        row({0, 0, 0, L / 2, -1.0});       // alpha*L/2 - gamma
+        row({0, 0, 0, L / 2, 1.0});        // alpha*L/2 + gamma
+        S.n_ort = 2;
+        if (type[i] == T_CYLINDER) { row({1.0, 0, 0, L / 2, 0}); row({-1.0, 0, 0, L / 2, 0}); S.n_ort = 4; }
+        S.soc[0] = R; tail = p + 2;
+      } break;
+      case T_CONE: {                        // :56-66
+        double H = p[0], beta = p[1], tb = std::tan(beta);
+        row({-1.0, 0, 0, H / 4});           // alpha*H/4 - x~1
+        S.n_ort = 1; S.soc[0] = tb; S.soc[1] = tb * 3 * H / 4; tail = p + 2;
+      } break;
+      case T_SPHERE: S.n_ort = 0; S.soc[0] = p[0]; tail = p + 1; break;   // :99-113
+      case T_ELLIPSOID: S.n_ort = 0; for (int k = 0; k < 9; k++) S.soc[k] = p[k]; tail = p + 9; break;   // :172-182
+      case T_POLYGON: {                     // u_i = b_i*alpha - A_i . e   (:124-134)
+        int n = (int)p[0];
+        if (n < 1 || avail < 2 + 3 * (int64_t)n + 12) { ctx->err = "dcol_set_shapes: bad polygon at shape " + std::to_string(i); return -1; }
+        const double* A = p + 1; const double* b = p + 1 + 2 * n;
+        for (int k = 0; k < n; k++) row({0, 0, 0, b[k], -A[2 * k], -A[2 * k + 1]});
+        S.n_ort = n; S.soc[0] = p[1 + 3 * n]; tail = p + 2 + 3 * n;
+      } break;
+    }
+    for (int k = 0; k < 3; k++) S.r_off[k] = tail[k];
+    for (int k = 0; k < 9; k++) S.Q_off[k] = tail[3 + k];
+    bool ident = true;
+    for (int k = 0; k < 3; k++) ident = ident && tail[k] == 0.0;
+    for (int k = 0; k < 9; k++) ident = ident && tail[3 + k] == ((k % 4 == 0) ? 1.0 : 0.0);
+    S.has_offset = ident ? 0 : 1;
+    cls[i] = c;
+    ctx->max_rows_cls[c] = std::max(ctx->max_rows_cls[c], S.n_ort);
+  }
+  if (rows.empty()) rows.push_back(0.0);
+  // dense sort keys ordered by (class1, class2, shape1, shape2) when the table is small enough
+  ctx->use_keymap = (int64_t)n_shapes * n_shapes <= MAX_KEYS;
+  std::vector<int32_t> keymap;
+  ctx->key_cp.clear();
+  if (ctx->use_keymap) {
+    std::vector<std::pair<int, int>> order;
+    for (int a = 0; a < n_shapes; a++) for (int b = 0; b < n_shapes; b++) order.push_back({a, b});
+    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& u, const std::pair<int, int>& v) {
+      return cls[u.first] * NCLS + cls[u.second] < cls[v.first] * NCLS + cls[v.second]; });
+    keymap.resize((size_t)n_shapes * n_shapes);
+    for (size_t k = 0; k < order.size(); k++) {
+      keymap[(size_t)order[k].first * n_shapes + order[k].second] = (int32_t)k;
+      ctx->key_cp.push_back(cls[order[k].first] * NCLS + cls[order[k].second]);
+    }
+    ctx->n_keys = (int)order.size();
+  } else {
+    ctx->n_keys = NCLS * NCLS;
+    for (int k = 0; k < ctx->n_keys; k++) ctx->key_cp.push_back(k);
+  }
+  CK(ctx->d_shapes.need(sizeof(DevShape) * n_shapes));
+  CK(ctx->d_rows.need(sizeof(double) * rows.size()));
+  CK(ctx->d_cls.need(sizeof(int32_t) * n_shapes));
+  CK(cudaMemcpy(ctx->d_shapes.p, hs.data(), sizeof(DevShape) * n_shapes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_rows.p, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_cls.p, cls.data(), sizeof(int32_t) * n_shapes, cudaMemcpyHostToDevice));
+  if (ctx->use_keymap) {
+    CK(ctx->d_keymap.need(sizeof(int32_t) * keymap.size()));
+    CK(cudaMemcpy(ctx->d_keymap.p, keymap.data(), sizeof(int32_t) * keymap.size(), cudaMemcpyHostToDevice));
+  }
+  ctx->h_shapes = hs;
+  ctx->n_shapes = n_shapes;
+  return 0;
+}
+
+double dcol_measure_fp64_tflops(dcol_ctx* ctx) {
+  if (!ctx) return -1.0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return -1.0;
+  int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+  cudaStream_t s = ctx->stream();
+  k_dfma<<<blocks, threads, 0, s>>>(d, 2000, 1.0000001, 1e-9);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(ctx->ev_k0, s);
+    k_dfma<<<blocks, threads, 0, s>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(ctx->ev_k1, s);
+    cudaEventSynchronize(ctx->ev_k1);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1);
+    best = std::min(best, ms);
+  }
+  ctx->launches += 4;
+  cudaFree(d);
+  double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// query driver
+// ---------------------------------------------------------------------------
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                     const double* r1, const double* att1, const double* r2, const double* att2,
+                     int att_kind, double pdip_tol, int mem,
+                     double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  ctx->last_ms = -1.0;
+  if (ctx->n_shapes == 0) { ctx->err = "dcol: shape table not set (call dcol_set_shapes first)"; return -1; }
+  if (n < 0 || n > 0x7fffffff) { ctx->err = "dcol: n out of range"; return -1; }
+  if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { ctx->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
+  if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
+  if (n == 0) return 0;
+  if (!shape1 || !shape2 || !r1 || !att1 || !r2 || !att2 || !alpha) { ctx->err = "dcol: NULL input/output pointer"; return -1; }
+  if (query == Q_PROX && !x) { ctx->err = "dcol_proximity: x is NULL"; return -1; }
+  if (query != Q_PROX && !deriv) { ctx->err = "dcol: derivative output is NULL"; return -1; }
+  if (query == Q_JAC && !x) { ctx->err = "dcol_proximity_jacobian: x is NULL"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t S = ctx->stream();
+  const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3;
+  const int nt = 6 + 2 * na;
+  const size_t dsz = (query == Q_GRAD) ? (size_t)nt : (query == Q_JAC ? (size_t)4 * nt : 0);
+
+  QueryParams P;
+  memset(&P, 0, sizeof(P));
+  P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
+  P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query;
+
+  // ---- stage inputs / outputs
+  size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
+  size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0, out_bytes = 0;
+  if (mem == DCOL_MEM_HOST) {
+    size_t b = 0;
+    o_s1 = b; b += align256(sizeof(int32_t) * n);
+    o_s2 = b; b += align256(sizeof(int32_t) * n);
+    o_r1 = b; b += align256(sizeof(double) * 3 * n);
+    o_a1 = b; b += align256(sizeof(double) * na * n);
+    o_r2 = b; b += align256(sizeof(double) * 3 * n);
+    o_a2 = b; b += align256(sizeof(double) * na * n);
+    CK(ctx->d_in.need(b));
+    char* di = (char*)ctx->d_in.p;
+    CK(cudaMemcpyAsync(di + o_s1, shape1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(di + o_s2, shape2, sizeof(int32_t) * n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(di + o_r1, r1, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(di + o_a1, att1, sizeof(double) * na * n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(di + o_r2, r2, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(di + o_a2, att2, sizeof(double) * na * n, cudaMemcpyHostToDevice, S));
+    P.shape1 = (const int32_t*)(di + o_s1); P.shape2 = (const int32_t*)(di + o_s2);
+    P.r1 = (const double*)(di + o_r1); P.att1 = (const double*)(di + o_a1);
+    P.r2 = (const double*)(di + o_r2); P.att2 = (const double*)(di + o_a2);
+    b = 0;
+    o_alpha = b; b += align256(sizeof(double) * n);
+    o_x = b; b += align256(sizeof(double) * 3 * n);
+    o_der = b; b += align256(sizeof(double) * dsz * n);
+    o_st = b; b += align256(sizeof(int32_t) * n);
+    o_it = b; b += align256(sizeof(int32_t) * n);
+    out_bytes = b;
+    CK(ctx->d_out.need(out_bytes));
+    char* dout = (char*)ctx->d_out.p;
+    P.alpha = (double*)(dout + o_alpha); P.x = (double*)(dout + o_x);
+    P.deriv = dsz ? (double*)(dout + o_der) : nullptr;
+    P.status = (int32_t*)(dout + o_st); P.iters = (int32_t*)(dout + o_it);
+  } else {
+    P.shape1 = shape1; P.shape2 = shape2; P.r1 = r1; P.att1 = att1; P.r2 = r2; P.att2 = att2;
+    P.alpha = alpha; P.x = x; P.deriv = deriv; P.status = status; P.iters = iters;
+  }
+
+  // ---- bin pairs by key (device counting sort)
+  const int nk = ctx->n_keys;
+  CK(ctx->d_perm.need(sizeof(int32_t) * n));
+  CK(ctx->d_hist.need(sizeof(int) * (3 * (size_t)nk + 8)));
+  int* d_hist = (int*)ctx->d_hist.p;
+  int* d_off = d_hist + nk;            // nk+1
+  int* d_cursor = d_off + nk + 1;      // nk
+  int* d_bad = d_cursor + nk;          // 1
+  CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * (3 * (size_t)nk + 8), S));
+  const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
+  {
+    int threads = 256;
+    int blocks = (int)std::min<int64_t>((n + threads * 8 - 1) / (threads * 8), 1184);
+    k_hist<<<blocks, threads, sizeof(int) * nk, S>>>(P.shape1, P.shape2, n, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
+    k_scan<<<1, 1024, 0, S>>>(d_hist, nk, d_off, d_cursor);
+    k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, S>>>(P.shape1, P.shape2, n, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, (int32_t*)ctx->d_perm.p);
+    ctx->launches += 3;
+  }
+  ctx->h_off.resize(nk + 2);
+  CK(cudaMemcpyAsync(ctx->h_off.data(), d_off, sizeof(int) * (nk + 1), cudaMemcpyDeviceToHost, S));
+  CK(cudaMemcpyAsync(ctx->h_off.data() + nk + 1, d_bad, sizeof(int), cudaMemcpyDeviceToHost, S));
+  CK(cudaStreamSynchronize(S));
+  if (ctx->h_off[nk + 1]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; return -1; }
+  P.perm = (const int32_t*)ctx->d_perm.p;
+
+  // class-pair ranges (keys are class-pair major)
+  struct Bin { int c1, c2, begin, count, rows_cap, stride; };
+  std::vector<Bin> bins;
+  {
+    int k = 0;
+    while (k < nk) {
+      int cp = ctx->key_cp[k], k2 = k;
+      while (k2 < nk && ctx->key_cp[k2] == cp) k2++;
+      int begin = ctx->h_off[k], count = ctx->h_off[k2] - begin;
+      if (count > 0) {
+        Bin b; b.c1 = cp / NCLS; b.c2 = cp % NCLS; b.begin = begin; b.count = count;
+        b.rows_cap = ctx->max_rows_cls[b.c1] + ctx->max_rows_cls[b.c2];
+        b.stride = 4 + cls_ne(b.c1) + cls_ne(b.c2) + 2 * b.rows_cap + 2 * (cls_d(b.c1) + cls_d(b.c2));
+        bins.push_back(b);
+      }
+      k = k2;
+    }
+  }
+  // solver-state scratch for the derivative kernels
+  int max_stride = 0;
+  for (const Bin& b : bins) max_stride = std::max(max_stride, b.stride);
+  if (query != Q_PROX) {
+    CK(ctx->d_state.need(sizeof(double) * (size_t)max_stride * n));
+    P.state = (double*)ctx->d_state.p;
+    P.state_stride = max_stride;
+  }
+
+  // ---- launch one solver (+ derivative) kernel per non-empty class pair, spread over side streams
+  CK(cudaEventRecord(ctx->ev_k0, S));
+  CK(cudaEventRecord(ctx->ev_fork, S));
+  int nside = (int)std::min<size_t>(NSIDE, bins.size());
+  for (int i = 0; i < nside; i++) CK(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+  for (size_t bi = 0; bi < bins.size(); bi++) {
+    const Bin& b = bins[bi];
+    cudaStream_t st = ctx->side[bi % NSIDE];
+    int block = 64;
+    size_t smem = (size_t)std::max(b.rows_cap, 1) * NFIELD * sizeof(double) * block;
+    if (smem > (size_t)MAX_SMEM) { block = 32; smem /= 2; }
+    if (smem > (size_t)MAX_SMEM) { ctx->err = "dcol: too many polytope faces / polygon sides for one pair (shared memory)"; return -3; }
+    SolveFn fn = get_solve_kernel(b.c1, b.c2);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (b.count + block - 1) / block;
+    fn<<<grid, block, smem, st>>>(P, b.begin, b.count);
+    ctx->launches++;
+    if (query != Q_PROX) {
+      SolveFn dfn = get_deriv_kernel(b.c1, b.c2);
+      int dblock = 64;
+      int dgrid = (b.count + dblock - 1) / dblock;
+      dfn<<<dgrid, dblock, 0, st>>>(P, b.begin, b.count);
+      ctx->launches++;
+    }
+    CK(cudaGetLastError());
+  }
+  for (int i = 0; i < nside; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->side[i])); CK(cudaStreamWaitEvent(S, ctx->ev_join[i], 0)); }
+  CK(cudaEventRecord(ctx->ev_k1, S));
+
+  // ---- results back
+  if (mem == DCOL_MEM_HOST) {
+    char* dout = (char*)ctx->d_out.p;
+    CK(cudaMemcpyAsync(alpha, dout + o_alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, S));
+    if (x) CK(cudaMemcpyAsync(x, dout + o_x, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, S));
+    if (dsz) CK(cudaMemcpyAsync(deriv, dout + o_der, sizeof(double) * dsz * n, cudaMemcpyDeviceToHost, S));
+    if (status) CK(cudaMemcpyAsync(status, dout + o_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, S));
+    if (iters) CK(cudaMemcpyAsync(iters, dout + o_it, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, S));
+  }
+  CK(cudaStreamSynchronize(S));
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->last_ms = ms;
+  return 0;
+}
+
+extern "C" {
+
+int dcol_proximity(dcol_ctx* ctx, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                   const double* r1, const double* att1, const double* r2, const double* att2,
+                   int att_kind, double pdip_tol, int mem,
+                   double* alpha, double* x, int32_t* status, int32_t* iters) {
+  return run_query(ctx, Q_PROX, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem, alpha, x, nullptr, status, iters);
+}
+
+int dcol_proximity_gradient(dcol_ctx* ctx, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                            const double* r1, const double* att1, const double* r2, const double* att2,
+                            int att_kind, double pdip_tol, int mem,
+                            double* alpha, double* grad, int32_t* status, int32_t* iters) {
+  return run_query(ctx, Q_GRAD, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem, alpha, nullptr, grad, status, iters);
+}
+
+int dcol_proximity_jacobian(dcol_ctx* ctx, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                            const double* r1, const double* att1, const double* r2, const double* att2,
+                            int att_kind, double pdip_tol, int mem,
+                            double* alpha, double* x, double* J, int32_t* status, int32_t* iters) {
+  return run_query(ctx, Q_JAC, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem, alpha, x, J, status, iters);
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// Shared definitions for the dcol_b200 CUDA library (sm_100a, FP64).
+//
+// Formulation: every primitive's constraint block is
+//     u_k(y) = C_k * [x~_k ; alpha ; e_k],   x~_k = Q_k^T (x - r~_k)   (body frame)
+// with C_k a pose-independent constant matrix (rows c_i, small SOC block), so the
+// reference's  h - G*y  (src/problem_matrices.jl:30-191, src/combine_problem_matrices.jl:15-86)
+// equals u(y) with  G = -C*T, h = C*t^.  The solver works in primitive-1's body
+// frame (xi = x~_1), where only the relative pose R = Q_2^T Q_1, t = Q_2^T (r~_1 - r~_2)
+// enters:  x~_2 = R*xi + t.  The PDIP iterates (s, z) are invariant under this
+// affine change of variables, so results match the reference up to round-off.
+#pragma once
+#include <cstdint>
+
+namespace dcol {
+
+// reference shape types (include/dcol_b200.h)
+enum { T_POLYTOPE = 0, T_CAPSULE = 1, T_CYLINDER = 2, T_CONE = 3, T_SPHERE = 4, T_ELLIPSOID = 5, T_POLYGON = 6 };
+// structural classes the kernels are specialised on
+enum { CLS_POLYTOPE = 0, CLS_SPHERE = 1, CLS_CAPCYL = 2, CLS_POLYGON = 3, CLS_CONE = 4, CLS_ELL = 5, NCLS = 6 };
+enum { SOC_NONE = 0, SOC_BALL = 1, SOC_CONE = 2, SOC_ELL = 3 };
+enum { ST_OK = 0, ST_PDIP_FAILED = 1, ST_NUMERICAL = 2 };
+enum { Q_PROX = 0, Q_GRAD = 1, Q_JAC = 2 };
+
+template <int CLS> struct Cls;
+template <> struct Cls<CLS_POLYTOPE> { static constexpr int NE = 0, SOC = SOC_NONE, D = 0; };
+template <> struct Cls<CLS_SPHERE>   { static constexpr int NE = 0, SOC = SOC_BALL, D = 4; };
+template <> struct Cls<CLS_CAPCYL>   { static constexpr int NE = 1, SOC = SOC_BALL, D = 4; };
+template <> struct Cls<CLS_POLYGON>  { static constexpr int NE = 2, SOC = SOC_BALL, D = 4; };
+template <> struct Cls<CLS_CONE>     { static constexpr int NE = 0, SOC = SOC_CONE, D = 3; };
+template <> struct Cls<CLS_ELL>      { static constexpr int NE = 0, SOC = SOC_ELL, D = 4; };
+
+__host__ __device__ inline int cls_ne(int c) { return c == CLS_CAPCYL ? 1 : (c == CLS_POLYGON ? 2 : 0); }
+__host__ __device__ inline int cls_d(int c) { return c == CLS_POLYTOPE ? 0 : (c == CLS_CONE ? 3 : 4); }
+
+// Device shape record.  rows: n_ort x (4+NE) doubles, signs baked so that
+// u_i = c_i . [x~ ; alpha ; e].  soc[]: BALL {R}; CONE {tan(beta), tan(beta)*3H/4}; ELL {U row-major 3x3}.
+struct DevShape {
+  int32_t cls, n_ort, type, has_offset;
+  int64_t rows_off;
+  double soc[9];
+  double r_off[3];
+  double Q_off[9];
+};
+
+constexpr int MAX_ITERS = 50;   // static_solver2.jl:132
+constexpr int NFIELD = 5;       // per-row shared-memory fields
+enum { F_S = 0, F_Z = 1, F_IS = 2, F_RZ = 3, F_P = 4 };
+
+struct QueryParams {
+  const DevShape* shapes;
+  const double* rows;            // packed row constants
+  const int32_t* perm;           // sorted position -> pair index
+  const int32_t* shape1;
+  const int32_t* shape2;
+  const double* r1;  const double* att1;
+  const double* r2;  const double* att2;
+  int att_kind;                  // 0 quaternion (stride 4), 1 MRP (stride 3)
+  double pdip_tol;
+  double* alpha; double* x; int32_t* status; int32_t* iters;
+  double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major
+  double* state;                 // solver state scratch for the derivative kernel (may be NULL)
+  int state_stride;              // doubles per pair in the scratch (field-major within the bin)
+  int query;
+};
+
+}  // namespace dcol

@@ -1,0 +1,726 @@
+// Thread-per-pair primal-dual interior-point solver (FP64, sm_100a).
+//
+// Restates the algorithm of the reference's solve_socp
+// (src/solvers/coneqp/static_solver2.jl:106-191: Mehrotra predictor-corrector,
+// Nesterov-Todd scaling NT_scaling_chol_2.jl:95-127, line search to the cone
+// boundary :2-51, initial point :52-103, mu-only termination :143-146, 0.99 step
+// damping :172, 50 iteration cap :132) in a form designed for the GPU:
+//   * the pair's problem is never materialised as dense (G,h): each primitive is a
+//     constant block C_k acting on body-frame coordinates (dcol_common.cuh);
+//   * orthant rows use the unscaled Newton equations (d_i = z_i/s_i), which are
+//     algebraically identical to the NT-scaled ones for the nonnegative orthant;
+//   * SOC blocks use the closed form W^-1 = (1/eta) J Wbar J instead of a dense
+//     Cholesky of W (NT_scaling_chol_2.jl:126) — same operator, fewer flops;
+//   * per-row state (s, z, 1/s, rz, scratch) lives in shared memory, strided by
+//     thread so a warp touches consecutive 8-byte words (no bank conflicts);
+//     everything else (y, Gram matrix, SOC blocks, relative pose) is in registers.
+#pragma once
+#include "dcol_common.cuh"
+
+namespace dcol {
+
+// ---------------------------------------------------------------------------
+// attitude maps (src/problem_matrices.jl:9-27), templated so the derivative
+// kernel can push a dual number through them
+// ---------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ T t_sqrt(const T& a);
+template <> __device__ __forceinline__ double t_sqrt<double>(const double& a) { return sqrt(a); }
+
+template <class T>
+__device__ __forceinline__ void dcm_from_q(const T q[4], T Q[3][3]) {
+  T nrm = t_sqrt<T>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  T q4 = q[0] / nrm, q1 = q[1] / nrm, q2 = q[2] / nrm, q3 = q[3] / nrm;
+  Q[0][0] = 2.0 * q1 * q1 + 2.0 * q4 * q4 - 1.0; Q[0][1] = 2.0 * (q1 * q2 - q3 * q4);         Q[0][2] = 2.0 * (q1 * q3 + q2 * q4);
+  Q[1][0] = 2.0 * (q1 * q2 + q3 * q4);         Q[1][1] = 2.0 * q2 * q2 + 2.0 * q4 * q4 - 1.0; Q[1][2] = 2.0 * (q2 * q3 - q1 * q4);
+  Q[2][0] = 2.0 * (q1 * q3 - q2 * q4);         Q[2][1] = 2.0 * (q2 * q3 + q1 * q4);         Q[2][2] = 2.0 * q3 * q3 + 2.0 * q4 * q4 - 1.0;
+}
+template <class T>
+__device__ __forceinline__ void dcm_from_mrp(const T p[3], T Q[3][3]) {
+  T p1 = p[0], p2 = p[1], p3 = p[2];
+  T den1 = p1 * p1 + p2 * p2 + p3 * p3 + 1.0;
+  T den = den1 * den1;
+  T a = 4.0 * p1 * p1 + 4.0 * p2 * p2 + 4.0 * p3 * p3 - 4.0;
+  T id = 1.0 / den;
+  Q[0][0] = 1.0 - (8.0 * p2 * p2 + 8.0 * p3 * p3) * id; Q[0][1] = (8.0 * p1 * p2 + p3 * a) * id; Q[0][2] = (8.0 * p1 * p3 - p2 * a) * id;
+  Q[1][0] = (8.0 * p1 * p2 - p3 * a) * id; Q[1][1] = 1.0 - (8.0 * p1 * p1 + 8.0 * p3 * p3) * id; Q[1][2] = (8.0 * p2 * p3 + p1 * a) * id;
+  Q[2][0] = (8.0 * p1 * p3 + p2 * a) * id; Q[2][1] = (8.0 * p2 * p3 - p1 * a) * id; Q[2][2] = 1.0 - (8.0 * p1 * p1 + 8.0 * p2 * p2) * id;
+}
+
+struct Frame { double Q[3][3]; double r[3]; };
+
+// r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
+__device__ __forceinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F) {
+  double Qn[3][3];
+  if (att_kind == 0) { double q[4] = {att[0], att[1], att[2], att[3]}; dcm_from_q<double>(q, Qn); }
+  else { double p[3] = {att[0], att[1], att[2]}; dcm_from_mrp<double>(p, Qn); }
+  if (S->has_offset) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      F.r[i] = r[i] + Qn[i][0] * S->r_off[0] + Qn[i][1] * S->r_off[1] + Qn[i][2] * S->r_off[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) F.Q[i][j] = Qn[i][0] * S->Q_off[j] + Qn[i][1] * S->Q_off[3 + j] + Qn[i][2] * S->Q_off[6 + j];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { F.r[i] = r[i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) F.Q[i][j] = Qn[i][j]; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory row store: field f of row i of this thread
+// ---------------------------------------------------------------------------
+struct RowStore {
+  double* base; int stride;   // base = smem + threadIdx.x ; stride = blockDim.x
+  __device__ __forceinline__ double& operator()(int f, int i) const { return base[(i * NFIELD + f) * stride]; }
+};
+
+// ---------------------------------------------------------------------------
+// small dense helpers (upper-triangular storage in full arrays; fully unrolled)
+// ---------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ bool chol_upper(double (&M)[N][N], double (&id)[N]) {   // M = U'U in place, id = 1/diag(U)
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    double d = M[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= M[k][j] * M[k][j];
+    ok = ok && (d > 0.0);
+    double inv = rsqrt(d);
+    id[j] = inv;
+    M[j][j] = d * inv;
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      double a = M[j][i];
+#pragma unroll
+      for (int k = 0; k < j; k++) a -= M[k][j] * M[k][i];
+      M[j][i] = a * inv;
+    }
+  }
+  return ok;
+}
+template <int N>
+__device__ __forceinline__ void chol_solve(const double (&U)[N][N], const double (&id)[N], const double (&b)[N], double (&x)[N]) {
+  double y[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { double a = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) a -= U[k][i] * y[k];
+    y[i] = a * id[i]; }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) { double a = y[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) a -= U[i][k] * x[k];
+    x[i] = a * id[i]; }
+}
+
+// ---------------------------------------------------------------------------
+// class-specific SOC block structure  u_s = Cs * yh   (yh = [x~; alpha; e])
+//   BALL<NE>: [R*alpha ; x~ - B~ e]            (capsule :30-39, cylinder :146-160, sphere :99-113, polygon :124-134)
+//   CONE    : [tb*x~1 + k*alpha ; x~2 ; x~3]   (cone :56-66, k = tb*3H/4)
+//   ELL     : [alpha ; U x~]                   (ellipsoid :172-182)
+// ---------------------------------------------------------------------------
+template <int CLS, int NV, int D>
+__device__ __forceinline__ void soc_apply(const double* sc, const double (&yh)[NV], double (&u)[D]) {
+  constexpr int SOC = Cls<CLS>::SOC, NE = Cls<CLS>::NE;
+  if constexpr (SOC == SOC_BALL) {
+    u[0] = sc[0] * yh[3];
+    u[1] = yh[0]; u[2] = yh[1]; u[3] = yh[2];
+    if constexpr (NE >= 1) u[1] -= yh[4];
+    if constexpr (NE == 2) u[2] -= yh[5];
+  } else if constexpr (SOC == SOC_CONE) {
+    u[0] = sc[0] * yh[0] + sc[1] * yh[3]; u[1] = yh[1]; u[2] = yh[2];
+  } else if constexpr (SOC == SOC_ELL) {
+    u[0] = yh[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[1 + i] = sc[3 * i] * yh[0] + sc[3 * i + 1] * yh[1] + sc[3 * i + 2] * yh[2];
+  }
+}
+// g += Cs' v
+template <int CLS, int NV, int D>
+__device__ __forceinline__ void soc_applyT(const double* sc, const double (&v)[D], double (&g)[NV]) {
+  constexpr int SOC = Cls<CLS>::SOC, NE = Cls<CLS>::NE;
+  if constexpr (SOC == SOC_BALL) {
+    g[0] += v[1]; g[1] += v[2]; g[2] += v[3]; g[3] += sc[0] * v[0];
+    if constexpr (NE >= 1) g[4] -= v[1];
+    if constexpr (NE == 2) g[5] -= v[2];
+  } else if constexpr (SOC == SOC_CONE) {
+    g[0] += sc[0] * v[0]; g[1] += v[1]; g[2] += v[2]; g[3] += sc[1] * v[0];
+  } else if constexpr (SOC == SOC_ELL) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) g[a] += sc[a] * v[1] + sc[3 + a] * v[2] + sc[6 + a] * v[3];
+    g[3] += v[0];
+  }
+}
+// N(upper) += scale * Cs' * B * Cs for a symmetric DxD matrix B (full storage)
+template <int CLS, int NV, int D>
+__device__ __forceinline__ void soc_gram(const double* sc, const double (&B)[D][D], double scale, double (&N)[NV][NV]) {
+  constexpr int SOC = Cls<CLS>::SOC, NE = Cls<CLS>::NE;
+  if constexpr (SOC == SOC_BALL) {
+    const double R = sc[0], sR = scale * R;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = i; j < 3; j++) N[i][j] += scale * B[i + 1][j + 1];
+      N[i][3] += sR * B[i + 1][0];
+      if constexpr (NE >= 1) N[i][4] -= scale * B[i + 1][1];
+      if constexpr (NE == 2) N[i][5] -= scale * B[i + 1][2];
+    }
+    N[3][3] += sR * R * B[0][0];
+    if constexpr (NE >= 1) { N[3][4] -= sR * B[0][1]; N[4][4] += scale * B[1][1]; }
+    if constexpr (NE == 2) { N[3][5] -= sR * B[0][2]; N[4][5] += scale * B[1][2]; N[5][5] += scale * B[2][2]; }
+  } else if constexpr (SOC == SOC_CONE) {
+    const double E[3] = {sc[0], 1.0, 1.0};
+    const double k = sc[1];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = i; j < 3; j++) N[i][j] += scale * E[i] * E[j] * B[i][j];
+      N[i][3] += scale * k * E[i] * B[i][0];
+    }
+    N[3][3] += scale * k * k * B[0][0];
+  } else if constexpr (SOC == SOC_ELL) {
+    double tmp[3][3];   // Bvv * U
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) tmp[i][b] = B[1 + i][1] * sc[b] + B[1 + i][2] * sc[3 + b] + B[1 + i][3] * sc[6 + b];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+      for (int b = a; b < 3; b++) N[a][b] += scale * (sc[a] * tmp[0][b] + sc[3 + a] * tmp[1][b] + sc[6 + a] * tmp[2][b]);
+      N[a][3] += scale * (sc[a] * B[1][0] + sc[3 + a] * B[2][0] + sc[6 + a] * B[3][0]);
+    }
+    N[3][3] += scale * B[0][0];
+  }
+}
+
+// reference SOC line search (static_solver2.jl:12-26); nu = J(y), sn = sqrt(nu)
+template <int D>
+__device__ __forceinline__ double soc_linesearch(const double (&y)[D], const double (&dl)[D], double nu, double sn) {
+  double zeta = y[0] * dl[0];
+#pragma unroll
+  for (int i = 1; i < D; i++) zeta -= y[i] * dl[i];
+  double isn = 1.0 / sn, inu = 1.0 / nu;
+  double rho0 = zeta * inu;
+  double f = ((zeta * isn) + dl[0]) / (y[0] * isn + 1.0);
+  double nr = 0.0;
+#pragma unroll
+  for (int i = 1; i < D; i++) { double r = dl[i] * isn - f * (y[i] * inu); nr += r * r; }
+  nr = sqrt(nr);
+  return (nr > rho0) ? fmin(1.0, 1.0 / (nr - rho0)) : 1.0;
+}
+
+// ---------------------------------------------------------------------------
+// per-primitive solver state
+// ---------------------------------------------------------------------------
+template <int CLS>
+struct Prim {
+  static constexpr int NE = Cls<CLS>::NE, NV = 4 + Cls<CLS>::NE, D = Cls<CLS>::D, DD = (Cls<CLS>::D > 0 ? Cls<CLS>::D : 1);
+  const double* rows; int n; int row0;
+  double sc[9];
+  double s[DD], z[DD];                 // SOC block iterates
+  double V[DD][DD], Vsq[DD][DD];       // Wbar^-1 and Wbar^-2
+  double ie, ie2, Js, Jz, sJs, sJz;    // 1/eta, 1/eta^2, J(s), J(z) and roots
+  double lam[DD], rz[DD], v[DD], wc[DD];
+
+  __device__ __forceinline__ void load(const DevShape* S, const double* rows_base, int row0_) {
+    n = S->n_ort; rows = rows_base + S->rows_off; row0 = row0_;
+    constexpr int SOC = Cls<CLS>::SOC;
+    if constexpr (SOC == SOC_BALL) sc[0] = S->soc[0];
+    if constexpr (SOC == SOC_CONE) { sc[0] = S->soc[0]; sc[1] = S->soc[1]; }
+    if constexpr (SOC == SOC_ELL) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) sc[i] = S->soc[i]; }
+  }
+
+  // ---- initial point (static_solver2.jl:86-103): unweighted Gram N = C'C and g = C' u(yh0)
+  __device__ __forceinline__ void init_gram(const double (&yh0)[NV], bool has_off, double (&N)[NV][NV], double (&g)[NV]) const {
+#pragma unroll
+    for (int a = 0; a < NV; a++) { g[a] = 0.0;
+#pragma unroll
+      for (int b = a; b < NV; b++) N[a][b] = 0.0; }
+    for (int i = 0; i < n; i++) {
+      double c[NV];
+#pragma unroll
+      for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
+      double u = 0.0;
+      if (has_off) {
+#pragma unroll
+        for (int a = 0; a < NV; a++) u += c[a] * yh0[a]; }
+#pragma unroll
+      for (int a = 0; a < NV; a++) { g[a] += u * c[a];
+#pragma unroll
+        for (int b = a; b < NV; b++) N[a][b] += c[a] * c[b]; }
+    }
+    if constexpr (D > 0) {
+      double I[D][D];
+#pragma unroll
+      for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j < D; j++) I[i][j] = (i == j) ? 1.0 : 0.0;
+      soc_gram<CLS, NV, D>(sc, I, 1.0, N);
+      if (has_off) { double u[D]; soc_apply<CLS, NV, D>(sc, yh0, u); soc_applyT<CLS, NV, D>(sc, u, g); }
+    }
+  }
+  // s~ = -u(yh), z~ = C*dh ; returns the bring2cone violations (static_solver2.jl:52-85)
+  __device__ __forceinline__ void init_rows(const RowStore& rs, const double (&yh)[NV], const double (&dh)[NV],
+                                            double& min_s, double& min_z, double& a_s, double& a_z) {
+    for (int i = 0; i < n; i++) {
+      double us = 0.0, uz = 0.0;
+#pragma unroll
+      for (int a = 0; a < NV; a++) { double c = __ldg(rows + i * NV + a); us += c * yh[a]; uz += c * dh[a]; }
+      rs(F_S, row0 + i) = -us; rs(F_Z, row0 + i) = uz;
+      min_s = fmin(min_s, -us); min_z = fmin(min_z, uz);
+    }
+    if constexpr (D > 0) {
+      double u[D];
+      soc_apply<CLS, NV, D>(sc, yh, u);
+      double ns = 0.0, nz = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) s[i] = -u[i];
+      soc_apply<CLS, NV, D>(sc, dh, z);
+#pragma unroll
+      for (int i = 1; i < D; i++) { ns += s[i] * s[i]; nz += z[i] * z[i]; }
+      double res_s = s[0] - sqrt(ns), res_z = z[0] - sqrt(nz);
+      if (res_s <= 0.0) a_s = fmax(a_s, -res_s);
+      if (res_z <= 0.0) a_z = fmax(a_z, -res_z);
+    }
+  }
+  __device__ __forceinline__ double init_shift(const RowStore& rs, double sh_s, double sh_z) {   // + (1+a)*e ; returns s.z
+    double sz = 0.0;
+    for (int i = 0; i < n; i++) {
+      double a = rs(F_S, row0 + i) + sh_s, b = rs(F_Z, row0 + i) + sh_z;
+      rs(F_S, row0 + i) = a; rs(F_Z, row0 + i) = b; sz += a * b;
+    }
+    if constexpr (D > 0) { s[0] += sh_s; z[0] += sh_z;
+#pragma unroll
+      for (int i = 0; i < D; i++) sz += s[i] * z[i]; }
+    return sz;
+  }
+
+  // ---- pass A: residual rz = s - u(yh), scalings, N = C' W^-2 C, g = C' W^-2 rz
+  __device__ __forceinline__ bool passA(const RowStore& rs, const double (&yh)[NV], double (&N)[NV][NV], double (&g)[NV]) {
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < NV; a++) { g[a] = 0.0;
+#pragma unroll
+      for (int b = a; b < NV; b++) N[a][b] = 0.0; }
+    for (int i = 0; i < n; i++) {
+      double c[NV];
+#pragma unroll
+      for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
+      double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i);
+      double u = 0.0;
+#pragma unroll
+      for (int a = 0; a < NV; a++) u += c[a] * yh[a];
+      double r = si - u;
+      double is = 1.0 / si;
+      double d = zi * is;
+      double dr = d * r;
+#pragma unroll
+      for (int a = 0; a < NV; a++) {
+        double dc = d * c[a];
+        g[a] += dr * c[a];
+#pragma unroll
+        for (int b = a; b < NV; b++) N[a][b] += dc * c[b];
+      }
+      rs(F_IS, row0 + i) = is; rs(F_RZ, row0 + i) = r;
+    }
+    if constexpr (D > 0) {
+      double u[D];
+      soc_apply<CLS, NV, D>(sc, yh, u);
+      Js = s[0] * s[0]; Jz = z[0] * z[0];
+      double dot = s[0] * z[0];
+#pragma unroll
+      for (int i = 0; i < D; i++) rz[i] = s[i] - u[i];
+#pragma unroll
+      for (int i = 1; i < D; i++) { Js -= s[i] * s[i]; Jz -= z[i] * z[i]; dot += s[i] * z[i]; }
+      ok = ok && (Js > 0.0) && (Jz > 0.0);
+      // Nesterov-Todd scaling (NT_scaling_chol_2.jl:95-112)
+      double irs = rsqrt(Js), irz = rsqrt(Jz);
+      sJs = Js * irs; sJz = Jz * irz;
+      double gam = sqrt(0.5 * (1.0 + dot * irs * irz));
+      double kk = 0.5 / gam;
+      double wb[D];
+      wb[0] = kk * (s[0] * irs + z[0] * irz);
+#pragma unroll
+      for (int i = 1; i < D; i++) wb[i] = kk * (s[i] * irs - z[i] * irz);
+      double bb = 1.0 / (wb[0] + 1.0);
+      double eta = sqrt(sJs * irz);          // (J(s)/J(z))^(1/4)
+      ie = sqrt(sJz * irs); ie2 = ie * ie;    // 1/eta
+      // lambda = W z = eta * Wbar z
+      double wz = 0.0;
+#pragma unroll
+      for (int i = 1; i < D; i++) wz += wb[i] * z[i];
+      lam[0] = eta * (wb[0] * z[0] + wz);
+#pragma unroll
+      for (int i = 1; i < D; i++) lam[i] = eta * (wb[i] * z[0] + z[i] + bb * wz * wb[i]);
+      // V = Wbar^-1 = J Wbar J
+      V[0][0] = wb[0];
+#pragma unroll
+      for (int i = 1; i < D; i++) { V[0][i] = -wb[i]; V[i][0] = -wb[i];
+#pragma unroll
+        for (int j = 1; j < D; j++) V[i][j] = ((i == j) ? 1.0 : 0.0) + bb * wb[i] * wb[j]; }
+      // Vsq = V*V (product form keeps the Gram block PSD to round-off)
+#pragma unroll
+      for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = i; j < D; j++) { double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) a += V[i][k] * V[k][j];
+          Vsq[i][j] = a; Vsq[j][i] = a; }
+      double t2[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a += Vsq[i][k] * rz[k];
+        t2[i] = ie2 * a; }
+      soc_applyT<CLS, NV, D>(sc, t2, g);
+      soc_gram<CLS, NV, D>(sc, Vsq, ie2, N);
+    }
+    return ok;
+  }
+
+  // ---- pass B: affine direction; step-to-boundary ratios; sums for rho; Mehrotra correction term
+  __device__ __forceinline__ void passB(const RowStore& rs, const double (&dyh)[NV], double& a_s, double& a_z, double& dot1, double& dot2) {
+    for (int i = 0; i < n; i++) {
+      double cd = 0.0;
+#pragma unroll
+      for (int a = 0; a < NV; a++) cd += __ldg(rows + i * NV + a) * dyh[a];
+      double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), is = rs(F_IS, row0 + i), r = rs(F_RZ, row0 + i);
+      double t = r - cd;
+      double dsa = -t, dza = zi * is * t - zi;
+      if (dsa < 0.0) a_s = fmin(a_s, -si / dsa);
+      if (dza < 0.0) a_z = fmin(a_z, -zi / dza);
+      double p = dsa * dza;
+      rs(F_P, row0 + i) = p;
+      dot1 += si * dza + zi * dsa; dot2 += p;
+    }
+    if constexpr (D > 0) {
+      double cd[D], t[D], dsa[D], dza[D];
+      soc_apply<CLS, NV, D>(sc, dyh, cd);
+#pragma unroll
+      for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; dsa[i] = -t[i]; }
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) { a += V[i][k] * t[k]; b += Vsq[i][k] * t[k]; }
+        v[i] = ie * a; dza[i] = ie2 * b - z[i]; }
+      a_s = fmin(a_s, soc_linesearch<D>(s, dsa, Js, sJs));
+      a_z = fmin(a_z, soc_linesearch<D>(z, dza, Jz, sJz));
+#pragma unroll
+      for (int i = 0; i < D; i++) { dot1 += s[i] * dza[i] + z[i] * dsa[i]; dot2 += dsa[i] * dza[i]; }
+      // -(W^-1 dsa) o (W dza) = v o (v - lambda)   (static_solver2.jl:164)
+      double c0 = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) c0 += v[i] * (v[i] - lam[i]);
+      wc[0] = c0;
+#pragma unroll
+      for (int i = 1; i < D; i++) wc[i] = v[0] * (v[i] - lam[i]) + (v[0] - lam[0]) * v[i];
+    }
+  }
+
+  // ---- pass C: corrector right-hand side  g2 = C' [ (sigma*mu - p)/s | W^-1 (lambda \ corr) ]
+  __device__ __forceinline__ void passC(const RowStore& rs, double sigmu, double (&g2)[NV]) {
+#pragma unroll
+    for (int a = 0; a < NV; a++) g2[a] = 0.0;
+    for (int i = 0; i < n; i++) {
+      double q = (sigmu - rs(F_P, row0 + i)) * rs(F_IS, row0 + i);
+#pragma unroll
+      for (int a = 0; a < NV; a++) g2[a] += q * __ldg(rows + i * NV + a);
+    }
+    if constexpr (D > 0) {
+      wc[0] += sigmu;
+      // kappa = lambda \ corr  (soc_utils.jl:52-67)
+      double rho = lam[0] * lam[0], nu = 0.0;
+#pragma unroll
+      for (int i = 1; i < D; i++) { rho -= lam[i] * lam[i]; nu += lam[i] * wc[i]; }
+      double irho = 1.0 / rho, il0 = 1.0 / lam[0];
+      double kap[D];
+      kap[0] = irho * (lam[0] * wc[0] - nu);
+#pragma unroll
+      for (int i = 1; i < D; i++) kap[i] = irho * ((nu * il0 - wc[0]) * lam[i] + (rho * il0) * wc[i]);
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a += V[i][k] * kap[k];
+        wc[i] = ie * a; }
+      soc_applyT<CLS, NV, D>(sc, wc, g2);
+    }
+  }
+
+  // ---- pass D: final direction and step-to-boundary ratios; directions parked in F_RZ/F_P (rows) and rz/v (SOC)
+  __device__ __forceinline__ void passD(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& a_s, double& a_z) {
+    for (int i = 0; i < n; i++) {
+      double cd = 0.0;
+#pragma unroll
+      for (int a = 0; a < NV; a++) cd += __ldg(rows + i * NV + a) * dyh[a];
+      double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), is = rs(F_IS, row0 + i), r = rs(F_RZ, row0 + i), p = rs(F_P, row0 + i);
+      double t = r - cd;
+      double ds = -t, dz = (zi * t + sigmu - p) * is - zi;
+      if (ds < 0.0) a_s = fmin(a_s, -si / ds);
+      if (dz < 0.0) a_z = fmin(a_z, -zi / dz);
+      rs(F_RZ, row0 + i) = ds; rs(F_P, row0 + i) = dz;
+    }
+    if constexpr (D > 0) {
+      double cd[D], t[D], ds[D], dz[D];
+      soc_apply<CLS, NV, D>(sc, dyh, cd);
+#pragma unroll
+      for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; ds[i] = -t[i]; }
+#pragma unroll
+      for (int i = 0; i < D; i++) { double b = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) b += Vsq[i][k] * t[k];
+        dz[i] = ie2 * b - z[i] + wc[i]; }
+      a_s = fmin(a_s, soc_linesearch<D>(s, ds, Js, sJs));
+      a_z = fmin(a_z, soc_linesearch<D>(z, dz, Jz, sJz));
+#pragma unroll
+      for (int i = 0; i < D; i++) { rz[i] = ds[i]; v[i] = dz[i]; }
+    }
+  }
+
+  // ---- pass E: take the step; returns the new s.z
+  __device__ __forceinline__ double passE(const RowStore& rs, double al) {
+    double sz = 0.0;
+    for (int i = 0; i < n; i++) {
+      double a = rs(F_S, row0 + i) + al * rs(F_RZ, row0 + i), b = rs(F_Z, row0 + i) + al * rs(F_P, row0 + i);
+      rs(F_S, row0 + i) = a; rs(F_Z, row0 + i) = b; sz += a * b;
+    }
+    if constexpr (D > 0) {
+#pragma unroll
+      for (int i = 0; i < D; i++) { s[i] += al * rz[i]; z[i] += al * v[i]; sz += s[i] * z[i]; }
+    }
+    return sz;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// pair-level assembly in primitive-1's body frame.  Pair variables
+// y = [xi(3), alpha, e1(NE1), e2(NE2)]  (column order of combine_problem_matrices.jl:57-84).
+// ---------------------------------------------------------------------------
+template <int NE1, int NE2>
+struct PairMap {
+  static constexpr int NX = 4 + NE1 + NE2, NV1 = 4 + NE1, NV2 = 4 + NE2;
+  __device__ static __forceinline__ constexpr int g2(int l) { return l < 4 ? l : 4 + NE1 + (l - 4); }   // prim-2 local -> pair index (l>=3)
+
+  // local vectors from the pair vector; with_t adds the frame offset t to prim 2
+  __device__ static __forceinline__ void to_local(const double (&y)[NX], const double (&R)[3][3], const double (&t)[3], bool with_t,
+                                                  double (&y1)[NV1], double (&y2)[NV2]) {
+#pragma unroll
+    for (int a = 0; a < NV1; a++) y1[a] = y[a];
+#pragma unroll
+    for (int a = 0; a < 3; a++) y2[a] = R[a][0] * y[0] + R[a][1] * y[1] + R[a][2] * y[2] + (with_t ? t[a] : 0.0);
+    y2[3] = y[3];
+#pragma unroll
+    for (int a = 4; a < NV2; a++) y2[a] = y[g2(a)];
+  }
+  // M(upper) = embed(N1) + T' N2 T ; b = embed(g1) + T' g2
+  __device__ static __forceinline__ void assemble(const double (&N1)[NV1][NV1], const double (&N2)[NV2][NV2], const double (&R)[3][3],
+                                                  double (&M)[NX][NX]) {
+#pragma unroll
+    for (int a = 0; a < NX; a++)
+#pragma unroll
+      for (int b = a; b < NX; b++) M[a][b] = (a < NV1 && b < NV1) ? N1[a][b] : 0.0;
+    double tmp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        double a0 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) a0 += ((c <= d) ? N2[c][d] : N2[d][c]) * R[d][b];
+        tmp[c][b] = a0;
+      }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+      for (int b = a; b < 3; b++) M[a][b] += R[0][a] * tmp[0][b] + R[1][a] * tmp[1][b] + R[2][a] * tmp[2][b];
+#pragma unroll
+      for (int l = 3; l < NV2; l++) M[a][g2(l)] += R[0][a] * N2[0][l] + R[1][a] * N2[1][l] + R[2][a] * N2[2][l];
+    }
+#pragma unroll
+    for (int l = 3; l < NV2; l++)
+#pragma unroll
+      for (int m = l; m < NV2; m++) M[g2(l)][g2(m)] += N2[l][m];
+  }
+  __device__ static __forceinline__ void assemble_vec(const double (&g1)[NV1], const double (&g2v)[NV2], const double (&R)[3][3], double (&b)[NX]) {
+#pragma unroll
+    for (int a = 0; a < NX; a++) b[a] = (a < NV1) ? g1[a] : 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) b[a] += R[0][a] * g2v[0] + R[1][a] * g2v[1] + R[2][a] * g2v[2];
+#pragma unroll
+    for (int l = 3; l < NV2; l++) b[g2(l)] += g2v[l];
+  }
+};
+
+// layout of the per-pair solver state handed to the derivative kernel
+// (field-major inside a bin: element f of sorted pair j lives at state[f*bin_count + j])
+//   [0,NX) y (frame 1) ; then rows: s[n1+n2], z[n1+n2] ; then soc1 s,z ; soc2 s,z
+template <int C1, int C2>
+__device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, int bin_begin, int bin_count, double* smem) {
+  using P1 = Prim<C1>; using P2 = Prim<C2>;
+  using PM = PairMap<P1::NE, P2::NE>;
+  constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
+
+  const int pair = p.perm[idx];
+  const DevShape* S1 = p.shapes + p.shape1[pair];
+  const DevShape* S2 = p.shapes + p.shape2[pair];
+  const int na = (p.att_kind == 0) ? 4 : 3;
+
+  RowStore rs{smem + threadIdx.x, (int)blockDim.x};
+  P1 A; P2 B;
+  A.load(S1, p.rows, 0);
+  B.load(S2, p.rows, A.n);
+
+  // relative pose
+  double R[3][3], t[3];
+  {
+    Frame F1, F2;
+    build_frame(S1, p.r1 + 3 * (int64_t)pair, p.att1 + na * (int64_t)pair, p.att_kind, F1);
+    build_frame(S2, p.r2 + 3 * (int64_t)pair, p.att2 + na * (int64_t)pair, p.att_kind, F2);
+    double dr[3] = {F1.r[0] - F2.r[0], F1.r[1] - F2.r[1], F1.r[2] - F2.r[2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      t[a] = F2.Q[0][a] * dr[0] + F2.Q[1][a] * dr[1] + F2.Q[2][a] * dr[2];
+#pragma unroll
+      for (int b = 0; b < 3; b++) R[a][b] = F2.Q[0][a] * F1.Q[0][b] + F2.Q[1][a] * F1.Q[1][b] + F2.Q[2][a] * F1.Q[2][b];
+    }
+  }
+
+  double y[NX];
+  double M[NX][NX], idg[NX];
+  double sz;
+  int status = ST_OK;
+  int cone_degree = A.n + B.n + (P1::D > 0 ? 1 : 0) + (P2::D > 0 ? 1 : 0);   // static_solver2.jl:124-130
+  const double inv_deg = 1.0 / (double)cone_degree;
+
+  // ---------------- initialize (static_solver2.jl:86-103) ----------------
+  {
+    double N1[NV1][NV1], g1[NV1], N2[NV2][NV2], g2[NV2];
+    double y1[NV1], y2[NV2];
+#pragma unroll
+    for (int a = 0; a < NX; a++) y[a] = 0.0;
+    PM::to_local(y, R, t, true, y1, y2);
+    A.init_gram(y1, false, N1, g1);
+    B.init_gram(y2, true, N2, g2);
+    PM::assemble(N1, N2, R, M);
+    double b0[NX], e4[NX], v2[NX];
+    PM::assemble_vec(g1, g2, R, b0);
+    bool ok = chol_upper<NX>(M, idg);
+#pragma unroll
+    for (int a = 0; a < NX; a++) { b0[a] = -b0[a]; e4[a] = (a == 3) ? 1.0 : 0.0; }
+    chol_solve<NX>(M, idg, b0, y);      // x^ = (G'G)\(G'h)
+    chol_solve<NX>(M, idg, e4, v2);     // z~ = G*((G'G)\(-c)) = C T v2
+    double d1[NV1], d2[NV2];
+    PM::to_local(y, R, t, true, y1, y2);
+    PM::to_local(v2, R, t, false, d1, d2);
+    double min_s = 1e300, min_z = 1e300, a_s = -1.0, a_z = -1.0;
+    double ms = 1e300, mz = 1e300;
+    A.init_rows(rs, y1, d1, ms, mz, a_s, a_z);
+    B.init_rows(rs, y2, d2, ms, mz, a_s, a_z);
+    min_s = ms; min_z = mz;
+    if (A.n + B.n > 0) {   // bring2cone :62-64 — orthant part first, then max with the SOC residuals
+      if (min_s <= 0.0) a_s = fmax(a_s, -min_s);
+      if (min_z <= 0.0) a_z = fmax(a_z, -min_z);
+    }
+    double sh_s = (a_s < 0.0) ? 0.0 : 1.0 + a_s, sh_z = (a_z < 0.0) ? 0.0 : 1.0 + a_z;
+    sz = A.init_shift(rs, sh_s, sh_z) + B.init_shift(rs, sh_s, sh_z);
+    if (!ok) status = ST_NUMERICAL;
+  }
+
+  // ---------------- main loop (static_solver2.jl:132-187) ----------------
+  int it = 0;
+  if (status == ST_OK) {
+    status = ST_PDIP_FAILED;
+    for (; it <= MAX_ITERS; it++) {
+      double mu = sz * inv_deg;
+      if (!(mu == mu)) { status = ST_NUMERICAL; break; }
+      if (mu < p.pdip_tol) { status = ST_OK; break; }
+      if (it == MAX_ITERS) break;
+      double rhs[NX], dy[NX];
+      double y1[NV1], y2[NV2];
+      bool ok;
+      {
+        double N1[NV1][NV1], g1[NV1], N2[NV2][NV2], g2[NV2];
+        PM::to_local(y, R, t, true, y1, y2);
+        ok = A.passA(rs, y1, N1, g1);
+        ok = B.passA(rs, y2, N2, g2) && ok;
+        PM::assemble(N1, N2, R, M);
+        PM::assemble_vec(g1, g2, R, rhs);
+      }
+      rhs[3] -= 1.0;                              // -c
+      ok = chol_upper<NX>(M, idg) && ok;
+      if (!ok) { status = ST_NUMERICAL; break; }
+      chol_solve<NX>(M, idg, rhs, dy);            // affine direction
+      double a_s = 1.0, a_z = 1.0, dot1 = 0.0, dot2 = 0.0;
+      PM::to_local(dy, R, t, false, y1, y2);
+      A.passB(rs, y1, a_s, a_z, dot1, dot2);
+      B.passB(rs, y2, a_s, a_z, dot1, dot2);
+      double aa = fmin(a_s, a_z);                 // :159
+      double rho = (sz + aa * (dot1 + aa * dot2)) / sz;
+      double sig = fmax(0.0, fmin(1.0, rho)); sig = sig * sig * sig;   // :161
+      double sigmu = sig * mu;
+      {
+        double g1[NV1], g2[NV2], rc[NX];
+        A.passC(rs, sigmu, g1);
+        B.passC(rs, sigmu, g2);
+        PM::assemble_vec(g1, g2, R, rc);
+#pragma unroll
+        for (int a = 0; a < NX; a++) rhs[a] += rc[a];
+      }
+      chol_solve<NX>(M, idg, rhs, dy);            // combined direction
+      a_s = 1.0; a_z = 1.0;
+      PM::to_local(dy, R, t, false, y1, y2);
+      A.passD(rs, y1, sigmu, a_s, a_z);
+      B.passD(rs, y2, sigmu, a_s, a_z);
+      double al = fmin(1.0, 0.99 * fmin(a_s, a_z));   // :172
+#pragma unroll
+      for (int a = 0; a < NX; a++) y[a] += al * dy[a];
+      sz = A.passE(rs, al) + B.passE(rs, al);
+    }
+  }
+
+  // ---------------- outputs ----------------
+  {
+    Frame F1;
+    build_frame(S1, p.r1 + 3 * (int64_t)pair, p.att1 + na * (int64_t)pair, p.att_kind, F1);
+    p.alpha[pair] = y[3];
+    if (p.x) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) p.x[3 * (int64_t)pair + a] = F1.r[a] + F1.Q[a][0] * y[0] + F1.Q[a][1] * y[1] + F1.Q[a][2] * y[2];
+    }
+    if (p.status) p.status[pair] = status;
+    if (p.iters) p.iters[pair] = it;
+  }
+  if (p.state) {
+    double* st = p.state + (int64_t)bin_begin * p.state_stride + (idx - bin_begin);
+    int f = 0;
+#pragma unroll
+    for (int a = 0; a < NX; a++) st[(int64_t)(f++) * bin_count] = y[a];
+    int nr = A.n + B.n;
+    for (int i = 0; i < nr; i++) { st[(int64_t)(f + i) * bin_count] = rs(F_S, i); st[(int64_t)(f + nr + i) * bin_count] = rs(F_Z, i); }
+    f += 2 * nr;
+    if constexpr (P1::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { st[(int64_t)(f + i) * bin_count] = A.s[i]; st[(int64_t)(f + P1::D + i) * bin_count] = A.z[i]; }
+      f += 2 * P1::D;
+    }
+    if constexpr (P2::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { st[(int64_t)(f + i) * bin_count] = B.s[i]; st[(int64_t)(f + P2::D + i) * bin_count] = B.z[i]; }
+    }
+  }
+}
+
+template <int C1, int C2>
+__global__ void solve_kernel(QueryParams p, int bin_begin, int bin_count) {
+  extern __shared__ double smem[];
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= bin_count) return;
+  solve_pair<C1, C2>(p, bin_begin + j, bin_begin, bin_count, smem);
+}
+
+}  // namespace dcol

@@ -1,0 +1,118 @@
+/* dcol_b200 — C ABI of the B200-native batched DCOL proximity library.
+ *
+ * The reference (kevin-tracy/DifferentiableCollisions.jl v0.1.5) is pure Julia and has
+ * no FFI boundary; this header is the boundary a Julia `ccall` (or Python ctypes)
+ * wrapper binds to replace the reference's call surface:
+ *
+ *   dcol_proximity           <-> dc.proximity            src/proximity.jl:3-14   (quat), :15-26   (MRP)
+ *   dcol_proximity_gradient  <-> dc.proximity_gradient   src/proximity_gradient.jl:80-95 (quat), :96-111 (MRP)
+ *   dcol_proximity_jacobian  <-> dc.proximity_jacobian   src/proximity.jl:168-181 (quat), :182-195 (MRP)
+ *   dcol_set_shapes          <-> the geometry fields of the 14 primitive structs
+ *                                src/primitives.jl:4-96, src/primitives_mrp.jl:2-96
+ *
+ * Each call is the batched form: arrays of n pairs.  The reference's single-pair call
+ * is a batch of 1.  All arithmetic is FP64 on the GPU; there is no CPU fallback.
+ *
+ * Layouts (all caller-allocated, contiguous):
+ *   shape1, shape2 : int32[n]   indices into the shape table
+ *   r1, r2         : f64[n*3]   positions  (prim.r)
+ *   att1, att2     : f64[n*4]   quaternions, scalar first, need not be normalised (att_kind 0; prim.q)
+ *                    f64[n*3]   modified Rodrigues parameters                       (att_kind 1; prim.p)
+ *   alpha          : f64[n]     minimum uniform scaling; collision <=> alpha <= 1
+ *   x              : f64[n*3]   intersection / witness point in the world frame
+ *   grad           : f64[n*nt]  d alpha / d[r1; att1; r2; att2],  nt = 14 (quat) or 12 (MRP)
+ *   J              : f64[n*4*nt] per pair a 4 x nt matrix, COLUMN-major (Julia SMatrix layout),
+ *                    rows (x1, x2, x3, alpha), columns [r1; att1; r2; att2]  (src/proximity.jl:83-86,101)
+ *   status         : int32[n]   0 ok, 1 "pdip failed" (no convergence in 50 iterations,
+ *                    static_solver2.jl:188), 2 numerical breakdown (non-PD / NaN)      [may be NULL]
+ *   iters          : int32[n]   interior-point steps taken                               [may be NULL]
+ *
+ * mem: DCOL_MEM_HOST   — all pointers are host memory; the library stages H2D/D2H itself.
+ *      DCOL_MEM_DEVICE — all pointers are device memory on the context's GPU; nothing is copied.
+ *
+ * Return value: 0 on success, <0 on API/CUDA error (see dcol_last_error).  Per-pair solver
+ * failures are reported through `status`, never through the return value.  No exceptions cross
+ * the ABI.  A context is NOT thread-safe; use one context per host thread / per GPU.
+ */
+#ifndef DCOL_B200_H
+#define DCOL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCOL_ATT_QUAT 0
+#define DCOL_ATT_MRP  1
+#define DCOL_MEM_HOST   0
+#define DCOL_MEM_DEVICE 1
+
+/* shape types (reference struct names) */
+#define DCOL_POLYTOPE  0
+#define DCOL_CAPSULE   1
+#define DCOL_CYLINDER  2
+#define DCOL_CONE      3
+#define DCOL_SPHERE    4
+#define DCOL_ELLIPSOID 5
+#define DCOL_POLYGON   6
+
+#define DCOL_STATUS_OK          0
+#define DCOL_STATUS_PDIP_FAILED 1
+#define DCOL_STATUS_NUMERICAL   2
+
+typedef struct dcol_ctx dcol_ctx;
+
+/* Create / destroy a context bound to one CUDA device.  Owns streams, the device copy of the
+ * shape table and scratch buffers. */
+int  dcol_create(dcol_ctx** out, int device_id);
+void dcol_destroy(dcol_ctx* ctx);
+/* Context-owned, NUL-terminated description of the last error ("" if none). Valid for ctx == NULL
+ * for errors raised by dcol_create. */
+const char* dcol_last_error(const dcol_ctx* ctx);
+const char* dcol_version(void);
+
+/* Optional: run on a caller-provided CUDA stream (cudaStream_t passed as void*); NULL = the
+ * context's own stream.  Device-pointer calls are then ordered after work already enqueued on
+ * that stream and complete before the call returns. */
+int dcol_set_stream(dcol_ctx* ctx, void* cuda_stream);
+
+/* Immutable shape table, copied to the device.  params (f64) packed at param_off[i]:
+ *   polytope  {n, A row-major n x 3, b[n]}     A x~ <= alpha b          src/primitives.jl:4-14
+ *   capsule   {R, L}                                                    :16-26
+ *   cylinder  {R, L}                                                    :28-38
+ *   cone      {H, beta}                                                 :40-50
+ *   sphere    {R}                                                       :52-61
+ *   ellipsoid {U row-major 3 x 3} with U = cholesky(P).U                :76-96
+ *   polygon   {nh, A row-major nh x 2, b[nh], R}                        :63-74
+ * followed, for every shape, by r_offset[3] and Q_offset[9] (row-major). */
+int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int64_t* param_off,
+                    const double* params, int64_t n_params);
+
+int dcol_proximity(dcol_ctx* ctx, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                   const double* r1, const double* att1, const double* r2, const double* att2,
+                   int att_kind, double pdip_tol, int mem,
+                   double* alpha, double* x, int32_t* status, int32_t* iters);
+
+int dcol_proximity_gradient(dcol_ctx* ctx, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                            const double* r1, const double* att1, const double* r2, const double* att2,
+                            int att_kind, double pdip_tol, int mem,
+                            double* alpha, double* grad, int32_t* status, int32_t* iters);
+
+int dcol_proximity_jacobian(dcol_ctx* ctx, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                            const double* r1, const double* att1, const double* r2, const double* att2,
+                            int att_kind, double pdip_tol, int mem,
+                            double* alpha, double* x, double* J, int32_t* status, int32_t* iters);
+
+/* Instrumentation for bench.py / tests. */
+/* kernels launched by this context since creation (solver + derivative + binning kernels) */
+int64_t dcol_launch_count(const dcol_ctx* ctx);
+/* device time (ms) of the solver+derivative kernels of the last query call, measured with CUDA
+ * events on the launching streams; <0 if unavailable */
+double  dcol_last_kernel_ms(const dcol_ctx* ctx);
+/* measured FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark, ~50 ms) */
+double  dcol_measure_fp64_tflops(dcol_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCOL_B200_H */

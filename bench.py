@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the DCOL proximity hot path (BASELINE.json metric: pair-queries/sec).
+
+One "step" = one pass of the hot path over one batch of synthetic random-pose pairs:
+  headline  : BASELINE config 2 — proximity, all 7x7 primitive-type pairs, quaternion, 1M pairs per GPU
+  secondary : BASELINE config 3 — proximity_jacobian, mixed primitives, MRP, 2M pairs per GPU
+              (16M sharded over 8 GPUs = 2M per GPU; reported under "jacobian" in the same JSON line)
+Pairs are independent, so N GPUs run N index shards with no data-path collective ("scaling": "weak");
+torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the device time.
+
+  value : device-resident whole-call throughput (inputs already in HBM, results left in HBM),
+          CUDA events on the stream the library launches on, L2 flushed between timed steps
+  e2e   : same metric through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+  roofline     : FP64 CUDA-core roofline of the solver kernels (algorithmic FLOPs from the frozen
+                 flops_model with each pair's actual iteration count / kernel time from CUDA events
+                 inside the library); peak = DFMA micro-benchmark run in the same process, because
+                 MEASURED_PEAKS.json carries no FP64 figure.  "hbm" sub-object: pose-in/result-out bytes.
+  cpu_baseline : the C++ oracle (restatement of the Julia reference) on all host threads, bounded sample
+
+`--impl reference` times the reference's CPU implementation of the path; Julia is not in the image, so
+this is the oracle port (kind "port") on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "proximity pair-queries/sec"
+UNIT = "pairs/s"
+PDIP_TOL = 1e-6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="proximity pairs per GPU per step (config 2)")
+    ap.add_argument("--jac-pairs", type=int, default=2_000_000, help="proximity_jacobian pairs per GPU per step (config 3)")
+    ap.add_argument("--no-jacobian", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="cube", choices=["cube", "scene"])
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "BASELINE config 2: proximity, all 7x7 primitive-type pairs (polytope/capsule/cylinder/cone/sphere/"
+                        "ellipsoid/polygon), quaternion attitude, random poses r1=2N(0,I) r2=N(0,I) q=normalize(N(0,I4))",
+            "pairs_per_gpu": args.pairs, "global_pairs": args.pairs * n_gpus, "pdip_tol": PDIP_TOL,
+            "shapes": args.variant, "parallelism": f"index-sharded x{n_gpus}, no data-path collective",
+            "l2": "flushed between timed steps (256 MiB memset); inputs+outputs 160 MB per step"}
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU path: C++ oracle port on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import dcol_b200 as dc
+    import util
+    from oracle import oracle as orc
+    threads = orc.max_threads()
+    sample = 100_000
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sample, dc.ATT_QUAT, seed=1234, variant=args.variant)
+    ta = t.arrays()
+    for _ in range(max(1, args.warmup)):
+        orc.query(0, ta, s1[:20000], s2[:20000], r1[:20000], a1[:20000], r2[:20000], a2[:20000], 0, PDIP_TOL)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.query(0, ta, s1, s2, r1, a1, r2, a2, 0, PDIP_TOL)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    cfg = workload_config(args, args.gpus)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} pairs of the config-2 workload per step, C++ restatement of the Julia reference "
+                                       f"(Julia is not installed in this image), std::thread x{threads}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dcol_b200 as dc
+    import util
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; dcol_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = dc.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def make(n, att_kind, seed):
+        t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, att_kind, seed=seed + 7919 * rank, variant=args.variant)
+        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (s1, s2, r1, a1, r2, a2)]
+        devt = [h.to(dev) for h in host]
+        return t, host, devt
+
+    def run_config(kind, att_kind, n, steps, warmup, seed):
+        na = 4 if att_kind == 0 else 3
+        nt = 6 + 2 * na
+        table, host, devt = make(n, att_kind, seed)
+        ctx.set_shape_arrays(*table.arrays())
+        d_alpha = torch.empty(n, dtype=torch.float64, device=dev)
+        d_x = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        d_der = torch.empty((n, nt, 4), dtype=torch.float64, device=dev) if kind == 2 else None
+        d_st = torch.empty(n, dtype=torch.int32, device=dev)
+        d_it = torch.empty(n, dtype=torch.int32, device=dev)
+        h_alpha = torch.empty(n, dtype=torch.float64).pin_memory()
+        h_x = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+        h_der = torch.empty((n, nt, 4), dtype=torch.float64).pin_memory() if kind == 2 else None
+        h_st = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_it = torch.empty(n, dtype=torch.int32).pin_memory()
+
+        def dev_step():
+            ctx.query_raw(kind, n, *devt, att_kind, PDIP_TOL, dc.MEM_DEVICE, d_alpha, d_x, d_der, d_st, d_it)
+
+        def host_step():
+            ctx.query_raw(kind, n, *host, att_kind, PDIP_TOL, dc.MEM_HOST, h_alpha, h_x, h_der, h_st, h_it)
+
+        for _ in range(warmup):
+            dev_step()
+        sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
+        if sampler:
+            sampler.start()
+        l0 = ctx.launch_count()
+        evs = []
+        kms = []
+        for _ in range(steps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            dev_step()
+            e1.record(stream)
+            evs.append((e0, e1))
+            kms.append(ctx.last_kernel_ms())
+        barrier()
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        dev_ms = max_over_ranks(dev_ms)
+        # end to end: host (pinned) buffers through the C ABI, H2D and D2H inside the timed region
+        host_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(2, steps // 2)
+        for _ in range(e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        iters = d_it.cpu().numpy()
+        status = d_st.cpu().numpy()
+        types, offs, params = table.arrays()
+        n_ort = np.array([int(params[o]) if t in (0, 6) else {1: 2, 2: 4, 3: 1, 4: 0, 5: 0}[int(t)] for t, o in zip(types, offs)])
+        flops = dc.flops_model.batch_flops(kind, types, n_ort, host[0].numpy(), host[1].numpy(), iters, att_kind)
+        in_b = n * (8 + 8 * (6 + 2 * na))
+        out_b = n * (8 + 8 * (1 + 3 + (4 * nt if kind == 2 else 0)))
+        return {"n": n, "dev_ms": dev_ms, "steps": steps, "kernel_ms": float(np.mean(kms)), "launches": launches, "clocks": clocks,
+                "e2e_s": e2e_s, "e2e_steps": e2e_steps, "flops": flops, "in_bytes": in_b, "out_bytes": out_b,
+                "mean_iters": float(iters.mean()), "max_iters": int(iters.max()), "failed": int((status != 0).sum())}
+
+    fp64_peak = ctx.measure_fp64_tflops()
+    prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234)
+    jac = None
+    if not args.no_jacobian:
+        jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), max(3, args.warmup), 4321)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        threads = orc.max_threads()
+        sample = 400_000
+        t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sample, dc.ATT_QUAT, seed=1234, variant=args.variant)
+        orc.query(0, t.arrays(), s1[:20000], s2[:20000], r1[:20000], a1[:20000], r2[:20000], a2[:20000], 0, PDIP_TOL)
+        t0 = time.perf_counter()
+        orc.query(0, t.arrays(), s1, s2, r1, a1, r2, a2, 0, PDIP_TOL)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample} pairs of the config-2 workload, C++ restatement of the Julia reference, std::thread x{threads}"}
+        sj = 200_000
+        t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sj, dc.ATT_MRP, seed=4321, variant=args.variant)
+        t0 = time.perf_counter()
+        orc.query(2, t.arrays(), s1, s2, r1, a1, r2, a2, 1, PDIP_TOL)
+        cpu["jacobian_value"] = sj / (time.perf_counter() - t0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+
+        def roof(r):
+            ach = r["flops"] / (r["kernel_ms"] * 1e-3) / 1e12
+            gbs = (r["in_bytes"] + r["out_bytes"]) / (r["kernel_ms"] * 1e-3) / 1e9
+            return {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "peak_source": "DFMA micro-benchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                    "traffic": None, "kernel_ms_per_step": r["kernel_ms"], "algorithmic_flops_per_pair": r["flops"] / r["n"],
+                    "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                            "peak_source": hbm_src, "algorithmic_bytes_per_pair": (r["in_bytes"] + r["out_bytes"]) / r["n"]}}
+
+        value = world * prox["n"] * prox["steps"] / (prox["dev_ms"] * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": prox["steps"], "warmup": args.warmup,
+                "ms_per_step": prox["dev_ms"] / prox["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "e2e": {"value": world * prox["n"] * prox["e2e_steps"] / prox["e2e_s"], "unit": UNIT,
+                        "h2d_bytes_per_step": prox["in_bytes"], "d2h_bytes_per_step": prox["out_bytes"]},
+                "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox),
+                "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if jac:
+            line["jacobian"] = {
+                "metric": "proximity_jacobian queries/sec", "unit": UNIT,
+                "value": world * jac["n"] * jac["steps"] / (jac["dev_ms"] * 1e-3), "steps": jac["steps"],
+                "ms_per_step": jac["dev_ms"] / jac["steps"],
+                "config": {"workload": "BASELINE config 3: proximity_jacobian, mixed 7x7 primitive types, MRP attitude",
+                           "pairs_per_gpu": jac["n"], "global_pairs": jac["n"] * world},
+                "e2e": {"value": world * jac["n"] * jac["e2e_steps"] / jac["e2e_s"], "unit": UNIT,
+                        "h2d_bytes_per_step": jac["in_bytes"], "d2h_bytes_per_step": jac["out_bytes"]},
+                "gpu_launches": jac["launches"], "clocks": jac["clocks"], "roofline": roof(jac),
+                "solver": {"mean_iters": jac["mean_iters"], "max_iters": jac["max_iters"], "failed_pairs": jac["failed"]}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,8 +13,7 @@
 
 namespace dcol {
 typedef void (*SolveFn)(QueryParams, int, int);
-SolveFn get_solve_kernel(int c1, int c2);   // dcol_kernels_*.cu
-SolveFn get_deriv_kernel(int c1, int c2);   // dcol_kernels_*.cu
+SolveFn get_solve_kernel(int c1, int c2, bool jac);   // dcol_kernels_*.cu
 }
 using namespace dcol;
 
@@ -58,7 +57,7 @@ struct dcol_ctx {
   int max_rows_cls[NCLS] = {};
   DevBuf d_shapes, d_rows, d_cls, d_keymap;
   // per-call scratch
-  DevBuf d_in, d_out, d_perm, d_hist, d_state;
+  DevBuf d_in, d_out, d_perm, d_hist;
   std::vector<int> h_off;
   int64_t launches = 0;
   double last_ms = -1.0;
@@ -200,7 +199,7 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_state};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -363,6 +362,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (query == Q_PROX && !x) { ctx->err = "dcol_proximity: x is NULL"; return -1; }
   if (query != Q_PROX && !deriv) { ctx->err = "dcol: derivative output is NULL"; return -1; }
   if (query == Q_JAC && !x) { ctx->err = "dcol_proximity_jacobian: x is NULL"; return -1; }
+  if (query == Q_JAC && mem == DCOL_MEM_DEVICE && ((uintptr_t)deriv & 15)) { ctx->err = "dcol_proximity_jacobian: J must be 16-byte aligned"; return -1; }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t S = ctx->stream();
   const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3;
@@ -439,7 +439,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   P.perm = (const int32_t*)ctx->d_perm.p;
 
   // class-pair ranges (keys are class-pair major)
-  struct Bin { int c1, c2, begin, count, rows_cap, stride; };
+  struct Bin { int c1, c2, begin, count, rows_cap; };
   std::vector<Bin> bins;
   {
     int k = 0;
@@ -450,21 +450,11 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (count > 0) {
         Bin b; b.c1 = cp / NCLS; b.c2 = cp % NCLS; b.begin = begin; b.count = count;
         b.rows_cap = ctx->max_rows_cls[b.c1] + ctx->max_rows_cls[b.c2];
-        b.stride = 4 + cls_ne(b.c1) + cls_ne(b.c2) + 2 * b.rows_cap + 2 * (cls_d(b.c1) + cls_d(b.c2));
         bins.push_back(b);
       }
       k = k2;
     }
   }
-  // solver-state scratch for the derivative kernels
-  int max_stride = 0;
-  for (const Bin& b : bins) max_stride = std::max(max_stride, b.stride);
-  if (query != Q_PROX) {
-    CK(ctx->d_state.need(sizeof(double) * (size_t)max_stride * n));
-    P.state = (double*)ctx->d_state.p;
-    P.state_stride = max_stride;
-  }
-
   // ---- launch one solver (+ derivative) kernel per non-empty class pair, spread over side streams
   CK(cudaEventRecord(ctx->ev_k0, S));
   CK(cudaEventRecord(ctx->ev_fork, S));
@@ -477,18 +467,11 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     size_t smem = (size_t)std::max(b.rows_cap, 1) * NFIELD * sizeof(double) * block;
     if (smem > (size_t)MAX_SMEM) { block = 32; smem /= 2; }
     if (smem > (size_t)MAX_SMEM) { ctx->err = "dcol: too many polytope faces / polygon sides for one pair (shared memory)"; return -3; }
-    SolveFn fn = get_solve_kernel(b.c1, b.c2);
+    SolveFn fn = get_solve_kernel(b.c1, b.c2, query == Q_JAC);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (b.count + block - 1) / block;
     fn<<<grid, block, smem, st>>>(P, b.begin, b.count);
     ctx->launches++;
-    if (query != Q_PROX) {
-      SolveFn dfn = get_deriv_kernel(b.c1, b.c2);
-      int dblock = 64;
-      int dgrid = (b.count + dblock - 1) / dblock;
-      dfn<<<dgrid, dblock, 0, st>>>(P, b.begin, b.count);
-      ctx->launches++;
-    }
     CK(cudaGetLastError());
   }
   for (int i = 0; i < nside; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->side[i])); CK(cudaStreamWaitEvent(S, ctx->ev_join[i], 0)); }

@@ -58,8 +58,6 @@ struct QueryParams {
   double pdip_tol;
   double* alpha; double* x; int32_t* status; int32_t* iters;
   double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major
-  double* state;                 // solver state scratch for the derivative kernel (may be NULL)
-  int state_stride;              // doubles per pair in the scratch (field-major within the bin)
   int query;
 };
 

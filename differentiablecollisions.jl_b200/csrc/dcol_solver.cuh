@@ -16,37 +16,9 @@
 //     everything else (y, Gram matrix, SOC blocks, relative pose) is in registers.
 #pragma once
 #include "dcol_common.cuh"
+#include "dcol_deriv.cuh"
 
 namespace dcol {
-
-// ---------------------------------------------------------------------------
-// attitude maps (src/problem_matrices.jl:9-27), templated so the derivative
-// kernel can push a dual number through them
-// ---------------------------------------------------------------------------
-template <class T> __device__ __forceinline__ T t_sqrt(const T& a);
-template <> __device__ __forceinline__ double t_sqrt<double>(const double& a) { return sqrt(a); }
-
-template <class T>
-__device__ __forceinline__ void dcm_from_q(const T q[4], T Q[3][3]) {
-  T nrm = t_sqrt<T>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  T q4 = q[0] / nrm, q1 = q[1] / nrm, q2 = q[2] / nrm, q3 = q[3] / nrm;
-  Q[0][0] = 2.0 * q1 * q1 + 2.0 * q4 * q4 - 1.0; Q[0][1] = 2.0 * (q1 * q2 - q3 * q4);         Q[0][2] = 2.0 * (q1 * q3 + q2 * q4);
-  Q[1][0] = 2.0 * (q1 * q2 + q3 * q4);         Q[1][1] = 2.0 * q2 * q2 + 2.0 * q4 * q4 - 1.0; Q[1][2] = 2.0 * (q2 * q3 - q1 * q4);
-  Q[2][0] = 2.0 * (q1 * q3 - q2 * q4);         Q[2][1] = 2.0 * (q2 * q3 + q1 * q4);         Q[2][2] = 2.0 * q3 * q3 + 2.0 * q4 * q4 - 1.0;
-}
-template <class T>
-__device__ __forceinline__ void dcm_from_mrp(const T p[3], T Q[3][3]) {
-  T p1 = p[0], p2 = p[1], p3 = p[2];
-  T den1 = p1 * p1 + p2 * p2 + p3 * p3 + 1.0;
-  T den = den1 * den1;
-  T a = 4.0 * p1 * p1 + 4.0 * p2 * p2 + 4.0 * p3 * p3 - 4.0;
-  T id = 1.0 / den;
-  Q[0][0] = 1.0 - (8.0 * p2 * p2 + 8.0 * p3 * p3) * id; Q[0][1] = (8.0 * p1 * p2 + p3 * a) * id; Q[0][2] = (8.0 * p1 * p3 - p2 * a) * id;
-  Q[1][0] = (8.0 * p1 * p2 - p3 * a) * id; Q[1][1] = 1.0 - (8.0 * p1 * p1 + 8.0 * p3 * p3) * id; Q[1][2] = (8.0 * p2 * p3 + p1 * a) * id;
-  Q[2][0] = (8.0 * p1 * p3 + p2 * a) * id; Q[2][1] = (8.0 * p2 * p3 - p1 * a) * id; Q[2][2] = 1.0 - (8.0 * p1 * p1 + 8.0 * p2 * p2) * id;
-}
-
-struct Frame { double Q[3][3]; double r[3]; };
 
 // r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
 __device__ __forceinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F) {
@@ -222,7 +194,7 @@ struct Prim {
   const double* rows; int n; int row0;
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
-  double V[DD][DD], Vsq[DD][DD];       // Wbar^-1 and Wbar^-2
+  double V[DD][DD];                    // Wbar^-1 (= J Wbar J)
   double ie, ie2, Js, Jz, sJs, sJz;    // 1/eta, 1/eta^2, J(s), J(z) and roots
   double lam[DD], rz[DD], v[DD], wc[DD];
 
@@ -364,7 +336,8 @@ struct Prim {
       for (int i = 1; i < D; i++) { V[0][i] = -wb[i]; V[i][0] = -wb[i];
 #pragma unroll
         for (int j = 1; j < D; j++) V[i][j] = ((i == j) ? 1.0 : 0.0) + bb * wb[i] * wb[j]; }
-      // Vsq = V*V (product form keeps the Gram block PSD to round-off)
+      // Vsq = V'V (a Gram product, so the KKT block stays PSD to round-off); local to this pass
+      double Vsq[D][D];
 #pragma unroll
       for (int i = 0; i < D; i++)
 #pragma unroll
@@ -372,11 +345,18 @@ struct Prim {
 #pragma unroll
           for (int k = 0; k < D; k++) a += V[i][k] * V[k][j];
           Vsq[i][j] = a; Vsq[j][i] = a; }
-      double t2[D];
+      // t2 = W^-2 rz as two applications of W^-1 (never through the squared matrix: its condition
+      // number is cond(W)^2 and the iterates near convergence need the scaled-space accuracy)
+      double t1[D], t2[D];
 #pragma unroll
       for (int i = 0; i < D; i++) { double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < D; k++) a += Vsq[i][k] * rz[k];
+        for (int k = 0; k < D; k++) a += V[i][k] * rz[k];
+        t1[i] = a; }
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a += V[i][k] * t1[k];
         t2[i] = ie2 * a; }
       soc_applyT<CLS, NV, D>(sc, t2, g);
       soc_gram<CLS, NV, D>(sc, Vsq, ie2, N);
@@ -404,11 +384,17 @@ struct Prim {
       soc_apply<CLS, NV, D>(sc, dyh, cd);
 #pragma unroll
       for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; dsa[i] = -t[i]; }
+      // v = W^-1 t ; dza = W^-1 (v - lambda)  [= W^-2 t - z, with the subtraction done in the scaled space]
 #pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0, b = 0.0;
+      for (int i = 0; i < D; i++) { double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < D; k++) { a += V[i][k] * t[k]; b += Vsq[i][k] * t[k]; }
-        v[i] = ie * a; dza[i] = ie2 * b - z[i]; }
+        for (int k = 0; k < D; k++) a += V[i][k] * t[k];
+        v[i] = ie * a; }
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a += V[i][k] * (v[k] - lam[k]);
+        dza[i] = ie * a; }
       a_s = fmin(a_s, soc_linesearch<D>(s, dsa, Js, sJs));
       a_z = fmin(a_z, soc_linesearch<D>(z, dza, Jz, sJz));
 #pragma unroll
@@ -443,12 +429,13 @@ struct Prim {
       kap[0] = irho * (lam[0] * wc[0] - nu);
 #pragma unroll
       for (int i = 1; i < D; i++) kap[i] = irho * ((nu * il0 - wc[0]) * lam[i] + (rho * il0) * wc[i]);
+      double wk[D];
 #pragma unroll
       for (int i = 0; i < D; i++) { double a = 0.0;
 #pragma unroll
         for (int k = 0; k < D; k++) a += V[i][k] * kap[k];
-        wc[i] = ie * a; }
-      soc_applyT<CLS, NV, D>(sc, wc, g2);
+        wk[i] = ie * a; wc[i] = kap[i]; }
+      soc_applyT<CLS, NV, D>(sc, wk, g2);
     }
   }
 
@@ -470,11 +457,18 @@ struct Prim {
       soc_apply<CLS, NV, D>(sc, dyh, cd);
 #pragma unroll
       for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; ds[i] = -t[i]; }
+      // dz = W^-1 (W^-1 t - lambda + kappa)   (scaled-space accumulation, static_solver2.jl:165-168)
+      double v2[D];
 #pragma unroll
-      for (int i = 0; i < D; i++) { double b = 0.0;
+      for (int i = 0; i < D; i++) { double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < D; k++) b += Vsq[i][k] * t[k];
-        dz[i] = ie2 * b - z[i] + wc[i]; }
+        for (int k = 0; k < D; k++) a += V[i][k] * t[k];
+        v2[i] = ie * a - lam[i] + wc[i]; }
+#pragma unroll
+      for (int i = 0; i < D; i++) { double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; k++) a += V[i][k] * v2[k];
+        dz[i] = ie * a; }
       a_s = fmin(a_s, soc_linesearch<D>(s, ds, Js, sJs));
       a_z = fmin(a_z, soc_linesearch<D>(z, dz, Jz, sJz));
 #pragma unroll
@@ -494,6 +488,90 @@ struct Prim {
       for (int i = 0; i < D; i++) { s[i] += al * rz[i]; z[i] += al * v[i]; sz += s[i] * z[i]; }
     }
     return sz;
+  }
+
+  // ---- derivative epilogue: the vectors of dcol_deriv.cuh's SideVecs for this primitive
+  //      wr = (C' z)[0:3] over the body-frame part (orthant rows, cone / ellipsoid SOC block),
+  //      zb = vector part of z of a ball SOC block, Be = B~ e
+  __device__ __forceinline__ void side_vecs(const RowStore& rs, const double (&yh)[NV], SideVecs& V) const {
+    double w[NV];
+#pragma unroll
+    for (int a = 0; a < NV; a++) w[a] = 0.0;
+    for (int i = 0; i < n; i++) {
+      double zi = rs(F_Z, row0 + i);
+#pragma unroll
+      for (int a = 0; a < 3; a++) w[a] += zi * __ldg(rows + i * NV + a);
+    }
+    constexpr int SOC = Cls<CLS>::SOC;
+    if constexpr (D > 0 && SOC != SOC_BALL) soc_applyT<CLS, NV, D>(sc, z, w);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { V.wr[a] = w[a]; V.xt[a] = yh[a]; V.zb[a] = 0.0; V.Be[a] = 0.0; }
+    if constexpr (SOC == SOC_BALL) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) V.zb[a] = z[1 + a];
+      if constexpr (NE >= 1) V.Be[0] = yh[4];
+      if constexpr (NE == 2) V.Be[1] = yh[5];
+    }
+  }
+  // ---- derivative epilogue: Nf = C' (S^-1 Z) C (full, slightly non-symmetric on SOC blocks), with the
+  // solver's slack s (src/proximity.jl:98-100: Z = arrow(z), S = arrow(s))
+  // Nbx = first three columns of the ball SOC block's share of Nf (zero for other classes)
+  __device__ __forceinline__ void ift_gram(const RowStore& rs, double (&Nf)[NV][NV], double (&Nbx)[NV][3]) const {
+#pragma unroll
+    for (int a = 0; a < NV; a++)
+#pragma unroll
+      for (int b = 0; b < NV; b++) Nf[a][b] = 0.0;
+    for (int i = 0; i < n; i++) {
+      double c[NV];
+#pragma unroll
+      for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
+      double d = rs(F_Z, row0 + i) / rs(F_S, row0 + i);
+#pragma unroll
+      for (int a = 0; a < NV; a++) { double dc = d * c[a];
+#pragma unroll
+        for (int b = a; b < NV; b++) Nf[a][b] += dc * c[b]; }
+    }
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+#pragma unroll
+      for (int b = 0; b < a; b++) Nf[a][b] = Nf[b][a];
+#pragma unroll
+      for (int c = 0; c < 3; c++) Nbx[a][c] = 0.0;
+    }
+    if constexpr (D > 0) {
+      // Bm = arrow(s)^-1 arrow(z), column by column through the closed-form Jordan division
+      double Bm[D][D];
+#pragma unroll
+      for (int c = 0; c < D; c++) {
+        double col[D], out[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) col[i] = (c == 0) ? z[i] : ((i == 0) ? z[c] : ((i == c) ? z[0] : 0.0));
+        soc_jdiv<D>(s, col, out);
+#pragma unroll
+        for (int i = 0; i < D; i++) Bm[i][c] = out[i];
+      }
+#pragma unroll
+      for (int b = 0; b < NV; b++) {
+        double e[NV], u[D], v[D], g[NV];
+#pragma unroll
+        for (int a = 0; a < NV; a++) { e[a] = (a == b) ? 1.0 : 0.0; g[a] = 0.0; }
+        soc_apply<CLS, NV, D>(sc, e, u);
+#pragma unroll
+        for (int i = 0; i < D; i++) { double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) acc += Bm[i][k] * u[k];
+          v[i] = acc; }
+        soc_applyT<CLS, NV, D>(sc, v, g);
+#pragma unroll
+        for (int a = 0; a < NV; a++) Nf[a][b] += g[a];
+        if constexpr (Cls<CLS>::SOC == SOC_BALL) {
+          if (b < 3) {
+#pragma unroll
+            for (int a = 0; a < NV; a++) Nbx[a][b] = g[a];
+          }
+        }
+      }
+    }
   }
 };
 
@@ -556,11 +634,11 @@ struct PairMap {
   }
 };
 
-// layout of the per-pair solver state handed to the derivative kernel
-// (field-major inside a bin: element f of sorted pair j lives at state[f*bin_count + j])
-//   [0,NX) y (frame 1) ; then rows: s[n1+n2], z[n1+n2] ; then soc1 s,z ; soc2 s,z
-template <int C1, int C2>
-__device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, int bin_begin, int bin_count, double* smem) {
+// One pair: relative pose -> initial point -> PDIP loop -> outputs (+ derivative epilogue).
+// JAC selects the kernel variant that carries the implicit-function-theorem epilogue; the
+// gradient epilogue is a few dozen flops and lives in the JAC=false variant behind p.query.
+template <int C1, int C2, bool JAC>
+__device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, double* smem) {
   using P1 = Prim<C1>; using P2 = Prim<C2>;
   using PM = PairMap<P1::NE, P2::NE>;
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
@@ -684,43 +762,143 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, int bi
   }
 
   // ---------------- outputs ----------------
-  {
-    Frame F1;
-    build_frame(S1, p.r1 + 3 * (int64_t)pair, p.att1 + na * (int64_t)pair, p.att_kind, F1);
-    p.alpha[pair] = y[3];
-    if (p.x) {
+  Frame F1, F2;
+  build_frame(S1, p.r1 + 3 * (int64_t)pair, p.att1 + na * (int64_t)pair, p.att_kind, F1);
+  p.alpha[pair] = y[3];
+  if (p.x) {
 #pragma unroll
-      for (int a = 0; a < 3; a++) p.x[3 * (int64_t)pair + a] = F1.r[a] + F1.Q[a][0] * y[0] + F1.Q[a][1] * y[1] + F1.Q[a][2] * y[2];
-    }
-    if (p.status) p.status[pair] = status;
-    if (p.iters) p.iters[pair] = it;
+    for (int a = 0; a < 3; a++) p.x[3 * (int64_t)pair + a] = F1.r[a] + F1.Q[a][0] * y[0] + F1.Q[a][1] * y[1] + F1.Q[a][2] * y[2];
   }
-  if (p.state) {
-    double* st = p.state + (int64_t)bin_begin * p.state_stride + (idx - bin_begin);
-    int f = 0;
-#pragma unroll
-    for (int a = 0; a < NX; a++) st[(int64_t)(f++) * bin_count] = y[a];
-    int nr = A.n + B.n;
-    for (int i = 0; i < nr; i++) { st[(int64_t)(f + i) * bin_count] = rs(F_S, i); st[(int64_t)(f + nr + i) * bin_count] = rs(F_Z, i); }
-    f += 2 * nr;
-    if constexpr (P1::D > 0) {
-#pragma unroll
-      for (int i = 0; i < P1::D; i++) { st[(int64_t)(f + i) * bin_count] = A.s[i]; st[(int64_t)(f + P1::D + i) * bin_count] = A.z[i]; }
-      f += 2 * P1::D;
+  if (p.iters) p.iters[pair] = it;
+  const int nt = 6 + 2 * na;
+
+  if constexpr (!JAC) {
+    // ---- proximity_gradient (src/proximity_gradient.jl:41-78): -z' du/dtheta
+    if (p.query == Q_GRAD) {
+      double* g = p.deriv + (int64_t)nt * pair;
+      if (status == ST_OK) {
+        build_frame(S2, p.r2 + 3 * (int64_t)pair, p.att2 + na * (int64_t)pair, p.att_kind, F2);
+        double y1[NV1], y2[NV2];
+        PM::to_local(y, R, t, true, y1, y2);
+        SideVecs V1, V2;
+        A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
+        grad_side(S1, F1, p.att1 + na * (int64_t)pair, p.att_kind, V1, g);
+        grad_side(S2, F2, p.att2 + na * (int64_t)pair, p.att_kind, V2, g + 3 + na);
+      } else {
+        for (int j = 0; j < nt; j++) g[j] = __longlong_as_double(0x7ff8000000000000LL);
+      }
     }
-    if constexpr (P2::D > 0) {
+  } else {
+    // ---- proximity_jacobian (src/proximity.jl:71-134): reduced KKT solve in primitive-1's frame
+    double* Jo = p.deriv + (int64_t)4 * nt * pair;
+    bool ok = (status == ST_OK);
+    if (ok) {
+      build_frame(S2, p.r2 + 3 * (int64_t)pair, p.att2 + na * (int64_t)pair, p.att_kind, F2);
+      double K1[4][3], K2[4][3], Kb1[4][3], Kb2[4][3], Ye1[4][2], Ye2[4][2], Hw[4][3];
+      SideVecs V1, V2;
+      {
+        double y1[NV1], y2[NV2];
+        PM::to_local(y, R, t, true, y1, y2);
+        A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
+      }
+      {
+        double N1[NV1][NV1], N2[NV2][NV2], Nb1[NV1][3], Nb2[NV2][3];
+        A.ift_gram(rs, N1, Nb1); B.ift_gram(rs, N2, Nb2);
+        double Mt[NX][NX], Y[NX][4];        // Mt = A'^T : row b of Mt = column b of A'
 #pragma unroll
-      for (int i = 0; i < P2::D; i++) { st[(int64_t)(f + i) * bin_count] = B.s[i]; st[(int64_t)(f + P2::D + i) * bin_count] = B.z[i]; }
+        for (int b = 0; b < NX; b++) {
+          double e[NX], y1[NV1], y2[NV2], n1[NV1], n2[NV2], col[NX];
+#pragma unroll
+          for (int a = 0; a < NX; a++) e[a] = (a == b) ? 1.0 : 0.0;
+          PM::to_local(e, R, t, false, y1, y2);
+#pragma unroll
+          for (int a = 0; a < NV1; a++) { double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < NV1; c++) acc += N1[a][c] * y1[c];
+            n1[a] = acc; }
+#pragma unroll
+          for (int a = 0; a < NV2; a++) { double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < NV2; c++) acc += N2[a][c] * y2[c];
+            n2[a] = acc; }
+          PM::assemble_vec(n1, n2, R, col);
+#pragma unroll
+          for (int a = 0; a < NX; a++) Mt[b][a] = col[a];
+        }
+#pragma unroll
+        for (int a = 0; a < NX; a++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) Y[a][i] = (a == i) ? 1.0 : 0.0;
+        ok = ge_solve<NX, 4>(Mt, Y);
+        // K'_k[i][c] = sum_l (T_k' Y)[l][i] N_k[l][c] ; H4[i][c] = Y[c][i] ; Ye'_k[i][m] = Y[extras_k m][i]
+        double Kp1[4][3], Kp2[4][3], Kq1[4][3], Kq2[4][3], Yp1[4][2], Yp2[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          double yc[NX], y1[NV1], y2[NV2];
+#pragma unroll
+          for (int a = 0; a < NX; a++) yc[a] = Y[a][i];
+          PM::to_local(yc, R, t, false, y1, y2);
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+            for (int l = 0; l < NV1; l++) { a1 += y1[l] * N1[l][c]; b1 += y1[l] * Nb1[l][c]; }
+#pragma unroll
+            for (int l = 0; l < NV2; l++) { a2 += y2[l] * N2[l][c]; b2 += y2[l] * Nb2[l][c]; }
+            Kp1[i][c] = a1; Kp2[i][c] = a2; Kq1[i][c] = b1; Kq2[i][c] = b2;
+          }
+#pragma unroll
+          for (int m = 0; m < 2; m++) {
+            Yp1[i][m] = (m < P1::NE) ? y1[(4 + m < NV1) ? 4 + m : 0] : 0.0;
+            Yp2[i][m] = (m < P2::NE) ? y2[(4 + m < NV2) ? 4 + m : 0] : 0.0;
+          }
+        }
+        // rotate rows 0..2 into the world frame (P4 = blkdiag(Q1, 1)); Hw = P4 H4 Q1'
+        double Hq[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) Hq[i][c] = Y[0][i] * F1.Q[c][0] + Y[1][i] * F1.Q[c][1] + Y[2][i] * F1.Q[c][2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            K1[i][c] = F1.Q[i][0] * Kp1[0][c] + F1.Q[i][1] * Kp1[1][c] + F1.Q[i][2] * Kp1[2][c];
+            K2[i][c] = F1.Q[i][0] * Kp2[0][c] + F1.Q[i][1] * Kp2[1][c] + F1.Q[i][2] * Kp2[2][c];
+            Kb1[i][c] = F1.Q[i][0] * Kq1[0][c] + F1.Q[i][1] * Kq1[1][c] + F1.Q[i][2] * Kq1[2][c];
+            Kb2[i][c] = F1.Q[i][0] * Kq2[0][c] + F1.Q[i][1] * Kq2[1][c] + F1.Q[i][2] * Kq2[2][c];
+            Hw[i][c] = F1.Q[i][0] * Hq[0][c] + F1.Q[i][1] * Hq[1][c] + F1.Q[i][2] * Hq[2][c];
+          }
+          K1[3][c] = Kp1[3][c]; K2[3][c] = Kp2[3][c]; Kb1[3][c] = Kq1[3][c]; Kb2[3][c] = Kq2[3][c]; Hw[3][c] = Hq[3][c];
+        }
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            Ye1[i][m] = F1.Q[i][0] * Yp1[0][m] + F1.Q[i][1] * Yp1[1][m] + F1.Q[i][2] * Yp1[2][m];
+            Ye2[i][m] = F1.Q[i][0] * Yp2[0][m] + F1.Q[i][1] * Yp2[1][m] + F1.Q[i][2] * Yp2[2][m];
+          }
+          Ye1[3][m] = Yp1[3][m]; Ye2[3][m] = Yp2[3][m];
+        }
+      }
+      if (ok) {
+        jac_side<P1::NE>(S1, F1, p.att1 + na * (int64_t)pair, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo);
+        jac_side<P2::NE>(S2, F2, p.att2 + na * (int64_t)pair, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + 4 * (3 + na));
+      } else {
+        status = ST_NUMERICAL;
+      }
     }
+    if (!ok) for (int j = 0; j < 4 * nt; j++) Jo[j] = __longlong_as_double(0x7ff8000000000000LL);
   }
+  if (p.status) p.status[pair] = status;
 }
 
-template <int C1, int C2>
+template <int C1, int C2, bool JAC>
 __global__ void solve_kernel(QueryParams p, int bin_begin, int bin_count) {
   extern __shared__ double smem[];
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= bin_count) return;
-  solve_pair<C1, C2>(p, bin_begin + j, bin_begin, bin_count, smem);
+  solve_pair<C1, C2, JAC>(p, bin_begin + j, smem);
 }
 
 }  // namespace dcol

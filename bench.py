@@ -42,7 +42,7 @@ PDIP_TOL = 1e-6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="proximity pairs per GPU per step (config 2)")
@@ -62,8 +62,11 @@ def workload_config(args, n_gpus):
 
 
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up; only samples whose timestamp falls inside the timed
+    region [t0, t1] are reported (the recipe's clocks line, /opt/skills/guides/B200_PROFILING.md)."""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
@@ -72,15 +75,17 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -89,20 +94,31 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, power, reasons, sm_all = [], [], [], set(), []
         for r in rows:
-            if len(r) < 9:
+            if len(r) < 10:
                 continue
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                c, m = float(r[2]), float(r[3])
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if r[5 + k].strip().lower().startswith("active"):
+            sm_all.append(c)
+            if ts < t0 - 0.02 or ts > t1 + 0.02:
+                continue
+            sm.append(c); mx.append(m)
+            try:
+                power.append(float(r[4]))
+            except ValueError:
+                pass
+            for k, nm in enumerate(self.NAMES):
+                if r[6 + k].strip().lower().startswith("active"):
                     reasons.add(nm)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power) if power else None)
+        elif sm_all:
+            out.update(sm_mhz=float(np.median(sm_all)), samples=0, note="no sample fell inside the timed region; median over the whole run")
         return out
 
 
@@ -202,12 +218,13 @@ def main():
         def host_step():
             ctx.query_raw(kind, n, *host, att_kind, PDIP_TOL, dc.MEM_HOST, h_alpha, h_x, h_der, h_st, h_it)
 
-        for _ in range(warmup):
-            dev_step()
         sampler = ClockSampler(local) if rank == 0 else None
-        barrier()
         if sampler:
             sampler.start()
+        for _ in range(warmup):
+            dev_step()
+        barrier()
+        t_begin = time.time()
         l0 = ctx.launch_count()
         evs = []
         kms = []
@@ -220,15 +237,16 @@ def main():
             evs.append((e0, e1))
             kms.append(ctx.last_kernel_ms())
         barrier()
+        t_end = time.time()
         launches = ctx.launch_count() - l0
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_begin, t_end) if sampler else None
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         dev_ms = max_over_ranks(dev_ms)
         # end to end: host (pinned) buffers through the C ABI, H2D and D2H inside the timed region
         host_step()
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(2, steps // 2)
+        e2e_steps = max(2, min(10, steps // 2))
         for _ in range(e2e_steps):
             host_step()
         torch.cuda.synchronize()
@@ -249,7 +267,7 @@ def main():
     prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234)
     jac = None
     if not args.no_jacobian:
-        jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), max(3, args.warmup), 4321)
+        jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), args.warmup, 4321)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,44 @@
+"""Index sharding of a pair batch over the GPUs of one box.
+
+Every pair query is independent, so the N>1 path is: rank g takes the g-th contiguous slice of the
+pair index range, runs the same C-ABI call on its own GPU, and — only if the caller wants the rows on
+every rank — an all-gather of the result rows (NCCL over NVLink on GPUs, gloo in the CPU tests).
+There is no collective on the data path itself.
+"""
+from __future__ import annotations
+
+
+def shard_bounds(n: int, world: int):
+    """Contiguous [begin, end) per rank; sizes differ by at most one; empty shards allowed when n < world."""
+    if world < 1 or n < 0:
+        raise ValueError("need world >= 1 and n >= 0")
+    base, rem = divmod(n, world)
+    out, b = [], 0
+    for r in range(world):
+        e = b + base + (1 if r < rem else 0)
+        out.append((b, e))
+        b = e
+    return out
+
+
+def shard(n: int, rank: int, world: int):
+    return shard_bounds(n, world)[rank]
+
+
+def gather_rows(local, n_total: int, rank: int, world: int, group=None):
+    """All-gather per-pair result rows (first dim = this rank's shard) into the full (n_total, ...) tensor on every
+    rank.  Shards are padded to the largest shard so a plain all_gather works on both NCCL and gloo."""
+    import torch
+    import torch.distributed as dist
+    bounds = shard_bounds(n_total, world)
+    b, e = bounds[rank]
+    if local.shape[0] != e - b:
+        raise ValueError(f"rank {rank}: local rows {local.shape[0]} != shard size {e - b}")
+    if world == 1:
+        return local
+    mx = max(e2 - b2 for b2, e2 in bounds)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: e - b] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], dim=0)

@@ -1,0 +1,263 @@
+# Drop-in Julia front end for the B200-native DCOL library (libdcol_b200.so).
+#
+# Keeps the call surface of kevin-tracy/DifferentiableCollisions.jl v0.1.5 —
+#   primitives        src/primitives.jl:4-96, src/primitives_mrp.jl:2-96
+#   proximity         src/proximity.jl:3-26
+#   proximity_jacobian   src/proximity.jl:168-195
+#   proximity_gradient   src/proximity_gradient.jl:80-111
+#   helpers           src/problem_matrices.jl:1-27, src/misc_primitive_constructors.jl:1-33
+# — and forwards every query through `ccall` to the C ABI of include/dcol_b200.h.  There is no Julia
+# numerics here and no CPU fallback: without the shared library and a CUDA device `__init__` throws.
+#
+# NOTE: Julia is not installed in the build image, so this file is written against the C header and
+# has NOT been executed; the same ABI is exercised from Python (ctypes) by tests/ and bench.py.
+# Set ENV["DCOL_B200_LIB"] to the path of libdcol_b200.so (default: next to this package).
+module DifferentiableCollisions
+
+using LinearAlgebra
+using StaticArrays
+
+export *, \
+
+const _lib = Ref{String}("")
+const _ctx = Ref{Ptr{Cvoid}}(C_NULL)
+
+const ATT_QUAT = Cint(0)
+const ATT_MRP = Cint(1)
+const MEM_HOST = Cint(0)
+const MEM_DEVICE = Cint(1)
+
+abstract type AbstractPrimitive end
+abstract type AbstractPrimitiveMRP end
+const AnyPrimitive = Union{AbstractPrimitive,AbstractPrimitiveMRP}
+
+# ---------------------------------------------------------------------------------------------
+# primitives: same names, fields and defaults as the reference (pose at the origin, identity attitude)
+# ---------------------------------------------------------------------------------------------
+_q0() = SA[1.0, 0.0, 0.0, 0.0]
+_p0() = SA[0.0, 0.0, 0.0]
+_r0() = SA[0.0, 0.0, 0.0]
+_I3() = SMatrix{3,3,Float64,9}(I)
+
+mutable struct Polytope{n,n3} <: AbstractPrimitive
+    r::SVector{3,Float64}; q::SVector{4,Float64}
+    A::SMatrix{n,3,Float64,n3}; b::SVector{n,Float64}
+    r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+    Polytope(A::SMatrix{n,3,Float64,n3}, b::SVector{n,Float64}) where {n,n3} = new{n,n3}(_r0(), _q0(), A, b, _r0(), _I3())
+end
+mutable struct PolytopeMRP{n,n3} <: AbstractPrimitiveMRP
+    r::SVector{3,Float64}; p::SVector{3,Float64}
+    A::SMatrix{n,3,Float64,n3}; b::SVector{n,Float64}
+    r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+    PolytopeMRP(A::SMatrix{n,3,Float64,n3}, b::SVector{n,Float64}) where {n,n3} = new{n,n3}(_r0(), _p0(), A, b, _r0(), _I3())
+end
+mutable struct Polygon{nh,nh2} <: AbstractPrimitive
+    r::SVector{3,Float64}; q::SVector{4,Float64}
+    A::SMatrix{nh,2,Float64,nh2}; b::SVector{nh,Float64}; R::Float64
+    r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+    Polygon(A::SMatrix{nh,2,Float64,nh2}, b::SVector{nh,Float64}, R::Float64) where {nh,nh2} = new{nh,nh2}(_r0(), _q0(), A, b, R, _r0(), _I3())
+end
+mutable struct PolygonMRP{nh,nh2} <: AbstractPrimitiveMRP
+    r::SVector{3,Float64}; p::SVector{3,Float64}
+    A::SMatrix{nh,2,Float64,nh2}; b::SVector{nh,Float64}; R::Float64
+    r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+    PolygonMRP(A::SMatrix{nh,2,Float64,nh2}, b::SVector{nh,Float64}, R::Float64) where {nh,nh2} = new{nh,nh2}(_r0(), _p0(), A, b, R, _r0(), _I3())
+end
+
+for (T, TM, geom) in ((:Capsule, :CapsuleMRP, (:R, :L)), (:Cylinder, :CylinderMRP, (:R, :L)),
+                      (:Cone, :ConeMRP, (:H, :β)), (:Sphere, :SphereMRP, (:R,)))
+    gf = [:($g::Float64) for g in geom]
+    @eval begin
+        mutable struct $T <: AbstractPrimitive
+            r::SVector{3,Float64}; q::SVector{4,Float64}
+            $(gf...)
+            r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+            $T($(gf...)) = new(_r0(), _q0(), $(geom...), _r0(), _I3())
+        end
+        mutable struct $TM <: AbstractPrimitiveMRP
+            r::SVector{3,Float64}; p::SVector{3,Float64}
+            $(gf...)
+            r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+            $TM($(gf...)) = new(_r0(), _p0(), $(geom...), _r0(), _I3())
+        end
+    end
+end
+
+# Ellipsoid: x'Px <= 1; keeps P, U = cholesky(P).U and F = eigen(P) like the reference.  Both
+# `Ellipsoid(P)` and `EllipsoidMRP(P)` are constructible (the reference's MRP constructor is
+# mis-named, src/primitives_mrp.jl:85).
+mutable struct Ellipsoid <: AbstractPrimitive
+    r::SVector{3,Float64}; q::SVector{4,Float64}
+    P::SMatrix{3,3,Float64,9}; U::SMatrix{3,3,Float64,9}; F::Eigen
+    r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+    Ellipsoid(P::SMatrix{3,3,Float64,9}) = new(_r0(), _q0(), P, SMatrix{3,3}(cholesky(Hermitian(P)).U), eigen(Matrix(P)), _r0(), _I3())
+end
+mutable struct EllipsoidMRP <: AbstractPrimitiveMRP
+    r::SVector{3,Float64}; p::SVector{3,Float64}
+    P::SMatrix{3,3,Float64,9}; U::SMatrix{3,3,Float64,9}; F::Eigen
+    r_offset::SVector{3,Float64}; Q_offset::SMatrix{3,3,Float64,9}
+    EllipsoidMRP(P::SMatrix{3,3,Float64,9}) = new(_r0(), _p0(), P, SMatrix{3,3}(cholesky(Hermitian(P)).U), eigen(Matrix(P)), _r0(), _I3())
+end
+
+# ---------------------------------------------------------------------------------------------
+# attitude helpers (host conveniences used by callers; not on the device path)
+# ---------------------------------------------------------------------------------------------
+mrp_from_q(q::SVector{4,T}) where {T} = q[SA[2, 3, 4]] / (1 + q[1])
+function q_from_mrp(p::SVector{3,T}) where {T}
+    pp = dot(p, p)
+    return (1 / (1 + pp)) * vcat(1 - pp, 2 * p)
+end
+function dcm_from_q(q::SVector{4,T}) where {T}
+    s, v1, v2, v3 = normalize(q)
+    return SA[2v1^2+2s^2-1 2(v1*v2-v3*s) 2(v1*v3+v2*s)
+              2(v1*v2+v3*s) 2v2^2+2s^2-1 2(v2*v3-v1*s)
+              2(v1*v3-v2*s) 2(v2*v3+v1*s) 2v3^2+2s^2-1]
+end
+dcm_from_mrp(p::SVector{3,T}) where {T} = dcm_from_q(q_from_mrp(p))
+
+function create_rect_prism(len = 20.0, wid = 20.0, hei = 2.0; attitude = :MRP)
+    A = SA[1.0 0 0; 0 1 0; 0 0 1; -1 0 0; 0 -1 0; 0 0 -1]
+    b = SA[len / 2, wid / 2, hei / 2, len / 2, wid / 2, hei / 2]
+    mass = len * wid * hei
+    inertia = (mass / 12) * Diagonal(SA[wid^2 + hei^2, len^2 + hei^2, len^2 + wid^2])
+    attitude == :MRP && return PolytopeMRP(A, b), mass, inertia
+    attitude == :quat && return Polytope(A, b), mass, inertia
+    error("attitude must be :MRP or :quat")
+end
+function create_n_sided(N, d)
+    ns = [[cos(θ), sin(θ)] for θ in 0:(2π / N):(2π * (N - 1) / N)]
+    A = vcat(transpose.(ns)...)
+    return SMatrix{N,2}(A), SVector{N}(d * ones(N))
+end
+
+# ---------------------------------------------------------------------------------------------
+# shape table packing (include/dcol_b200.h: dcol_set_shapes)
+# ---------------------------------------------------------------------------------------------
+_rowmajor(M) = vec(collect(transpose(M)))
+_tail(P) = vcat(collect(P.r_offset), _rowmajor(P.Q_offset))
+shape_type(::Union{Polytope,PolytopeMRP}) = Cint(0)
+shape_type(::Union{Capsule,CapsuleMRP}) = Cint(1)
+shape_type(::Union{Cylinder,CylinderMRP}) = Cint(2)
+shape_type(::Union{Cone,ConeMRP}) = Cint(3)
+shape_type(::Union{Sphere,SphereMRP}) = Cint(4)
+shape_type(::Union{Ellipsoid,EllipsoidMRP}) = Cint(5)
+shape_type(::Union{Polygon,PolygonMRP}) = Cint(6)
+shape_params(P::Union{Polytope,PolytopeMRP}) = vcat(Float64(length(P.b)), _rowmajor(P.A), collect(P.b), _tail(P))
+shape_params(P::Union{Capsule,CapsuleMRP,Cylinder,CylinderMRP}) = vcat(P.R, P.L, _tail(P))
+shape_params(P::Union{Cone,ConeMRP}) = vcat(P.H, P.β, _tail(P))
+shape_params(P::Union{Sphere,SphereMRP}) = vcat(P.R, _tail(P))
+shape_params(P::Union{Ellipsoid,EllipsoidMRP}) = vcat(_rowmajor(P.U), _tail(P))
+shape_params(P::Union{Polygon,PolygonMRP}) = vcat(Float64(length(P.b)), _rowmajor(P.A), collect(P.b), P.R, _tail(P))
+att(P::AbstractPrimitive) = P.q
+att(P::AbstractPrimitiveMRP) = P.p
+att_kind(::AbstractPrimitive) = ATT_QUAT
+att_kind(::AbstractPrimitiveMRP) = ATT_MRP
+
+"Immutable table of shapes; `ShapeTable(prims)` packs geometry once, poses are passed per query."
+struct ShapeTable
+    types::Vector{Cint}
+    offs::Vector{Int64}
+    params::Vector{Float64}
+end
+function ShapeTable(prims::AbstractVector)
+    types = Cint[]; offs = Int64[]; params = Float64[]
+    for P in prims
+        push!(types, shape_type(P)); push!(offs, length(params)); append!(params, shape_params(P))
+    end
+    return ShapeTable(types, offs, params)
+end
+
+_check(rc) = rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_last_error, _lib[]), Cstring, (Ptr{Cvoid},), _ctx[])))
+
+function set_shapes!(t::ShapeTable)
+    _check(ccall((:dcol_set_shapes, _lib[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Float64}, Int64),
+                 _ctx[], length(t.types), t.types, t.offs, t.params, length(t.params)))
+    return nothing
+end
+
+function __init__()
+    _lib[] = get(ENV, "DCOL_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "differentiablecollisions.jl_b200", "libdcol_b200.so"))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:dcol_create, _lib[]), Cint, (Ref{Ptr{Cvoid}}, Cint), h, parse(Cint, get(ENV, "DCOL_B200_DEVICE", "0")))
+    rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_last_error, _lib[]), Cstring, (Ptr{Cvoid},), C_NULL)))
+    _ctx[] = h[]
+    atexit(() -> ccall((:dcol_destroy, _lib[]), Cvoid, (Ptr{Cvoid},), _ctx[]))
+end
+
+# ---------------------------------------------------------------------------------------------
+# batched API (new): arrays of poses, Julia column-major => r is 3 x n, att is (4|3) x n,
+# J comes back as 4 x nt x n — exactly the C layout, no transposes.
+# ---------------------------------------------------------------------------------------------
+struct BatchResult
+    α::Vector{Float64}
+    x::Matrix{Float64}              # 3 x n  (empty for gradient queries)
+    deriv::Array{Float64}           # gradient: nt x n ; jacobian: 4 x nt x n ; proximity: empty
+    status::Vector{Int32}           # 0 ok, 1 "pdip failed", 2 numerical breakdown
+    iters::Vector{Int32}
+end
+
+function _query(sym::Symbol, shape1::Vector{Int32}, shape2::Vector{Int32}, r1, a1, r2, a2, kind::Cint, pdip_tol::Float64)
+    n = length(shape1)
+    nt = 6 + 2 * size(a1, 1)
+    α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
+    x = Matrix{Float64}(undef, 3, sym === :dcol_proximity_gradient ? 0 : n)
+    if sym === :dcol_proximity
+        deriv = Float64[]
+        _check(ccall((:dcol_proximity, _lib[]), Cint,
+                     (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                     _ctx[], n, shape1, shape2, r1, a1, r2, a2, kind, pdip_tol, MEM_HOST, α, x, status, iters))
+    elseif sym === :dcol_proximity_gradient
+        deriv = Matrix{Float64}(undef, nt, n)
+        _check(ccall((:dcol_proximity_gradient, _lib[]), Cint,
+                     (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                     _ctx[], n, shape1, shape2, r1, a1, r2, a2, kind, pdip_tol, MEM_HOST, α, deriv, status, iters))
+    else
+        deriv = Array{Float64}(undef, 4, nt, n)
+        _check(ccall((:dcol_proximity_jacobian, _lib[]), Cint,
+                     (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                     _ctx[], n, shape1, shape2, r1, a1, r2, a2, kind, pdip_tol, MEM_HOST, α, x, deriv, status, iters))
+    end
+    return BatchResult(α, x, deriv, status, iters)
+end
+
+"`proximity_batch(shape1, shape2, R1, Q1, R2, Q2; pdip_tol)`: shape ids are 0-based rows of the ShapeTable passed to `set_shapes!`."
+proximity_batch(s1, s2, r1::Matrix{Float64}, a1::Matrix{Float64}, r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6) =
+    _query(:dcol_proximity, Int32.(s1), Int32.(s2), r1, a1, r2, a2, size(a1, 1) == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol))
+proximity_gradient_batch(s1, s2, r1::Matrix{Float64}, a1::Matrix{Float64}, r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6) =
+    _query(:dcol_proximity_gradient, Int32.(s1), Int32.(s2), r1, a1, r2, a2, size(a1, 1) == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol))
+proximity_jacobian_batch(s1, s2, r1::Matrix{Float64}, a1::Matrix{Float64}, r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6) =
+    _query(:dcol_proximity_jacobian, Int32.(s1), Int32.(s2), r1, a1, r2, a2, size(a1, 1) == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol))
+
+# ---------------------------------------------------------------------------------------------
+# single-pair drop-in calls: a batch of one through the same entry points
+# ---------------------------------------------------------------------------------------------
+function _single(sym, P1, P2, pdip_tol)
+    set_shapes!(ShapeTable([P1, P2]))
+    col(v) = reshape(collect(Float64, v), :, 1)
+    res = _query(sym, Int32[0], Int32[1], col(P1.r), col(att(P1)), col(P2.r), col(att(P2)), att_kind(P1), Float64(pdip_tol))
+    res.status[1] == 1 && error("pdip failed")                        # static_solver2.jl:188
+    res.status[1] == 0 || throw(DomainError(res.status[1], "numerical breakdown in the conic solver"))
+    return res
+end
+
+for (PT, nt) in ((:AbstractPrimitive, 14), (:AbstractPrimitiveMRP, 12))
+    @eval begin
+        function proximity(prim1::$PT, prim2::$PT; pdip_tol::Float64 = 1e-6, verbose::Bool = false)
+            res = _single(:dcol_proximity, prim1, prim2, pdip_tol)
+            return res.α[1], SVector{3}(res.x[:, 1])
+        end
+        function proximity_gradient(prim1::$PT, prim2::$PT; pdip_tol::Float64 = 1e-6, verbose::Bool = false)
+            res = _single(:dcol_proximity_gradient, prim1, prim2, pdip_tol)
+            return res.α[1], SVector{$nt}(res.deriv[:, 1])
+        end
+        function proximity_jacobian(prim1::$PT, prim2::$PT; pdip_tol::Float64 = 1e-6, verbose::Bool = false)
+            res = _single(:dcol_proximity_jacobian, prim1, prim2, pdip_tol)
+            return res.α[1], SVector{3}(res.x[:, 1]), SMatrix{4,$nt}(res.deriv[:, :, 1])
+        end
+    end
+end
+
+end # module

@@ -8,18 +8,19 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 namespace dcol {
-typedef void (*SolveFn)(QueryParams, int, int);
-SolveFn get_solve_kernel(int c1, int c2, bool jac);   // dcol_kernels_*.cu
+const void* persistent_kernel_ptr(bool jac);                                                          // dcol_dispatch.cu
+cudaError_t launch_persistent(bool jac, int grid, int block, size_t smem, cudaStream_t st, const LaunchTable* tt, int* counter);
 }
 using namespace dcol;
 
 namespace {
 
-constexpr int NSIDE = 8;            // side streams for concurrent class-pair bins
+constexpr int NSIDE = 6;            // side streams: one per shared-memory tier
 constexpr int MAX_KEYS = 4096;      // counting-sort key space
 constexpr int MAX_SMEM = 227 * 1024;
 thread_local std::string g_create_err;
@@ -57,7 +58,8 @@ struct dcol_ctx {
   int max_rows_cls[NCLS] = {};
   DevBuf d_shapes, d_rows, d_cls, d_keymap;
   // per-call scratch
-  DevBuf d_in, d_out, d_perm, d_hist;
+  DevBuf d_in, d_out, d_perm, d_hist, d_tables;
+  int n_sm = 148;
   std::vector<int> h_off;
   int64_t launches = 0;
   double last_ms = -1.0;
@@ -191,6 +193,7 @@ int dcol_create(dcol_ctx** out, int device_id) {
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_k1)) != cudaSuccess) return fail("cudaEventCreate", e);
+  { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount; }
   *out = ctx;
   return 0;
 }
@@ -199,7 +202,7 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -416,12 +419,13 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   // ---- bin pairs by key (device counting sort)
   const int nk = ctx->n_keys;
   CK(ctx->d_perm.need(sizeof(int32_t) * n));
-  CK(ctx->d_hist.need(sizeof(int) * (3 * (size_t)nk + 8)));
+  CK(ctx->d_hist.need(sizeof(int) * (3 * (size_t)nk + 16)));
   int* d_hist = (int*)ctx->d_hist.p;
   int* d_off = d_hist + nk;            // nk+1
   int* d_cursor = d_off + nk + 1;      // nk
   int* d_bad = d_cursor + nk;          // 1
-  CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * (3 * (size_t)nk + 8), S));
+  int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier (<= 6)
+  CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * (3 * (size_t)nk + 16), S));
   const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
   {
     int threads = 256;
@@ -455,26 +459,63 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       k = k2;
     }
   }
-  // ---- launch one solver (+ derivative) kernel per non-empty class pair, spread over side streams
+  // ---- persistent launches: bins grouped into shared-memory tiers by their orthant-row capacity, one launch
+  // per non-empty tier; inside a tier the heaviest bins are queued first so the cheap ones fill the tail
+  static const int tier_cap[] = {8, 16, 32, 64, 128, MAX_SMEM / (NFIELD * (int)sizeof(double) * TILE)};
+  constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
+  std::sort(bins.begin(), bins.end(), [](const Bin& a, const Bin& b) {
+    return (int64_t)a.count * (a.rows_cap + 8) > (int64_t)b.count * (b.rows_cap + 8); });
+  std::vector<LaunchTable> tables;
+  std::vector<int> tier_block;
+  for (int tier = 0; tier < NTIER; tier++) {
+    LaunchTable T;
+    memset(&T, 0, sizeof(T));
+    T.P = P;
+    // CTA size of the tier: as many warps (<= 8) as the row store of tier_cap rows per thread allows
+    int cap_rows = 0;
+    for (const Bin& b : bins) {
+      int need = std::max(b.rows_cap, 1);
+      if (need > tier_cap[NTIER - 1]) { ctx->err = "dcol: too many polytope faces / polygon sides for one pair (shared memory)"; return -3; }
+      if (need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1])) cap_rows = std::max(cap_rows, need);
+    }
+    if (!cap_rows) continue;
+    int warps = std::min(8, MAX_SMEM / (cap_rows * NFIELD * (int)sizeof(double) * 32));
+    warps = std::max(1, warps);
+    if (const char* e = getenv("DCOL_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));   // tuning knob
+    const int tile = 32 * warps;
+    for (const Bin& b : bins) {
+      int need = std::max(b.rows_cap, 1);
+      if (!(need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1]))) continue;
+      int k = T.n_bins++;
+      T.begin[k] = b.begin; T.end[k] = b.begin + b.count; T.cp[k] = b.c1 * NCLS + b.c2;
+      T.tile_prefix[k] = T.n_tiles;
+      T.n_tiles += (b.count + tile - 1) / tile;
+    }
+    T.rows_cap = cap_rows;
+    for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = T.n_tiles;
+    tables.push_back(T);
+    tier_block.push_back(tile);
+  }
+  CK(ctx->d_tables.need(sizeof(LaunchTable) * std::max<size_t>(tables.size(), 1)));
+  if (!tables.empty()) CK(cudaMemcpyAsync(ctx->d_tables.p, tables.data(), sizeof(LaunchTable) * tables.size(), cudaMemcpyHostToDevice, S));
+  const bool jac = (query == Q_JAC);
+  const void* kfn = persistent_kernel_ptr(jac);
   CK(cudaEventRecord(ctx->ev_k0, S));
   CK(cudaEventRecord(ctx->ev_fork, S));
-  int nside = (int)std::min<size_t>(NSIDE, bins.size());
-  for (int i = 0; i < nside; i++) CK(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
-  for (size_t bi = 0; bi < bins.size(); bi++) {
-    const Bin& b = bins[bi];
-    cudaStream_t st = ctx->side[bi % NSIDE];
-    int block = 64;
-    size_t smem = (size_t)std::max(b.rows_cap, 1) * NFIELD * sizeof(double) * block;
-    if (smem > (size_t)MAX_SMEM) { block = 32; smem /= 2; }
-    if (smem > (size_t)MAX_SMEM) { ctx->err = "dcol: too many polytope faces / polygon sides for one pair (shared memory)"; return -3; }
-    SolveFn fn = get_solve_kernel(b.c1, b.c2, query == Q_JAC);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (b.count + block - 1) / block;
-    fn<<<grid, block, smem, st>>>(P, b.begin, b.count);
+  for (size_t ti = 0; ti < tables.size(); ti++) {
+    const LaunchTable& T = tables[ti];
+    cudaStream_t st = (tables.size() == 1) ? S : ctx->side[ti % NSIDE];
+    if (st != S) CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+    const int block = tier_block[ti];
+    size_t smem = (size_t)T.rows_cap * NFIELD * sizeof(double) * block;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, block, smem));
+    int grid = std::min(T.n_tiles, std::max(1, occ) * ctx->n_sm);
+    CK(launch_persistent(jac, grid, block, smem, st, (const LaunchTable*)ctx->d_tables.p + ti, d_counter + ti));
     ctx->launches++;
-    CK(cudaGetLastError());
+    if (st != S) { CK(cudaEventRecord(ctx->ev_join[ti % NSIDE], st)); CK(cudaStreamWaitEvent(S, ctx->ev_join[ti % NSIDE], 0)); }
   }
-  for (int i = 0; i < nside; i++) { CK(cudaEventRecord(ctx->ev_join[i], ctx->side[i])); CK(cudaStreamWaitEvent(S, ctx->ev_join[i], 0)); }
   CK(cudaEventRecord(ctx->ev_k1, S));
 
   // ---- results back

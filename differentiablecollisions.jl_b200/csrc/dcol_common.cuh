@@ -44,7 +44,7 @@ struct DevShape {
 
 constexpr int MAX_ITERS = 50;   // static_solver2.jl:132
 constexpr int NFIELD = 5;       // per-row shared-memory fields
-enum { F_S = 0, F_Z = 1, F_IS = 2, F_RZ = 3, F_P = 4 };
+enum { F_S = 0, F_Z = 1, F_R = 2, F_RZ = 3, F_P = 4 };   // s, z, 1/(s z), rz | ds, p | dz
 
 struct QueryParams {
   const DevShape* shapes;
@@ -59,6 +59,23 @@ struct QueryParams {
   double* alpha; double* x; int32_t* status; int32_t* iters;
   double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major
   int query;
+};
+
+
+// Work description of one persistent launch (lives in global memory, written by the host per call).
+// Tiles are warp-sized (32 consecutive sorted positions of one class-pair bin); tiles of a bin are
+// contiguous in the queue and bins are queued heaviest first, so at any moment the warps in flight
+// execute (nearly) the same specialisation — instruction-cache friendly — and only the end of the
+// queue has a tail.
+constexpr int MAX_BINS = NCLS * NCLS;
+constexpr int TILE = 32;
+struct LaunchTable {
+  QueryParams P;
+  int n_bins, n_tiles, rows_cap, pad_;
+  int tile_prefix[MAX_BINS + 1];   // first tile of bin b
+  int begin[MAX_BINS];             // sorted-position range of bin b
+  int end[MAX_BINS];
+  int cp[MAX_BINS];                // class pair c1*NCLS + c2
 };
 
 }  // namespace dcol

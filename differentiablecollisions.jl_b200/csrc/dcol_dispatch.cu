@@ -1,14 +1,62 @@
-// Kernel lookup by (class1, class2, variant).
+// Persistent proximity kernels: every warp pulls 32-pair tiles from a global queue and dispatches to
+// the class-pair specialisation of the tile's bin (device-linked entries from dcol_kernels_c*.cu).
 #include "dcol_common.cuh"
+#include <cuda_runtime.h>
+
 namespace dcol {
-typedef void (*SolveFn)(QueryParams, int, int);
-SolveFn solve_row_0(int, bool); SolveFn solve_row_1(int, bool); SolveFn solve_row_2(int, bool);
-SolveFn solve_row_3(int, bool); SolveFn solve_row_4(int, bool); SolveFn solve_row_5(int, bool);
-SolveFn get_solve_kernel(int c1, int c2, bool jac) {
-  switch (c1) {
-    case 0: return solve_row_0(c2, jac); case 1: return solve_row_1(c2, jac); case 2: return solve_row_2(c2, jac);
-    case 3: return solve_row_3(c2, jac); case 4: return solve_row_4(c2, jac); case 5: return solve_row_5(c2, jac);
+
+template <int C1, int C2, bool JAC>
+__device__ void solve_entry(const QueryParams* p, int idx, double* warp_smem);   // dcol_kernels_c*.cu
+
+template <int C1, bool JAC>
+__device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, int idx, double* wsm) {
+  switch (c2) {
+    case 0: solve_entry<C1, 0, JAC>(p, idx, wsm); break;
+    case 1: solve_entry<C1, 1, JAC>(p, idx, wsm); break;
+    case 2: solve_entry<C1, 2, JAC>(p, idx, wsm); break;
+    case 3: solve_entry<C1, 3, JAC>(p, idx, wsm); break;
+    case 4: solve_entry<C1, 4, JAC>(p, idx, wsm); break;
+    case 5: solve_entry<C1, 5, JAC>(p, idx, wsm); break;
   }
-  return nullptr;
+}
+
+template <bool JAC>
+__global__ void __launch_bounds__(256, 1) proximity_persistent(const LaunchTable* __restrict__ tt, int* __restrict__ counter) {
+  extern __shared__ double smem[];
+  __shared__ int s_tile;
+  const int n_tiles = tt->n_tiles;
+  const int tile_sz = blockDim.x;
+  for (;;) {
+    __syncthreads();                       // previous tile done: row store and s_tile can be reused
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    int b = 0;
+    while (tile >= __ldg(&tt->tile_prefix[b + 1])) b++;
+    // lanes past the end of the bin redo its last pair (identical stores), so every thread of the CTA
+    // runs the same specialisation and reaches the same barriers
+    const int last = __ldg(&tt->end[b]) - 1;
+    const int idx = min(__ldg(&tt->begin[b]) + (tile - __ldg(&tt->tile_prefix[b])) * tile_sz + (int)threadIdx.x, last);
+    const int cp = __ldg(&tt->cp[b]);
+    const int c1 = cp / NCLS, c2 = cp - c1 * NCLS;
+    switch (c1) {
+      case 0: dispatch_c2<0, JAC>(c2, &tt->P, idx, smem); break;
+      case 1: dispatch_c2<1, JAC>(c2, &tt->P, idx, smem); break;
+      case 2: dispatch_c2<2, JAC>(c2, &tt->P, idx, smem); break;
+      case 3: dispatch_c2<3, JAC>(c2, &tt->P, idx, smem); break;
+      case 4: dispatch_c2<4, JAC>(c2, &tt->P, idx, smem); break;
+      case 5: dispatch_c2<5, JAC>(c2, &tt->P, idx, smem); break;
+    }
+  }
+}
+
+const void* persistent_kernel_ptr(bool jac) {
+  return jac ? (const void*)proximity_persistent<true> : (const void*)proximity_persistent<false>;
+}
+cudaError_t launch_persistent(bool jac, int grid, int block, size_t smem, cudaStream_t st, const LaunchTable* tt, int* counter) {
+  if (jac) proximity_persistent<true><<<grid, block, smem, st>>>(tt, counter);
+  else proximity_persistent<false><<<grid, block, smem, st>>>(tt, counter);
+  return cudaGetLastError();
 }
 }  // namespace dcol

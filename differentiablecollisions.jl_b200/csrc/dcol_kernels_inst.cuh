@@ -1,21 +1,11 @@
-// Explicit instantiation of the proximity kernels for one first-primitive class (DCOL_C1):
+// Explicit instantiation of the per-pair solver entries for one first-primitive class (DCOL_C1):
 // 6 second classes x {solver(+gradient epilogue), solver+Jacobian epilogue}.  Split over six
-// translation units so nvcc compiles them in parallel.
+// translation units (compiled in parallel, relocatable device code) and device-linked.
 #include "dcol_solver.cuh"
 
 namespace dcol {
-typedef void (*SolveFn)(QueryParams, int, int);
-#define DCOL_CAT2(a, b) a##b
-#define DCOL_CAT(a, b) DCOL_CAT2(a, b)
-SolveFn DCOL_CAT(solve_row_, DCOL_C1)(int c2, bool jac) {
-  switch (c2) {
-    case 0: return jac ? solve_kernel<DCOL_C1, 0, true> : solve_kernel<DCOL_C1, 0, false>;
-    case 1: return jac ? solve_kernel<DCOL_C1, 1, true> : solve_kernel<DCOL_C1, 1, false>;
-    case 2: return jac ? solve_kernel<DCOL_C1, 2, true> : solve_kernel<DCOL_C1, 2, false>;
-    case 3: return jac ? solve_kernel<DCOL_C1, 3, true> : solve_kernel<DCOL_C1, 3, false>;
-    case 4: return jac ? solve_kernel<DCOL_C1, 4, true> : solve_kernel<DCOL_C1, 4, false>;
-    case 5: return jac ? solve_kernel<DCOL_C1, 5, true> : solve_kernel<DCOL_C1, 5, false>;
-  }
-  return nullptr;
-}
+#define DCOL_INST(C2) \
+  template __device__ void solve_entry<DCOL_C1, C2, false>(const QueryParams*, int, double*); \
+  template __device__ void solve_entry<DCOL_C1, C2, true>(const QueryParams*, int, double*);
+DCOL_INST(0) DCOL_INST(1) DCOL_INST(2) DCOL_INST(3) DCOL_INST(4) DCOL_INST(5)
 }  // namespace dcol

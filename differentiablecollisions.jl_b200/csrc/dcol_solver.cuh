@@ -14,11 +14,50 @@
 //   * per-row state (s, z, 1/s, rz, scratch) lives in shared memory, strided by
 //     thread so a warp touches consecutive 8-byte words (no bank conflicts);
 //     everything else (y, Gram matrix, SOC blocks, relative pose) is in registers.
+// Warps are independent (persistent warps pulling 32-pair tiles from a queue, dcol_dispatch.cu).
 #pragma once
 #include "dcol_common.cuh"
 #include "dcol_deriv.cuh"
 
+#ifndef DCOL_LOCKSTEP
+#define DCOL_LOCKSTEP 1
+#endif
+#if DCOL_LOCKSTEP
+#define DCOL_VOTE(pred) __syncthreads_or(pred)
+#else
+#define DCOL_VOTE(pred) __any_sync(0xffffffffu, pred)
+#endif
+
 namespace dcol {
+
+// ---------------------------------------------------------------------------
+// branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H,
+// ~20 good bits) + two Newton steps.  No slow-path calls: operands here are positive, normal
+// numbers (failures are flagged by explicit `ok` tests before the result is used), and the
+// straight-line form keeps the solver passes in large basic blocks the scheduler can interleave.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);      // 0.5 - 0.5 x y^2
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 0
+  double r = fast_rsqrt(fmax(x, 1e-300));
+  double sq = x * r;
+  return fma(fma(-sq, sq, x), 0.5 * r, sq);               // one correction step on the product
+}
 
 // r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
 __device__ __forceinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F) {
@@ -60,7 +99,7 @@ __device__ __forceinline__ bool chol_upper(double (&M)[N][N], double (&id)[N]) {
 #pragma unroll
     for (int k = 0; k < j; k++) d -= M[k][j] * M[k][j];
     ok = ok && (d > 0.0);
-    double inv = rsqrt(d);
+    double inv = fast_rsqrt(d);
     id[j] = inv;
     M[j][j] = d * inv;
 #pragma unroll
@@ -169,20 +208,20 @@ __device__ __forceinline__ void soc_gram(const double* sc, const double (&B)[D][
   }
 }
 
-// reference SOC line search (static_solver2.jl:12-26); nu = J(y), sn = sqrt(nu)
+// reference SOC line search (static_solver2.jl:12-26) in reciprocal form: returns m such that the
+// step to the cone boundary is 1/m (m <= 0: no bound).  i = 1/sqrt(J(y)), den = 1/(y0*i + 1).
 template <int D>
-__device__ __forceinline__ double soc_linesearch(const double (&y)[D], const double (&dl)[D], double nu, double sn) {
+__device__ __forceinline__ double soc_linesearch_m(const double (&y)[D], const double (&dl)[D], double i, double den) {
   double zeta = y[0] * dl[0];
 #pragma unroll
-  for (int i = 1; i < D; i++) zeta -= y[i] * dl[i];
-  double isn = 1.0 / sn, inu = 1.0 / nu;
-  double rho0 = zeta * inu;
-  double f = ((zeta * isn) + dl[0]) / (y[0] * isn + 1.0);
+  for (int k = 1; k < D; k++) zeta -= y[k] * dl[k];
+  const double i2 = i * i;
+  const double rho0 = zeta * i2;
+  const double f = (zeta * i + dl[0]) * den * i2;
   double nr = 0.0;
 #pragma unroll
-  for (int i = 1; i < D; i++) { double r = dl[i] * isn - f * (y[i] * inu); nr += r * r; }
-  nr = sqrt(nr);
-  return (nr > rho0) ? fmin(1.0, 1.0 / (nr - rho0)) : 1.0;
+  for (int k = 1; k < D; k++) { double r = dl[k] * i - f * y[k]; nr += r * r; }
+  return fast_sqrt(nr) - rho0;
 }
 
 // ---------------------------------------------------------------------------
@@ -194,9 +233,21 @@ struct Prim {
   const double* rows; int n; int row0;
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
-  double V[DD][DD];                    // Wbar^-1 (= J Wbar J)
-  double ie, ie2, Js, Jz, sJs, sJz;    // 1/eta, 1/eta^2, J(s), J(z) and roots
+  double wb[DD], bb;                   // NT scaling point wbar and 1/(1+wbar0):  Wbar^-1 = J Wbar J (rank-one form)
+  double ie;                           // 1/eta
+  double irs, irz, dens, denz;         // 1/sqrt(J(s)), 1/sqrt(J(z)), 1/(s0*irs+1), 1/(z0*irz+1)  (line searches)
   double lam[DD], rz[DD], v[DD], wc[DD];
+
+  // out = Wbar^-1 t  with Wbar^-1 = [wb0, -wbv'; -wbv, I + bb wbv wbv']
+  __device__ __forceinline__ void applyV(const double (&t)[DD], double (&out)[DD]) const {
+    double c = 0.0;
+#pragma unroll
+    for (int i = 1; i < D; i++) c += wb[i] * t[i];
+    out[0] = wb[0] * t[0] - c;
+    const double f = bb * c - t[0];
+#pragma unroll
+    for (int i = 1; i < D; i++) out[i] = t[i] + wb[i] * f;
+  }
 
   __device__ __forceinline__ void load(const DevShape* S, const double* rows_base, int row0_) {
     n = S->n_ort; rows = rows_base + S->rows_off; row0 = row0_;
@@ -273,216 +324,222 @@ struct Prim {
     return sz;
   }
 
+  // Every pass is split into its orthant-row loop and its SOC part so that solve_pair can run the row
+  // loops of both primitives first and then the two (independent) straight-line SOC parts back to back,
+  // which lets the scheduler interleave them.
+
   // ---- pass A: residual rz = s - u(yh), scalings, N = C' W^-2 C, g = C' W^-2 rz
-  __device__ __forceinline__ bool passA(const RowStore& rs, const double (&yh)[NV], double (&N)[NV][NV], double (&g)[NV]) {
-    bool ok = true;
+  __device__ __forceinline__ void passA_rows(const RowStore& rs, const double (&yh)[NV], double (&N)[NV][NV], double (&g)[NV]) {
 #pragma unroll
     for (int a = 0; a < NV; a++) { g[a] = 0.0;
 #pragma unroll
       for (int b = a; b < NV; b++) N[a][b] = 0.0; }
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
       for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
-      double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i);
+      const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i);
       double u = 0.0;
 #pragma unroll
       for (int a = 0; a < NV; a++) u += c[a] * yh[a];
-      double r = si - u;
-      double is = 1.0 / si;
-      double d = zi * is;
-      double dr = d * r;
+      const double r = si - u;
+      const double rr = fast_rcp(si * zi);     // 1/(s z): 1/s = z*rr, 1/z = s*rr
+      const double d = zi * zi * rr;           // z/s
+      const double dr = d * r;
 #pragma unroll
       for (int a = 0; a < NV; a++) {
-        double dc = d * c[a];
+        const double dc = d * c[a];
         g[a] += dr * c[a];
 #pragma unroll
         for (int b = a; b < NV; b++) N[a][b] += dc * c[b];
       }
-      rs(F_IS, row0 + i) = is; rs(F_RZ, row0 + i) = r;
+      rs(F_R, row0 + i) = rr; rs(F_RZ, row0 + i) = r;
     }
+  }
+  __device__ __forceinline__ bool passA_soc(const double (&yh)[NV], double (&N)[NV][NV], double (&g)[NV]) {
     if constexpr (D > 0) {
       double u[D];
       soc_apply<CLS, NV, D>(sc, yh, u);
-      Js = s[0] * s[0]; Jz = z[0] * z[0];
+      double Js = s[0] * s[0], Jz = z[0] * z[0];
       double dot = s[0] * z[0];
 #pragma unroll
       for (int i = 0; i < D; i++) rz[i] = s[i] - u[i];
 #pragma unroll
       for (int i = 1; i < D; i++) { Js -= s[i] * s[i]; Jz -= z[i] * z[i]; dot += s[i] * z[i]; }
-      ok = ok && (Js > 0.0) && (Jz > 0.0);
+      const bool ok = (Js > 0.0) && (Jz > 0.0);
       // Nesterov-Todd scaling (NT_scaling_chol_2.jl:95-112)
-      double irs = rsqrt(Js), irz = rsqrt(Jz);
-      sJs = Js * irs; sJz = Jz * irz;
-      double gam = sqrt(0.5 * (1.0 + dot * irs * irz));
-      double kk = 0.5 / gam;
-      double wb[D];
+      irs = fast_rsqrt(Js); irz = fast_rsqrt(Jz);
+      dens = fast_rcp(s[0] * irs + 1.0); denz = fast_rcp(z[0] * irz + 1.0);
+      const double kk = 0.5 * fast_rsqrt(0.5 * (1.0 + dot * irs * irz));     // 1/(2 gamma)
       wb[0] = kk * (s[0] * irs + z[0] * irz);
 #pragma unroll
       for (int i = 1; i < D; i++) wb[i] = kk * (s[i] * irs - z[i] * irz);
-      double bb = 1.0 / (wb[0] + 1.0);
-      double eta = sqrt(sJs * irz);          // (J(s)/J(z))^(1/4)
-      ie = sqrt(sJz * irs); ie2 = ie * ie;    // 1/eta
+      bb = fast_rcp(wb[0] + 1.0);
+      const double x = irs * (Jz * irz);          // sqrt(J(z)/J(s)) = 1/eta^2
+      const double eta = fast_rsqrt(x);           // (J(s)/J(z))^(1/4)
+      ie = x * eta;
+      const double ie2 = x;
       // lambda = W z = eta * Wbar z
       double wz = 0.0;
 #pragma unroll
       for (int i = 1; i < D; i++) wz += wb[i] * z[i];
       lam[0] = eta * (wb[0] * z[0] + wz);
+      const double fz = z[0] + bb * wz;
 #pragma unroll
-      for (int i = 1; i < D; i++) lam[i] = eta * (wb[i] * z[0] + z[i] + bb * wz * wb[i]);
-      // V = Wbar^-1 = J Wbar J
-      V[0][0] = wb[0];
+      for (int i = 1; i < D; i++) lam[i] = eta * (z[i] + wb[i] * fz);
+      // Vsq = V'V with V = Wbar^-1, expanded entrywise (a Gram product: PSD to round-off, no use of
+      // the identity wb0^2 - |wbv|^2 = 1, which loses accuracy as the iterates approach the boundary)
+      double nw = 0.0;
 #pragma unroll
-      for (int i = 1; i < D; i++) { V[0][i] = -wb[i]; V[i][0] = -wb[i];
-#pragma unroll
-        for (int j = 1; j < D; j++) V[i][j] = ((i == j) ? 1.0 : 0.0) + bb * wb[i] * wb[j]; }
-      // Vsq = V'V (a Gram product, so the KKT block stays PSD to round-off); local to this pass
+      for (int i = 1; i < D; i++) nw += wb[i] * wb[i];
+      const double c0 = wb[0] + 1.0 + bb * nw;
+      const double c1 = 1.0 + bb * (2.0 + bb * nw);
       double Vsq[D][D];
+      Vsq[0][0] = wb[0] * wb[0] + nw;
 #pragma unroll
-      for (int i = 0; i < D; i++)
+      for (int i = 1; i < D; i++) { Vsq[0][i] = -wb[i] * c0; Vsq[i][0] = Vsq[0][i];
 #pragma unroll
-        for (int j = i; j < D; j++) { double a = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; k++) a += V[i][k] * V[k][j];
-          Vsq[i][j] = a; Vsq[j][i] = a; }
-      // t2 = W^-2 rz as two applications of W^-1 (never through the squared matrix: its condition
-      // number is cond(W)^2 and the iterates near convergence need the scaled-space accuracy)
+        for (int j = i; j < D; j++) { double e = c1 * wb[i] * wb[j] + ((i == j) ? 1.0 : 0.0); Vsq[i][j] = e; Vsq[j][i] = e; } }
+      // t2 = W^-2 rz as two applications of W^-1 (scaled-space accuracy)
       double t1[D], t2[D];
+      applyV(rz, t1); applyV(t1, t2);
 #pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * rz[k];
-        t1[i] = a; }
-#pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * t1[k];
-        t2[i] = ie2 * a; }
+      for (int i = 0; i < D; i++) t2[i] *= ie2;
       soc_applyT<CLS, NV, D>(sc, t2, g);
       soc_gram<CLS, NV, D>(sc, Vsq, ie2, N);
+      return ok;
+    } else {
+      return true;
     }
-    return ok;
   }
 
-  // ---- pass B: affine direction; step-to-boundary ratios; sums for rho; Mehrotra correction term
-  __device__ __forceinline__ void passB(const RowStore& rs, const double (&dyh)[NV], double& a_s, double& a_z, double& dot1, double& dot2) {
+  // ---- pass B: affine direction; step bounds (reciprocal form: m = max -d/y); sums for rho; Mehrotra correction
+  __device__ __forceinline__ void passB_rows(const RowStore& rs, const double (&dyh)[NV], double& m_s, double& m_z, double& dot1, double& dot2) {
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
 #pragma unroll
       for (int a = 0; a < NV; a++) cd += __ldg(rows + i * NV + a) * dyh[a];
-      double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), is = rs(F_IS, row0 + i), r = rs(F_RZ, row0 + i);
-      double t = r - cd;
-      double dsa = -t, dza = zi * is * t - zi;
-      if (dsa < 0.0) a_s = fmin(a_s, -si / dsa);
-      if (dza < 0.0) a_z = fmin(a_z, -zi / dza);
-      double p = dsa * dza;
-      rs(F_P, row0 + i) = p;
-      dot1 += si * dza + zi * dsa; dot2 += p;
+      const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i);
+      const double t = r - cd;                  // -ds
+      const double is = zi * rr;
+      const double q = is * t;                  // -ds/s  and  1 + dz/z
+      const double dza = zi * q - zi;
+      m_s = fmax(m_s, q); m_z = fmax(m_z, 1.0 - q);
+      const double pp = -t * dza;
+      rs(F_P, row0 + i) = pp;
+      dot1 += si * dza - zi * t; dot2 += pp;
     }
+  }
+  __device__ __forceinline__ void passB_soc(const double (&dyh)[NV], double& m_s, double& m_z, double& dot1, double& dot2) {
     if constexpr (D > 0) {
-      double cd[D], t[D], dsa[D], dza[D];
+      double cd[D], t[D], dsa[D], dza[D], w[D];
       soc_apply<CLS, NV, D>(sc, dyh, cd);
 #pragma unroll
       for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; dsa[i] = -t[i]; }
-      // v = W^-1 t ; dza = W^-1 (v - lambda)  [= W^-2 t - z, with the subtraction done in the scaled space]
+      // v = W^-1 t ; dza = W^-1 (v - lambda)  [= W^-2 t - z, subtraction done in the scaled space]
+      applyV(t, v);
 #pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
+      for (int i = 0; i < D; i++) { v[i] *= ie; w[i] = v[i] - lam[i]; }
+      applyV(w, dza);
 #pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * t[k];
-        v[i] = ie * a; }
-#pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * (v[k] - lam[k]);
-        dza[i] = ie * a; }
-      a_s = fmin(a_s, soc_linesearch<D>(s, dsa, Js, sJs));
-      a_z = fmin(a_z, soc_linesearch<D>(z, dza, Jz, sJz));
+      for (int i = 0; i < D; i++) dza[i] *= ie;
+      m_s = fmax(m_s, soc_linesearch_m<D>(s, dsa, irs, dens));
+      m_z = fmax(m_z, soc_linesearch_m<D>(z, dza, irz, denz));
 #pragma unroll
       for (int i = 0; i < D; i++) { dot1 += s[i] * dza[i] + z[i] * dsa[i]; dot2 += dsa[i] * dza[i]; }
       // -(W^-1 dsa) o (W dza) = v o (v - lambda)   (static_solver2.jl:164)
       double c0 = 0.0;
 #pragma unroll
-      for (int i = 0; i < D; i++) c0 += v[i] * (v[i] - lam[i]);
+      for (int i = 0; i < D; i++) c0 += v[i] * w[i];
       wc[0] = c0;
 #pragma unroll
-      for (int i = 1; i < D; i++) wc[i] = v[0] * (v[i] - lam[i]) + (v[0] - lam[0]) * v[i];
+      for (int i = 1; i < D; i++) wc[i] = v[0] * w[i] + w[0] * v[i];
     }
   }
 
   // ---- pass C: corrector right-hand side  g2 = C' [ (sigma*mu - p)/s | W^-1 (lambda \ corr) ]
-  __device__ __forceinline__ void passC(const RowStore& rs, double sigmu, double (&g2)[NV]) {
+  __device__ __forceinline__ void passC_rows(const RowStore& rs, double sigmu, double (&g2)[NV]) {
 #pragma unroll
     for (int a = 0; a < NV; a++) g2[a] = 0.0;
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
-      double q = (sigmu - rs(F_P, row0 + i)) * rs(F_IS, row0 + i);
+      const double q = (sigmu - rs(F_P, row0 + i)) * rs(F_Z, row0 + i) * rs(F_R, row0 + i);
 #pragma unroll
       for (int a = 0; a < NV; a++) g2[a] += q * __ldg(rows + i * NV + a);
     }
+  }
+  __device__ __forceinline__ void passC_soc(double sigmu, double (&g2)[NV]) {
     if constexpr (D > 0) {
       wc[0] += sigmu;
-      // kappa = lambda \ corr  (soc_utils.jl:52-67)
-      double rho = lam[0] * lam[0], nu = 0.0;
+      double kap[D], wk[D];
+      soc_jdiv_fast(lam, wc, kap);              // kappa = lambda \ corr  (soc_utils.jl:52-67)
+      applyV(kap, wk);
 #pragma unroll
-      for (int i = 1; i < D; i++) { rho -= lam[i] * lam[i]; nu += lam[i] * wc[i]; }
-      double irho = 1.0 / rho, il0 = 1.0 / lam[0];
-      double kap[D];
-      kap[0] = irho * (lam[0] * wc[0] - nu);
-#pragma unroll
-      for (int i = 1; i < D; i++) kap[i] = irho * ((nu * il0 - wc[0]) * lam[i] + (rho * il0) * wc[i]);
-      double wk[D];
-#pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * kap[k];
-        wk[i] = ie * a; wc[i] = kap[i]; }
+      for (int i = 0; i < D; i++) { wk[i] *= ie; wc[i] = kap[i]; }
       soc_applyT<CLS, NV, D>(sc, wk, g2);
     }
   }
+  __device__ __forceinline__ void soc_jdiv_fast(const double (&l)[DD], const double (&w)[DD], double (&out)[DD]) const {
+    double rho = l[0] * l[0], nu = 0.0;
+#pragma unroll
+    for (int i = 1; i < D; i++) { rho -= l[i] * l[i]; nu += l[i] * w[i]; }
+    const double il0 = fast_rcp(l[0]);
+    const double irho = fast_rcp(rho);
+    out[0] = irho * (l[0] * w[0] - nu);
+    const double f1 = irho * (nu * il0 - w[0]);
+#pragma unroll
+    for (int i = 1; i < D; i++) out[i] = f1 * l[i] + il0 * w[i];
+  }
 
-  // ---- pass D: final direction and step-to-boundary ratios; directions parked in F_RZ/F_P (rows) and rz/v (SOC)
-  __device__ __forceinline__ void passD(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& a_s, double& a_z) {
+  // ---- pass D: final direction and step bounds; directions parked in F_RZ/F_P (rows) and rz/v (SOC)
+  __device__ __forceinline__ void passD_rows(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& m_s, double& m_z) {
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
 #pragma unroll
       for (int a = 0; a < NV; a++) cd += __ldg(rows + i * NV + a) * dyh[a];
-      double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), is = rs(F_IS, row0 + i), r = rs(F_RZ, row0 + i), p = rs(F_P, row0 + i);
-      double t = r - cd;
-      double ds = -t, dz = (zi * t + sigmu - p) * is - zi;
-      if (ds < 0.0) a_s = fmin(a_s, -si / ds);
-      if (dz < 0.0) a_z = fmin(a_z, -zi / dz);
-      rs(F_RZ, row0 + i) = ds; rs(F_P, row0 + i) = dz;
+      const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i), pp = rs(F_P, row0 + i);
+      const double t = r - cd;
+      const double is = zi * rr, iz = si * rr;
+      const double dz = (zi * t + sigmu - pp) * is - zi;
+      m_s = fmax(m_s, t * is); m_z = fmax(m_z, -dz * iz);
+      rs(F_RZ, row0 + i) = -t; rs(F_P, row0 + i) = dz;
     }
+  }
+  __device__ __forceinline__ void passD_soc(const double (&dyh)[NV], double& m_s, double& m_z) {
     if constexpr (D > 0) {
-      double cd[D], t[D], ds[D], dz[D];
+      double cd[D], t[D], ds[D], dz[D], v2[D];
       soc_apply<CLS, NV, D>(sc, dyh, cd);
 #pragma unroll
       for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; ds[i] = -t[i]; }
       // dz = W^-1 (W^-1 t - lambda + kappa)   (scaled-space accumulation, static_solver2.jl:165-168)
-      double v2[D];
+      applyV(t, v2);
 #pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
+      for (int i = 0; i < D; i++) v2[i] = ie * v2[i] - lam[i] + wc[i];
+      applyV(v2, dz);
 #pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * t[k];
-        v2[i] = ie * a - lam[i] + wc[i]; }
-#pragma unroll
-      for (int i = 0; i < D; i++) { double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; k++) a += V[i][k] * v2[k];
-        dz[i] = ie * a; }
-      a_s = fmin(a_s, soc_linesearch<D>(s, ds, Js, sJs));
-      a_z = fmin(a_z, soc_linesearch<D>(z, dz, Jz, sJz));
+      for (int i = 0; i < D; i++) dz[i] *= ie;
+      m_s = fmax(m_s, soc_linesearch_m<D>(s, ds, irs, dens));
+      m_z = fmax(m_z, soc_linesearch_m<D>(z, dz, irz, denz));
 #pragma unroll
       for (int i = 0; i < D; i++) { rz[i] = ds[i]; v[i] = dz[i]; }
     }
   }
 
   // ---- pass E: take the step; returns the new s.z
-  __device__ __forceinline__ double passE(const RowStore& rs, double al) {
+  __device__ __forceinline__ double passE_rows(const RowStore& rs, double al) {
     double sz = 0.0;
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
       double a = rs(F_S, row0 + i) + al * rs(F_RZ, row0 + i), b = rs(F_Z, row0 + i) + al * rs(F_P, row0 + i);
       rs(F_S, row0 + i) = a; rs(F_Z, row0 + i) = b; sz += a * b;
     }
+    return sz;
+  }
+  __device__ __forceinline__ double passE_soc(double al) {
+    double sz = 0.0;
     if constexpr (D > 0) {
 #pragma unroll
       for (int i = 0; i < D; i++) { s[i] += al * rz[i]; z[i] += al * v[i]; sz += s[i] * z[i]; }
@@ -710,54 +767,72 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, double
   }
 
   // ---------------- main loop (static_solver2.jl:132-187) ----------------
+  // All warps of the CTA step through the iterations together (one block-wide vote per iteration):
+  // the unrolled loop body is far larger than the SM's instruction cache, and warps in lockstep
+  // share each fetched instruction line instead of streaming the loop once per warp.
   int it = 0;
-  if (status == ST_OK) {
-    status = ST_PDIP_FAILED;
-    for (; it <= MAX_ITERS; it++) {
-      double mu = sz * inv_deg;
-      if (!(mu == mu)) { status = ST_NUMERICAL; break; }
-      if (mu < p.pdip_tol) { status = ST_OK; break; }
-      if (it == MAX_ITERS) break;
+  bool active = (status == ST_OK);
+  if (active) status = ST_PDIP_FAILED;
+  for (int k = 0;; k++) {
+    const double mu = sz * inv_deg;
+    if (active) {
+      if (!(mu == mu)) { status = ST_NUMERICAL; active = false; it = k; }
+      else if (mu < p.pdip_tol) { status = ST_OK; active = false; it = k; }
+      else if (k == MAX_ITERS) { active = false; it = k; }
+    }
+    if (!DCOL_VOTE(active)) break;
+    if (active) {
       double rhs[NX], dy[NX];
       double y1[NV1], y2[NV2];
       bool ok;
       {
         double N1[NV1][NV1], g1[NV1], N2[NV2][NV2], g2[NV2];
         PM::to_local(y, R, t, true, y1, y2);
-        ok = A.passA(rs, y1, N1, g1);
-        ok = B.passA(rs, y2, N2, g2) && ok;
+        A.passA_rows(rs, y1, N1, g1);
+        B.passA_rows(rs, y2, N2, g2);
+        ok = A.passA_soc(y1, N1, g1);
+        ok = B.passA_soc(y2, N2, g2) && ok;
         PM::assemble(N1, N2, R, M);
         PM::assemble_vec(g1, g2, R, rhs);
       }
       rhs[3] -= 1.0;                              // -c
       ok = chol_upper<NX>(M, idg) && ok;
-      if (!ok) { status = ST_NUMERICAL; break; }
-      chol_solve<NX>(M, idg, rhs, dy);            // affine direction
-      double a_s = 1.0, a_z = 1.0, dot1 = 0.0, dot2 = 0.0;
-      PM::to_local(dy, R, t, false, y1, y2);
-      A.passB(rs, y1, a_s, a_z, dot1, dot2);
-      B.passB(rs, y2, a_s, a_z, dot1, dot2);
-      double aa = fmin(a_s, a_z);                 // :159
-      double rho = (sz + aa * (dot1 + aa * dot2)) / sz;
-      double sig = fmax(0.0, fmin(1.0, rho)); sig = sig * sig * sig;   // :161
-      double sigmu = sig * mu;
-      {
-        double g1[NV1], g2[NV2], rc[NX];
-        A.passC(rs, sigmu, g1);
-        B.passC(rs, sigmu, g2);
-        PM::assemble_vec(g1, g2, R, rc);
+      if (!ok) { status = ST_NUMERICAL; active = false; it = k; }
+      else {
+        chol_solve<NX>(M, idg, rhs, dy);            // affine direction
+        double m_s = 0.0, m_z = 0.0, dot1 = 0.0, dot2 = 0.0;
+        PM::to_local(dy, R, t, false, y1, y2);
+        A.passB_rows(rs, y1, m_s, m_z, dot1, dot2);
+        B.passB_rows(rs, y2, m_s, m_z, dot1, dot2);
+        A.passB_soc(y1, m_s, m_z, dot1, dot2);
+        B.passB_soc(y2, m_s, m_z, dot1, dot2);
+        const double aa = fast_rcp(fmax(1.0, fmax(m_s, m_z)));   // min(1, step to the boundary)  :159
+        const double rho = (sz + aa * (dot1 + aa * dot2)) * fast_rcp(sz);
+        double sig = fmax(0.0, fmin(1.0, rho)); sig = sig * sig * sig;   // :161
+        const double sigmu = sig * mu;
+        {
+          double g1[NV1], g2[NV2], rc[NX];
+          A.passC_rows(rs, sigmu, g1);
+          B.passC_rows(rs, sigmu, g2);
+          A.passC_soc(sigmu, g1);
+          B.passC_soc(sigmu, g2);
+          PM::assemble_vec(g1, g2, R, rc);
 #pragma unroll
-        for (int a = 0; a < NX; a++) rhs[a] += rc[a];
+          for (int a = 0; a < NX; a++) rhs[a] += rc[a];
+        }
+        chol_solve<NX>(M, idg, rhs, dy);            // combined direction
+        m_s = 0.0; m_z = 0.0;
+        PM::to_local(dy, R, t, false, y1, y2);
+        A.passD_rows(rs, y1, sigmu, m_s, m_z);
+        B.passD_rows(rs, y2, sigmu, m_s, m_z);
+        A.passD_soc(y1, m_s, m_z);
+        B.passD_soc(y2, m_s, m_z);
+        const double al = 0.99 * fast_rcp(fmax(1.0, fmax(m_s, m_z)));   // min(1, 0.99 * step to the boundary)  :172
+#pragma unroll
+        for (int a = 0; a < NX; a++) y[a] += al * dy[a];
+        sz = A.passE_rows(rs, al) + B.passE_rows(rs, al);
+        sz += A.passE_soc(al) + B.passE_soc(al);
       }
-      chol_solve<NX>(M, idg, rhs, dy);            // combined direction
-      a_s = 1.0; a_z = 1.0;
-      PM::to_local(dy, R, t, false, y1, y2);
-      A.passD(rs, y1, sigmu, a_s, a_z);
-      B.passD(rs, y2, sigmu, a_s, a_z);
-      double al = fmin(1.0, 0.99 * fmin(a_s, a_z));   // :172
-#pragma unroll
-      for (int a = 0; a < NX; a++) y[a] += al * dy[a];
-      sz = A.passE(rs, al) + B.passE(rs, al);
     }
   }
 
@@ -893,12 +968,11 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, double
   if (p.status) p.status[pair] = status;
 }
 
+// Out-of-line entry of one specialisation (separate compilation: each class row lives in its own
+// translation unit and is device-linked into the persistent kernels of dcol_dispatch.cu).
 template <int C1, int C2, bool JAC>
-__global__ void solve_kernel(QueryParams p, int bin_begin, int bin_count) {
-  extern __shared__ double smem[];
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= bin_count) return;
-  solve_pair<C1, C2, JAC>(p, bin_begin + j, smem);
+__device__ __noinline__ void solve_entry(const QueryParams* p, int idx, double* warp_smem) {
+  solve_pair<C1, C2, JAC>(*p, idx, warp_smem);
 }
 
 }  // namespace dcol

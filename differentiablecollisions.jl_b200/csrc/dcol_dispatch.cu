@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256, 1) proximity_persistent(const LaunchTable
   const int n_tiles = tt->n_tiles;
   const int tile_sz = blockDim.x;
   for (;;) {
+    // one tile per atomic: the whole GPU walks the queue together, so at any moment (nearly) all CTAs run
+    // the same class-pair specialisation and share it in the GPC-level instruction cache
     __syncthreads();                       // previous tile done: row store and s_tile can be reused
     if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1);
     __syncthreads();

@@ -59,26 +59,6 @@ __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 
   return fma(fma(-sq, sq, x), 0.5 * r, sq);               // one correction step on the product
 }
 
-// r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
-__device__ __forceinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F) {
-  double Qn[3][3];
-  if (att_kind == 0) { double q[4] = {att[0], att[1], att[2], att[3]}; dcm_from_q<double>(q, Qn); }
-  else { double p[3] = {att[0], att[1], att[2]}; dcm_from_mrp<double>(p, Qn); }
-  if (S->has_offset) {
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      F.r[i] = r[i] + Qn[i][0] * S->r_off[0] + Qn[i][1] * S->r_off[1] + Qn[i][2] * S->r_off[2];
-#pragma unroll
-      for (int j = 0; j < 3; j++) F.Q[i][j] = Qn[i][0] * S->Q_off[j] + Qn[i][1] * S->Q_off[3 + j] + Qn[i][2] * S->Q_off[6 + j];
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 3; i++) { F.r[i] = r[i];
-#pragma unroll
-      for (int j = 0; j < 3; j++) F.Q[i][j] = Qn[i][j]; }
-  }
-}
-
 // ---------------------------------------------------------------------------
 // shared-memory row store: field f of row i of this thread
 // ---------------------------------------------------------------------------

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdcol_b200.so")
+LIB_PATH = os.environ.get("DCOL_B200_LIB") or os.path.join(_HERE, "libdcol_b200.so")
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)

@@ -3,6 +3,9 @@
 // Entry points are declared in include/dcol_b200.h.
 #include "../../include/dcol_b200.h"
 #include "dcol_common.cuh"
+#ifndef DCOL_MAXTHREADS
+#define DCOL_MAXTHREADS 256
+#endif
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -57,10 +60,16 @@ struct dcol_ctx {
   int n_keys = 0; bool use_keymap = false;
   int max_rows_cls[NCLS] = {};
   DevBuf d_shapes, d_rows, d_cls, d_keymap;
-  // per-call scratch
+  // static launch plan derived from the shape table (dcol_set_shapes): one entry per shared-memory tier
+  struct Tier { int n_bins = 0, rows_cap = 0, block = 0; size_t smem = 0; int grid[2] = {0, 0};
+                int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; };
+  std::vector<Tier> tiers;
+  // per-call scratch (one slot per pipelined chunk)
+  static constexpr int MAX_CHUNKS = 8;
   DevBuf d_in, d_out, d_perm, d_hist, d_tables;
+  cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
   int n_sm = 148;
-  std::vector<int> h_off;
   int64_t launches = 0;
   double last_ms = -1.0;
   cudaStream_t stream() const { return user ? user : own; }
@@ -141,6 +150,25 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
   }
 }
 
+// single block: turns the static per-tier bin lists (key ranges parked in begin[]/end[]) into sorted-position ranges
+// and tile prefixes, from the bin offsets of this call — the host never needs the histogram.
+__global__ void k_build_tables(LaunchTable* __restrict__ tables, int n_tiers, const int* __restrict__ tile_sz,
+                               const int* __restrict__ off) {
+  const int t = threadIdx.x;
+  if (t >= n_tiers) return;
+  LaunchTable& T = tables[t];
+  const int tile = tile_sz[t];
+  int tiles = 0;
+  for (int k = 0; k < T.n_bins; k++) {
+    const int b = off[T.begin[k]], e = off[T.end[k]];
+    T.begin[k] = b; T.end[k] = e;
+    T.tile_prefix[k] = tiles;
+    tiles += (e - b + tile - 1) / tile;
+  }
+  for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
+  T.n_tiles = tiles;
+}
+
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -191,6 +219,15 @@ int dcol_create(dcol_ctx** out, int device_id) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   }
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_t0[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_t1[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+  }
   if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_k1)) != cudaSuccess) return fail("cudaEventCreate", e);
   { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount; }
@@ -205,6 +242,15 @@ void dcol_destroy(dcol_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_t0[i]) cudaEventDestroy(ctx->ev_t0[i]);
+    if (ctx->ev_t1[i]) cudaEventDestroy(ctx->ev_t1[i]);
+  }
+  if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
@@ -314,6 +360,52 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   }
   ctx->h_shapes = hs;
   ctx->n_shapes = n_shapes;
+
+  // ---- static launch plan: class pairs present in the table, grouped into shared-memory tiers by the orthant-row
+  // capacity a pair of that class pair can need; inside a tier the heaviest class pairs are queued first
+  ctx->tiers.clear();
+  {
+    static const int tier_cap[] = {8, 16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32)};
+    constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
+    bool present[NCLS] = {};
+    for (int i = 0; i < n_shapes; i++) present[cls[i]] = true;
+    // first key of every class pair (keys are class-pair major); key_first[cp+1] closes the range
+    std::vector<int> key_first(NCLS * NCLS + 1, ctx->n_keys);
+    for (int k = ctx->n_keys - 1; k >= 0; k--) key_first[ctx->key_cp[k]] = k;
+    for (int cp = NCLS * NCLS - 1; cp >= 0; cp--) if (key_first[cp] == ctx->n_keys || key_first[cp] > key_first[cp + 1]) key_first[cp] = key_first[cp + 1];
+    for (int tier = 0; tier < NTIER; tier++) {
+      dcol_ctx::Tier T;
+      std::vector<std::pair<int, int>> members;   // (weight, cp)
+      for (int c1 = 0; c1 < NCLS; c1++) for (int c2 = 0; c2 < NCLS; c2++) {
+        if (!present[c1] || !present[c2]) continue;
+        int need = std::max(1, ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]);
+        if (need > tier_cap[NTIER - 1]) { ctx->err = "dcol_set_shapes: too many polytope faces / polygon sides for one pair (shared memory)"; ctx->n_shapes = 0; return -3; }
+        if (!(need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1]))) continue;
+        int weight = need + 6 * (cls_d(c1) + cls_d(c2)) + 8 * (cls_ne(c1) + cls_ne(c2));
+        members.push_back({-weight, c1 * NCLS + c2});
+        T.rows_cap = std::max(T.rows_cap, need);
+      }
+      if (members.empty()) continue;
+      std::sort(members.begin(), members.end());
+      for (auto& m : members) {
+        int k = T.n_bins++;
+        T.cp[k] = m.second; T.key_begin[k] = key_first[m.second]; T.key_end[k] = key_first[m.second + 1];
+      }
+      int warps = std::min(DCOL_MAXTHREADS / 32, (MAX_SMEM - 1024) / (T.rows_cap * NFIELD * (int)sizeof(double) * 32));
+      warps = std::max(1, warps);
+      if (const char* e = getenv("DCOL_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));   // tuning knob
+      T.block = 32 * warps;
+      T.smem = (size_t)T.rows_cap * NFIELD * sizeof(double) * T.block;
+      for (int jac = 0; jac < 2; jac++) {
+        const void* kfn = persistent_kernel_ptr(jac != 0);
+        if (T.smem > 48 * 1024) CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_SMEM - 1024)));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, T.block, T.smem));
+        T.grid[jac] = std::max(1, occ) * ctx->n_sm;
+      }
+      ctx->tiers.push_back(T);
+    }
+  }
   return 0;
 }
 
@@ -367,19 +459,29 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (query == Q_JAC && !x) { ctx->err = "dcol_proximity_jacobian: x is NULL"; return -1; }
   if (query == Q_JAC && mem == DCOL_MEM_DEVICE && ((uintptr_t)deriv & 15)) { ctx->err = "dcol_proximity_jacobian: J must be 16-byte aligned"; return -1; }
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t S = ctx->stream();
   const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3;
   const int nt = 6 + 2 * na;
   const size_t dsz = (query == Q_GRAD) ? (size_t)nt : (query == Q_JAC ? (size_t)4 * nt : 0);
 
-  QueryParams P;
-  memset(&P, 0, sizeof(P));
-  P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
-  P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query;
+  // ---- chunking: device-pointer calls run as one chunk; host-pointer calls are split so that the H2D copy of
+  // chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (three streams)
+  int nchunks = 1;
+  if (mem == DCOL_MEM_HOST) {
+    int64_t target = 350000;
+    if (const char* e = getenv("DCOL_CHUNK")) target = std::max<int64_t>(1024, atoll(e));
+    nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(dcol_ctx::MAX_CHUNKS, (n + target / 2) / target));
+  }
+  const int nk = ctx->n_keys;
+  const int nt_tiers = (int)ctx->tiers.size();
+  const size_t hist_ints = 3 * (size_t)nk + 16 + NSIDE;           // hist | off | cursor | bad | counters | tile sizes
+  const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
+  CK(ctx->d_perm.need(sizeof(int32_t) * n));
+  CK(ctx->d_hist.need(sizeof(int) * hist_stride * nchunks));
+  CK(ctx->d_tables.need(sizeof(LaunchTable) * std::max(1, nt_tiers) * nchunks));
 
-  // ---- stage inputs / outputs
   size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
-  size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0, out_bytes = 0;
+  size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0;
+  char* di = nullptr; char* dout = nullptr;
   if (mem == DCOL_MEM_HOST) {
     size_t b = 0;
     o_s1 = b; b += align256(sizeof(int32_t) * n);
@@ -389,147 +491,119 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     o_r2 = b; b += align256(sizeof(double) * 3 * n);
     o_a2 = b; b += align256(sizeof(double) * na * n);
     CK(ctx->d_in.need(b));
-    char* di = (char*)ctx->d_in.p;
-    CK(cudaMemcpyAsync(di + o_s1, shape1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, S));
-    CK(cudaMemcpyAsync(di + o_s2, shape2, sizeof(int32_t) * n, cudaMemcpyHostToDevice, S));
-    CK(cudaMemcpyAsync(di + o_r1, r1, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, S));
-    CK(cudaMemcpyAsync(di + o_a1, att1, sizeof(double) * na * n, cudaMemcpyHostToDevice, S));
-    CK(cudaMemcpyAsync(di + o_r2, r2, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, S));
-    CK(cudaMemcpyAsync(di + o_a2, att2, sizeof(double) * na * n, cudaMemcpyHostToDevice, S));
-    P.shape1 = (const int32_t*)(di + o_s1); P.shape2 = (const int32_t*)(di + o_s2);
-    P.r1 = (const double*)(di + o_r1); P.att1 = (const double*)(di + o_a1);
-    P.r2 = (const double*)(di + o_r2); P.att2 = (const double*)(di + o_a2);
     b = 0;
     o_alpha = b; b += align256(sizeof(double) * n);
     o_x = b; b += align256(sizeof(double) * 3 * n);
     o_der = b; b += align256(sizeof(double) * dsz * n);
     o_st = b; b += align256(sizeof(int32_t) * n);
     o_it = b; b += align256(sizeof(int32_t) * n);
-    out_bytes = b;
-    CK(ctx->d_out.need(out_bytes));
-    char* dout = (char*)ctx->d_out.p;
-    P.alpha = (double*)(dout + o_alpha); P.x = (double*)(dout + o_x);
-    P.deriv = dsz ? (double*)(dout + o_der) : nullptr;
-    P.status = (int32_t*)(dout + o_st); P.iters = (int32_t*)(dout + o_it);
-  } else {
-    P.shape1 = shape1; P.shape2 = shape2; P.r1 = r1; P.att1 = att1; P.r2 = r2; P.att2 = att2;
-    P.alpha = alpha; P.x = x; P.deriv = deriv; P.status = status; P.iters = iters;
+    CK(ctx->d_out.need(b));
+    di = (char*)ctx->d_in.p; dout = (char*)ctx->d_out.p;
   }
-
-  // ---- bin pairs by key (device counting sort)
-  const int nk = ctx->n_keys;
-  CK(ctx->d_perm.need(sizeof(int32_t) * n));
-  CK(ctx->d_hist.need(sizeof(int) * (3 * (size_t)nk + 16)));
-  int* d_hist = (int*)ctx->d_hist.p;
-  int* d_off = d_hist + nk;            // nk+1
-  int* d_cursor = d_off + nk + 1;      // nk
-  int* d_bad = d_cursor + nk;          // 1
-  int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier (<= 6)
-  CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * (3 * (size_t)nk + 16), S));
-  const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
-  {
-    int threads = 256;
-    int blocks = (int)std::min<int64_t>((n + threads * 8 - 1) / (threads * 8), 1184);
-    k_hist<<<blocks, threads, sizeof(int) * nk, S>>>(P.shape1, P.shape2, n, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
-    k_scan<<<1, 1024, 0, S>>>(d_hist, nk, d_off, d_cursor);
-    k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, S>>>(P.shape1, P.shape2, n, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, (int32_t*)ctx->d_perm.p);
-    ctx->launches += 3;
-  }
-  ctx->h_off.resize(nk + 2);
-  CK(cudaMemcpyAsync(ctx->h_off.data(), d_off, sizeof(int) * (nk + 1), cudaMemcpyDeviceToHost, S));
-  CK(cudaMemcpyAsync(ctx->h_off.data() + nk + 1, d_bad, sizeof(int), cudaMemcpyDeviceToHost, S));
-  CK(cudaStreamSynchronize(S));
-  if (ctx->h_off[nk + 1]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; return -1; }
-  P.perm = (const int32_t*)ctx->d_perm.p;
-
-  // class-pair ranges (keys are class-pair major)
-  struct Bin { int c1, c2, begin, count, rows_cap; };
-  std::vector<Bin> bins;
-  {
-    int k = 0;
-    while (k < nk) {
-      int cp = ctx->key_cp[k], k2 = k;
-      while (k2 < nk && ctx->key_cp[k2] == cp) k2++;
-      int begin = ctx->h_off[k], count = ctx->h_off[k2] - begin;
-      if (count > 0) {
-        Bin b; b.c1 = cp / NCLS; b.c2 = cp % NCLS; b.begin = begin; b.count = count;
-        b.rows_cap = ctx->max_rows_cls[b.c1] + ctx->max_rows_cls[b.c2];
-        bins.push_back(b);
-      }
-      k = k2;
-    }
-  }
-  // ---- persistent launches: bins grouped into shared-memory tiers by their orthant-row capacity, one launch
-  // per non-empty tier; inside a tier the heaviest bins are queued first so the cheap ones fill the tail
-  static const int tier_cap[] = {8, 16, 32, 64, 128, MAX_SMEM / (NFIELD * (int)sizeof(double) * TILE)};
-  constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
-  std::sort(bins.begin(), bins.end(), [](const Bin& a, const Bin& b) {
-    return (int64_t)a.count * (a.rows_cap + 8) > (int64_t)b.count * (b.rows_cap + 8); });
-  std::vector<LaunchTable> tables;
-  std::vector<int> tier_block;
-  for (int tier = 0; tier < NTIER; tier++) {
-    LaunchTable T;
-    memset(&T, 0, sizeof(T));
-    T.P = P;
-    // CTA size of the tier: as many warps (<= 8) as the row store of tier_cap rows per thread allows
-    int cap_rows = 0;
-    for (const Bin& b : bins) {
-      int need = std::max(b.rows_cap, 1);
-      if (need > tier_cap[NTIER - 1]) { ctx->err = "dcol: too many polytope faces / polygon sides for one pair (shared memory)"; return -3; }
-      if (need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1])) cap_rows = std::max(cap_rows, need);
-    }
-    if (!cap_rows) continue;
-    int warps = std::min(8, MAX_SMEM / (cap_rows * NFIELD * (int)sizeof(double) * 32));
-    warps = std::max(1, warps);
-    if (const char* e = getenv("DCOL_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));   // tuning knob
-    const int tile = 32 * warps;
-    for (const Bin& b : bins) {
-      int need = std::max(b.rows_cap, 1);
-      if (!(need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1]))) continue;
-      int k = T.n_bins++;
-      T.begin[k] = b.begin; T.end[k] = b.begin + b.count; T.cp[k] = b.c1 * NCLS + b.c2;
-      T.tile_prefix[k] = T.n_tiles;
-      T.n_tiles += (b.count + tile - 1) / tile;
-    }
-    T.rows_cap = cap_rows;
-    for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = T.n_tiles;
-    tables.push_back(T);
-    tier_block.push_back(tile);
-  }
-  CK(ctx->d_tables.need(sizeof(LaunchTable) * std::max<size_t>(tables.size(), 1)));
-  if (!tables.empty()) CK(cudaMemcpyAsync(ctx->d_tables.p, tables.data(), sizeof(LaunchTable) * tables.size(), cudaMemcpyHostToDevice, S));
   const bool jac = (query == Q_JAC);
-  const void* kfn = persistent_kernel_ptr(jac);
-  CK(cudaEventRecord(ctx->ev_k0, S));
-  CK(cudaEventRecord(ctx->ev_fork, S));
-  for (size_t ti = 0; ti < tables.size(); ti++) {
-    const LaunchTable& T = tables[ti];
-    cudaStream_t st = (tables.size() == 1) ? S : ctx->side[ti % NSIDE];
-    if (st != S) CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
-    const int block = tier_block[ti];
-    size_t smem = (size_t)T.rows_cap * NFIELD * sizeof(double) * block;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, block, smem));
-    int grid = std::min(T.n_tiles, std::max(1, occ) * ctx->n_sm);
-    CK(launch_persistent(jac, grid, block, smem, st, (const LaunchTable*)ctx->d_tables.p + ti, d_counter + ti));
-    ctx->launches++;
-    if (st != S) { CK(cudaEventRecord(ctx->ev_join[ti % NSIDE], st)); CK(cudaStreamWaitEvent(S, ctx->ev_join[ti % NSIDE], 0)); }
-  }
-  CK(cudaEventRecord(ctx->ev_k1, S));
+  cudaStream_t S = ctx->stream();
+  cudaStream_t SC = (nchunks > 1) ? ctx->s_comp : S;          // compute stream of the pipeline
+  if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_fork, S)); CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(SC, ctx->ev_fork, 0)); }
+  std::vector<LaunchTable> tables(std::max(1, nt_tiers));
+  std::vector<int> h_tile(NSIDE, 0);
+  for (int t = 0; t < nt_tiers; t++) h_tile[t] = ctx->tiers[t].block;
 
-  // ---- results back
-  if (mem == DCOL_MEM_HOST) {
-    char* dout = (char*)ctx->d_out.p;
-    CK(cudaMemcpyAsync(alpha, dout + o_alpha, sizeof(double) * n, cudaMemcpyDeviceToHost, S));
-    if (x) CK(cudaMemcpyAsync(x, dout + o_x, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, S));
-    if (dsz) CK(cudaMemcpyAsync(deriv, dout + o_der, sizeof(double) * dsz * n, cudaMemcpyDeviceToHost, S));
-    if (status) CK(cudaMemcpyAsync(status, dout + o_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, S));
-    if (iters) CK(cudaMemcpyAsync(iters, dout + o_it, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, S));
+  for (int c = 0; c < nchunks; c++) {
+    const int64_t c0 = n * c / nchunks, c1 = n * (c + 1) / nchunks, nc = c1 - c0;
+    QueryParams P;
+    memset(&P, 0, sizeof(P));
+    P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
+    P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query;
+    if (mem == DCOL_MEM_HOST) {
+      cudaStream_t SI = (nchunks > 1) ? ctx->s_copy : S;
+      CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_s2 + sizeof(int32_t) * c0, shape2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_r1 + sizeof(double) * 3 * c0, r1 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_a1 + sizeof(double) * na * c0, att1 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+      if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, ctx->ev_in[c], 0)); }
+      P.shape1 = (const int32_t*)(di + o_s1) + c0; P.shape2 = (const int32_t*)(di + o_s2) + c0;
+      P.r1 = (const double*)(di + o_r1) + 3 * c0; P.att1 = (const double*)(di + o_a1) + na * c0;
+      P.r2 = (const double*)(di + o_r2) + 3 * c0; P.att2 = (const double*)(di + o_a2) + na * c0;
+      P.alpha = (double*)(dout + o_alpha) + c0; P.x = (double*)(dout + o_x) + 3 * c0;
+      P.deriv = dsz ? (double*)(dout + o_der) + dsz * c0 : nullptr;
+      P.status = (int32_t*)(dout + o_st) + c0; P.iters = (int32_t*)(dout + o_it) + c0;
+    } else {
+      P.shape1 = shape1; P.shape2 = shape2; P.r1 = r1; P.att1 = att1; P.r2 = r2; P.att2 = att2;
+      P.alpha = alpha; P.x = x; P.deriv = deriv; P.status = status; P.iters = iters;
+    }
+    // ---- bin the chunk's pairs by key (device counting sort), build the tile tables on the device
+    int* d_hist = (int*)ctx->d_hist.p + hist_stride * c;
+    int* d_off = d_hist + nk;            // nk+1
+    int* d_cursor = d_off + nk + 1;      // nk
+    int* d_bad = d_cursor + nk;          // 1
+    int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier
+    int* d_tile = d_counter + NSIDE + 1; // tile size per tier
+    int32_t* d_perm = (int32_t*)ctx->d_perm.p + c0;
+    LaunchTable* d_tab = (LaunchTable*)ctx->d_tables.p + (size_t)std::max(1, nt_tiers) * c;
+    P.perm = d_perm;
+    CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
+    CK(cudaMemcpyAsync(d_tile, h_tile.data(), sizeof(int) * NSIDE, cudaMemcpyHostToDevice, SC));
+    for (int t = 0; t < nt_tiers; t++) {
+      const dcol_ctx::Tier& TR = ctx->tiers[t];
+      LaunchTable& T = tables[t];
+      memset(&T, 0, sizeof(T));
+      T.P = P; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap;
+      for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; }
+    }
+    CK(cudaMemcpyAsync(d_tab, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
+    const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
+    {
+      int threads = 256;
+      int blocks = (int)std::min<int64_t>((nc + threads * 8 - 1) / (threads * 8), 1184);
+      k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
+      k_scan<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor);
+      k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_perm);
+      k_build_tables<<<1, 32, 0, SC>>>(d_tab, nt_tiers, d_tile, d_off);
+      ctx->launches += 4;
+    }
+    // ---- persistent solver launches, one per shared-memory tier present in the shape table
+    CK(cudaEventRecord(ctx->ev_t0[c], SC));
+    if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
+    for (int t = 0; t < nt_tiers; t++) {
+      const dcol_ctx::Tier& TR = ctx->tiers[t];
+      cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
+      if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
+      CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, d_tab + t, d_counter + t));
+      ctx->launches++;
+      if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
+    }
+    CK(cudaEventRecord(ctx->ev_t1[c], SC));
+    // ---- results of this chunk back (host mode), overlapping the next chunk's kernels
+    if (mem == DCOL_MEM_HOST) {
+      cudaStream_t SO = (nchunks > 1) ? ctx->s_out : S;
+      if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_done[c], SC)); CK(cudaStreamWaitEvent(SO, ctx->ev_done[c], 0)); }
+      CK(cudaMemcpyAsync(alpha + c0, dout + o_alpha + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
+      if (x) CK(cudaMemcpyAsync(x + 3 * c0, dout + o_x + sizeof(double) * 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, SO));
+      if (dsz) CK(cudaMemcpyAsync(deriv + dsz * c0, dout + o_der + sizeof(double) * dsz * c0, sizeof(double) * dsz * nc, cudaMemcpyDeviceToHost, SO));
+      if (status) CK(cudaMemcpyAsync(status + c0, dout + o_st + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
+      if (iters) CK(cudaMemcpyAsync(iters + c0, dout + o_it + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
+    }
+  }
+  // ---- join; the only host synchronisation of the call
+  std::vector<int> h_bad(nchunks, 0);
+  cudaStream_t SL = (nchunks > 1) ? ctx->s_out : S;
+  for (int c = 0; c < nchunks; c++)
+    CK(cudaMemcpyAsync(&h_bad[c], (int*)ctx->d_hist.p + hist_stride * c + 3 * (size_t)nk + 1, sizeof(int), cudaMemcpyDeviceToHost, SL));
+  if (nchunks > 1) {
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(SC));
   }
   CK(cudaStreamSynchronize(S));
-  float ms = -1.f;
-  if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->last_ms = ms;
+  double total_ms = 0.0;
+  for (int c = 0; c < nchunks; c++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_t0[c], ctx->ev_t1[c]) == cudaSuccess) total_ms += ms;
+  }
+  ctx->last_ms = total_ms;
+  for (int c = 0; c < nchunks; c++)
+    if (h_bad[c]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; return -1; }
   return 0;
 }
 

@@ -3,26 +3,28 @@
 #include "dcol_common.cuh"
 #include <cuda_runtime.h>
 
+#ifndef DCOL_MAXTHREADS
+#define DCOL_MAXTHREADS 256
+#endif
 namespace dcol {
 
 template <int C1, int C2, bool JAC>
-__device__ void solve_entry(const QueryParams* p, int idx, double* warp_smem);   // dcol_kernels_c*.cu
+__device__ void solve_entry(const QueryParams* p, int idx);   // dcol_kernels_c*.cu
 
 template <int C1, bool JAC>
-__device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, int idx, double* wsm) {
+__device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, int idx) {
   switch (c2) {
-    case 0: solve_entry<C1, 0, JAC>(p, idx, wsm); break;
-    case 1: solve_entry<C1, 1, JAC>(p, idx, wsm); break;
-    case 2: solve_entry<C1, 2, JAC>(p, idx, wsm); break;
-    case 3: solve_entry<C1, 3, JAC>(p, idx, wsm); break;
-    case 4: solve_entry<C1, 4, JAC>(p, idx, wsm); break;
-    case 5: solve_entry<C1, 5, JAC>(p, idx, wsm); break;
+    case 0: solve_entry<C1, 0, JAC>(p, idx); break;
+    case 1: solve_entry<C1, 1, JAC>(p, idx); break;
+    case 2: solve_entry<C1, 2, JAC>(p, idx); break;
+    case 3: solve_entry<C1, 3, JAC>(p, idx); break;
+    case 4: solve_entry<C1, 4, JAC>(p, idx); break;
+    case 5: solve_entry<C1, 5, JAC>(p, idx); break;
   }
 }
 
 template <bool JAC>
-__global__ void __launch_bounds__(256, 1) proximity_persistent(const LaunchTable* __restrict__ tt, int* __restrict__ counter) {
-  extern __shared__ double smem[];
+__global__ void __launch_bounds__(DCOL_MAXTHREADS, 1) proximity_persistent(const LaunchTable* __restrict__ tt, int* __restrict__ counter) {
   __shared__ int s_tile;
   const int n_tiles = tt->n_tiles;
   const int tile_sz = blockDim.x;
@@ -43,12 +45,12 @@ __global__ void __launch_bounds__(256, 1) proximity_persistent(const LaunchTable
     const int cp = __ldg(&tt->cp[b]);
     const int c1 = cp / NCLS, c2 = cp - c1 * NCLS;
     switch (c1) {
-      case 0: dispatch_c2<0, JAC>(c2, &tt->P, idx, smem); break;
-      case 1: dispatch_c2<1, JAC>(c2, &tt->P, idx, smem); break;
-      case 2: dispatch_c2<2, JAC>(c2, &tt->P, idx, smem); break;
-      case 3: dispatch_c2<3, JAC>(c2, &tt->P, idx, smem); break;
-      case 4: dispatch_c2<4, JAC>(c2, &tt->P, idx, smem); break;
-      case 5: dispatch_c2<5, JAC>(c2, &tt->P, idx, smem); break;
+      case 0: dispatch_c2<0, JAC>(c2, &tt->P, idx); break;
+      case 1: dispatch_c2<1, JAC>(c2, &tt->P, idx); break;
+      case 2: dispatch_c2<2, JAC>(c2, &tt->P, idx); break;
+      case 3: dispatch_c2<3, JAC>(c2, &tt->P, idx); break;
+      case 4: dispatch_c2<4, JAC>(c2, &tt->P, idx); break;
+      case 5: dispatch_c2<5, JAC>(c2, &tt->P, idx); break;
     }
   }
 }

@@ -62,9 +62,12 @@ __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 
 // ---------------------------------------------------------------------------
 // shared-memory row store: field f of row i of this thread
 // ---------------------------------------------------------------------------
+// The dynamic shared memory of the persistent kernel, declared here (not passed as a pointer through the
+// out-of-line entry) so that accesses compile to LDS/STS instead of generic loads and stores.
+extern __shared__ double dcol_dyn_smem[];
 struct RowStore {
-  double* base; int stride;   // base = smem + threadIdx.x ; stride = blockDim.x
-  __device__ __forceinline__ double& operator()(int f, int i) const { return base[(i * NFIELD + f) * stride]; }
+  int tid, stride;            // element (f, i) of this thread lives at [(i*NFIELD + f)*blockDim.x + threadIdx.x]
+  __device__ __forceinline__ double& operator()(int f, int i) const { return dcol_dyn_smem[(i * NFIELD + f) * stride + tid]; }
 };
 
 // ---------------------------------------------------------------------------
@@ -675,7 +678,7 @@ struct PairMap {
 // JAC selects the kernel variant that carries the implicit-function-theorem epilogue; the
 // gradient epilogue is a few dozen flops and lives in the JAC=false variant behind p.query.
 template <int C1, int C2, bool JAC>
-__device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, double* smem) {
+__device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
   using P1 = Prim<C1>; using P2 = Prim<C2>;
   using PM = PairMap<P1::NE, P2::NE>;
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
@@ -685,7 +688,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, double
   const DevShape* S2 = p.shapes + p.shape2[pair];
   const int na = (p.att_kind == 0) ? 4 : 3;
 
-  RowStore rs{smem + threadIdx.x, (int)blockDim.x};
+  RowStore rs{(int)threadIdx.x, (int)blockDim.x};
   P1 A; P2 B;
   A.load(S1, p.rows, 0);
   B.load(S2, p.rows, A.n);
@@ -951,8 +954,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx, double
 // Out-of-line entry of one specialisation (separate compilation: each class row lives in its own
 // translation unit and is device-linked into the persistent kernels of dcol_dispatch.cu).
 template <int C1, int C2, bool JAC>
-__device__ __noinline__ void solve_entry(const QueryParams* p, int idx, double* warp_smem) {
-  solve_pair<C1, C2, JAC>(*p, idx, warp_smem);
+__device__ __noinline__ void solve_entry(const QueryParams* p, int idx) {
+  solve_pair<C1, C2, JAC>(*p, idx);
 }
 
 }  // namespace dcol

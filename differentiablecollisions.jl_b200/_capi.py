@@ -29,6 +29,12 @@ SYMBOLS = {
     "dcol_proximity": (C.c_int, _Q_ARGS + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_proximity_gradient": (C.c_int, _Q_ARGS + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_proximity_jacobian": (C.c_int, _Q_ARGS + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_query_indexed": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_scene_pair_count": (C.c_int64, [C.c_int]),
+    "dcol_scene_allpairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_launch_count": (C.c_int64, [C.c_void_p]),
     "dcol_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),

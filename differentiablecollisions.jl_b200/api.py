@@ -135,6 +135,59 @@ class Context:
             out["J"] = np.ascontiguousarray(deriv.transpose(0, 2, 1))  # (n, 4, nt)
         return out
 
+    def _alloc_out(self, kind, n, nt):
+        out = {"alpha": np.empty(n), "status": np.empty(n, dtype=np.int32), "iters": np.empty(n, dtype=np.int32)}
+        x = np.empty((n, 3)) if kind != 1 else None
+        deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
+        return out, x, deriv
+
+    @staticmethod
+    def _finish(out, kind, x, deriv):
+        if x is not None:
+            out["x"] = x
+        if kind == 1:
+            out["grad"] = deriv
+        elif kind == 2:
+            out["J"] = np.ascontiguousarray(deriv.transpose(0, 2, 1))  # (n, 4, nt)
+        return out
+
+    def query_indexed(self, kind, shape1, shape2, pose1, pose2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        """Pose-table variant (`dcol_query_indexed`): pair k uses rows pose1[k] of (r1, att1) and pose2[k] of (r2, att2)."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
+        shape2 = np.ascontiguousarray(shape2, dtype=np.int32).reshape(-1)
+        pose1 = np.ascontiguousarray(pose1, dtype=np.int32).reshape(-1)
+        pose2 = np.ascontiguousarray(pose2, dtype=np.int32).reshape(-1)
+        n = shape1.shape[0]
+        na = 4 if att_kind == ATT_QUAT else 3
+        nt = 6 + 2 * na
+        r1 = np.ascontiguousarray(r1, dtype=np.float64).reshape(-1, 3); att1 = np.ascontiguousarray(att1, dtype=np.float64).reshape(-1, na)
+        r2 = np.ascontiguousarray(r2, dtype=np.float64).reshape(-1, 3); att2 = np.ascontiguousarray(att2, dtype=np.float64).reshape(-1, na)
+        if n and (pose1.max() >= r1.shape[0] or pose2.max() >= r2.shape[0] or pose1.min() < 0 or pose2.min() < 0):
+            raise IndexError("pose index out of range")
+        out, x, deriv = self._alloc_out(kind, n, nt)
+        self._check(self._lib.dcol_query_indexed(self._h, int(kind), n, _ptr(shape1), _ptr(shape2), _ptr(pose1), _ptr(pose2),
+                                                 r1.shape[0], _ptr(r1), _ptr(att1), r2.shape[0], _ptr(r2), _ptr(att2),
+                                                 int(att_kind), float(pdip_tol), MEM_HOST,
+                                                 _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
+        return self._finish(out, kind, x, deriv)
+
+    def scene_allpairs(self, kind, shape, r, att, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        """All i<j pairs of a scene in `combinations` order (`dcol_scene_allpairs`); pair list generated on the device."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(-1)
+        nb = shape.shape[0]
+        na = 4 if att_kind == ATT_QUAT else 3
+        nt = 6 + 2 * na
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(nb, 3); att = np.ascontiguousarray(att, dtype=np.float64).reshape(nb, na)
+        n = int(self._lib.dcol_scene_pair_count(nb))
+        out, x, deriv = self._alloc_out(kind, n, nt)
+        self._check(self._lib.dcol_scene_allpairs(self._h, int(kind), nb, _ptr(shape), _ptr(r), _ptr(att), int(att_kind), float(pdip_tol),
+                                                  MEM_HOST, _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
+        return self._finish(out, kind, x, deriv)
+
     def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
         return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
 

@@ -66,7 +66,7 @@ struct dcol_ctx {
   std::vector<Tier> tiers;
   // per-call scratch (one slot per pipelined chunk)
   static constexpr int MAX_CHUNKS = 8;
-  DevBuf d_in, d_out, d_perm, d_hist, d_tables;
+  DevBuf d_in, d_out, d_perm, d_hist, d_tables, d_scene, d_pairs;
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
   int n_sm = 148;
@@ -169,6 +169,21 @@ __global__ void k_build_tables(LaunchTable* __restrict__ tables, int n_tiers, co
   T.n_tiles = tiles;
 }
 
+// (i, j), i < j in combinations(1:N, 2) order (the pair list of examples/contact_physics/ncp_contact_simulation.jl:48),
+// generated on the device: pair k of row i starts at k_i = i(2N - i - 1)/2.
+__global__ void k_allpairs(int n_bodies, int64_t n_pairs, const int32_t* __restrict__ shape,
+                           int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ p1, int32_t* __restrict__ p2) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_pairs; k += (int64_t)gridDim.x * blockDim.x) {
+    const double N = (double)n_bodies;
+    int64_t i = (int64_t)floor(((2.0 * N - 1.0) - sqrt((2.0 * N - 1.0) * (2.0 * N - 1.0) - 8.0 * (double)k)) * 0.5);
+    i = max((int64_t)0, min(i, (int64_t)n_bodies - 2));
+    while (i > 0 && i * (2 * (int64_t)n_bodies - i - 1) / 2 > k) i--;
+    while ((i + 1) * (2 * (int64_t)n_bodies - i - 2) / 2 <= k) i++;
+    const int64_t j = k - i * (2 * (int64_t)n_bodies - i - 1) / 2 + i + 1;
+    s1[k] = shape[i]; s2[k] = shape[j]; p1[k] = (int32_t)i; p2[k] = (int32_t)j;
+  }
+}
+
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -239,7 +254,7 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables, &ctx->d_scene, &ctx->d_pairs};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
@@ -441,10 +456,17 @@ double dcol_measure_fp64_tflops(dcol_ctx* ctx) {
 // ---------------------------------------------------------------------------
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// pose1/pose2 == NULL: r*/att* have one row per pair.  Otherwise they are tables of np1 / np2 rows and pair k uses
+// rows pose1[k] / pose2[k].  in_mem: where the INPUT arrays live (lets the scene operator feed device-generated
+// pair lists while the outputs still go to host buffers).
 static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
                      const double* r1, const double* att1, const double* r2, const double* att2,
                      int att_kind, double pdip_tol, int mem,
-                     double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+                     double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters,
+                     const int32_t* pose1 = nullptr, const int32_t* pose2 = nullptr, int64_t np1 = 0, int64_t np2 = 0,
+                     int in_mem = -1) {
+  if (in_mem < 0) in_mem = mem;
+  const bool indexed = (pose1 != nullptr);
   if (!ctx) return -1;
   ctx->err.clear();
   ctx->last_ms = -1.0;
@@ -454,6 +476,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
   if (n == 0) return 0;
   if (!shape1 || !shape2 || !r1 || !att1 || !r2 || !att2 || !alpha) { ctx->err = "dcol: NULL input/output pointer"; return -1; }
+  if (indexed && (!pose2 || np1 <= 0 || np2 <= 0)) { ctx->err = "dcol: indexed query needs pose1, pose2 and the pose table sizes"; return -1; }
   if (query == Q_PROX && !x) { ctx->err = "dcol_proximity: x is NULL"; return -1; }
   if (query != Q_PROX && !deriv) { ctx->err = "dcol: derivative output is NULL"; return -1; }
   if (query == Q_JAC && !x) { ctx->err = "dcol_proximity_jacobian: x is NULL"; return -1; }
@@ -466,7 +489,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   // ---- chunking: device-pointer calls run as one chunk; host-pointer calls are split so that the H2D copy of
   // chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (three streams)
   int nchunks = 1;
-  if (mem == DCOL_MEM_HOST) {
+  if (mem == DCOL_MEM_HOST || in_mem == DCOL_MEM_HOST) {
     int64_t target = 350000;
     if (const char* e = getenv("DCOL_CHUNK")) target = std::max<int64_t>(1024, atoll(e));
     nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(dcol_ctx::MAX_CHUNKS, (n + target / 2) / target));
@@ -482,23 +505,30 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
   size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0;
   char* di = nullptr; char* dout = nullptr;
-  if (mem == DCOL_MEM_HOST) {
+  size_t o_p1 = 0, o_p2 = 0;
+  const int64_t rows1 = indexed ? np1 : n, rows2 = indexed ? np2 : n;
+  if (in_mem == DCOL_MEM_HOST) {
     size_t b = 0;
     o_s1 = b; b += align256(sizeof(int32_t) * n);
     o_s2 = b; b += align256(sizeof(int32_t) * n);
-    o_r1 = b; b += align256(sizeof(double) * 3 * n);
-    o_a1 = b; b += align256(sizeof(double) * na * n);
-    o_r2 = b; b += align256(sizeof(double) * 3 * n);
-    o_a2 = b; b += align256(sizeof(double) * na * n);
+    o_p1 = b; b += align256(sizeof(int32_t) * (indexed ? n : 0));
+    o_p2 = b; b += align256(sizeof(int32_t) * (indexed ? n : 0));
+    o_r1 = b; b += align256(sizeof(double) * 3 * rows1);
+    o_a1 = b; b += align256(sizeof(double) * na * rows1);
+    o_r2 = b; b += align256(sizeof(double) * 3 * rows2);
+    o_a2 = b; b += align256(sizeof(double) * na * rows2);
     CK(ctx->d_in.need(b));
-    b = 0;
+    di = (char*)ctx->d_in.p;
+  }
+  if (mem == DCOL_MEM_HOST) {
+    size_t b = 0;
     o_alpha = b; b += align256(sizeof(double) * n);
     o_x = b; b += align256(sizeof(double) * 3 * n);
     o_der = b; b += align256(sizeof(double) * dsz * n);
     o_st = b; b += align256(sizeof(int32_t) * n);
     o_it = b; b += align256(sizeof(int32_t) * n);
     CK(ctx->d_out.need(b));
-    di = (char*)ctx->d_in.p; dout = (char*)ctx->d_out.p;
+    dout = (char*)ctx->d_out.p;
   }
   const bool jac = (query == Q_JAC);
   cudaStream_t S = ctx->stream();
@@ -508,30 +538,54 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   std::vector<int> h_tile(NSIDE, 0);
   for (int t = 0; t < nt_tiers; t++) h_tile[t] = ctx->tiers[t].block;
 
+  if (indexed && in_mem == DCOL_MEM_HOST) {       // pose tables go up once, ahead of the first chunk's pair lists
+    cudaStream_t SI = (nchunks > 1) ? ctx->s_copy : S;
+    CK(cudaMemcpyAsync(di + o_r1, r1, sizeof(double) * 3 * np1, cudaMemcpyHostToDevice, SI));
+    CK(cudaMemcpyAsync(di + o_a1, att1, sizeof(double) * na * np1, cudaMemcpyHostToDevice, SI));
+    CK(cudaMemcpyAsync(di + o_r2, r2, sizeof(double) * 3 * np2, cudaMemcpyHostToDevice, SI));
+    CK(cudaMemcpyAsync(di + o_a2, att2, sizeof(double) * na * np2, cudaMemcpyHostToDevice, SI));
+  }
   for (int c = 0; c < nchunks; c++) {
     const int64_t c0 = n * c / nchunks, c1 = n * (c + 1) / nchunks, nc = c1 - c0;
     QueryParams P;
     memset(&P, 0, sizeof(P));
     P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
     P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query;
-    if (mem == DCOL_MEM_HOST) {
+    if (in_mem == DCOL_MEM_HOST) {
       cudaStream_t SI = (nchunks > 1) ? ctx->s_copy : S;
       CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       CK(cudaMemcpyAsync(di + o_s2 + sizeof(int32_t) * c0, shape2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
-      CK(cudaMemcpyAsync(di + o_r1 + sizeof(double) * 3 * c0, r1 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
-      CK(cudaMemcpyAsync(di + o_a1 + sizeof(double) * na * c0, att1 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
-      CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
-      CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+      if (indexed) {
+        CK(cudaMemcpyAsync(di + o_p1 + sizeof(int32_t) * c0, pose1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_p2 + sizeof(int32_t) * c0, pose2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+      } else {
+        CK(cudaMemcpyAsync(di + o_r1 + sizeof(double) * 3 * c0, r1 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_a1 + sizeof(double) * na * c0, att1 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+      }
       if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, ctx->ev_in[c], 0)); }
       P.shape1 = (const int32_t*)(di + o_s1) + c0; P.shape2 = (const int32_t*)(di + o_s2) + c0;
-      P.r1 = (const double*)(di + o_r1) + 3 * c0; P.att1 = (const double*)(di + o_a1) + na * c0;
-      P.r2 = (const double*)(di + o_r2) + 3 * c0; P.att2 = (const double*)(di + o_a2) + na * c0;
+      if (indexed) {
+        P.pose1 = (const int32_t*)(di + o_p1) + c0; P.pose2 = (const int32_t*)(di + o_p2) + c0;
+        P.r1 = (const double*)(di + o_r1); P.att1 = (const double*)(di + o_a1);
+        P.r2 = (const double*)(di + o_r2); P.att2 = (const double*)(di + o_a2);
+      } else {
+        P.r1 = (const double*)(di + o_r1) + 3 * c0; P.att1 = (const double*)(di + o_a1) + na * c0;
+        P.r2 = (const double*)(di + o_r2) + 3 * c0; P.att2 = (const double*)(di + o_a2) + na * c0;
+      }
+    } else {
+      P.shape1 = shape1 + c0; P.shape2 = shape2 + c0;
+      if (indexed) { P.pose1 = pose1 + c0; P.pose2 = pose2 + c0; P.r1 = r1; P.att1 = att1; P.r2 = r2; P.att2 = att2; }
+      else { P.r1 = r1 + 3 * c0; P.att1 = att1 + na * c0; P.r2 = r2 + 3 * c0; P.att2 = att2 + na * c0; }
+    }
+    if (mem == DCOL_MEM_HOST) {
       P.alpha = (double*)(dout + o_alpha) + c0; P.x = (double*)(dout + o_x) + 3 * c0;
       P.deriv = dsz ? (double*)(dout + o_der) + dsz * c0 : nullptr;
       P.status = (int32_t*)(dout + o_st) + c0; P.iters = (int32_t*)(dout + o_it) + c0;
     } else {
-      P.shape1 = shape1; P.shape2 = shape2; P.r1 = r1; P.att1 = att1; P.r2 = r2; P.att2 = att2;
-      P.alpha = alpha; P.x = x; P.deriv = deriv; P.status = status; P.iters = iters;
+      P.alpha = alpha + c0; P.x = x ? x + 3 * c0 : nullptr; P.deriv = deriv ? deriv + dsz * c0 : nullptr;
+      P.status = status ? status + c0 : nullptr; P.iters = iters ? iters + c0 : nullptr;
     }
     // ---- bin the chunk's pairs by key (device counting sort), build the tile tables on the device
     int* d_hist = (int*)ctx->d_hist.p + hist_stride * c;
@@ -628,6 +682,62 @@ int dcol_proximity_jacobian(dcol_ctx* ctx, int64_t n, const int32_t* shape1, con
                             int att_kind, double pdip_tol, int mem,
                             double* alpha, double* x, double* J, int32_t* status, int32_t* iters) {
   return run_query(ctx, Q_JAC, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem, alpha, x, J, status, iters);
+}
+
+
+static int check_query_kind(dcol_ctx* ctx, int query) {
+  if (!ctx) return -1;
+  if (query != Q_PROX && query != Q_GRAD && query != Q_JAC) { ctx->err = "dcol: query must be 0 (proximity), 1 (gradient) or 2 (jacobian)"; return -1; }
+  return 0;
+}
+
+int dcol_query_indexed(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                       const int32_t* pose1, const int32_t* pose2,
+                       int64_t n_pose1, const double* r1, const double* att1,
+                       int64_t n_pose2, const double* r2, const double* att2,
+                       int att_kind, double pdip_tol, int mem,
+                       double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  if (check_query_kind(ctx, query)) return -1;
+  if (!pose1 || !pose2) { ctx->err = "dcol_query_indexed: pose1/pose2 are NULL"; return -1; }
+  return run_query(ctx, query, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem, alpha, x, deriv, status, iters,
+                   pose1, pose2, n_pose1, n_pose2);
+}
+
+int64_t dcol_scene_pair_count(int n_bodies) { return n_bodies < 2 ? 0 : (int64_t)n_bodies * (n_bodies - 1) / 2; }
+
+int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* shape, const double* r, const double* att,
+                        int att_kind, double pdip_tol, int mem,
+                        double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  if (check_query_kind(ctx, query)) return -1;
+  ctx->err.clear();
+  if (n_bodies < 0 || !shape || !r || !att) { ctx->err = "dcol_scene_allpairs: bad arguments"; return -1; }
+  if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { ctx->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
+  if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
+  const int64_t np = dcol_scene_pair_count(n_bodies);
+  if (np == 0) return 0;
+  if (np > 0x7fffffff) { ctx->err = "dcol_scene_allpairs: too many pairs for one call"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t S = ctx->stream();
+  const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3;
+  // body arrays on the device
+  const int32_t* d_shape = shape; const double* d_r = r; const double* d_att = att;
+  if (mem == DCOL_MEM_HOST) {
+    size_t b0 = align256(sizeof(int32_t) * n_bodies), b1 = align256(sizeof(double) * 3 * n_bodies), b2 = align256(sizeof(double) * na * n_bodies);
+    CK(ctx->d_scene.need(b0 + b1 + b2));
+    char* d = (char*)ctx->d_scene.p;
+    CK(cudaMemcpyAsync(d, shape, sizeof(int32_t) * n_bodies, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0, r, sizeof(double) * 3 * n_bodies, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0 + b1, att, sizeof(double) * na * n_bodies, cudaMemcpyHostToDevice, S));
+    d_shape = (const int32_t*)d; d_r = (const double*)(d + b0); d_att = (const double*)(d + b0 + b1);
+  }
+  // pair lists generated on the device
+  CK(ctx->d_pairs.need(sizeof(int32_t) * 4 * (size_t)np));
+  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* p1 = s2 + np; int32_t* p2 = p1 + np;
+  k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return run_query(ctx, query, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, mem, alpha, x, deriv, status, iters,
+                   p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE);
 }
 
 }  // extern "C"

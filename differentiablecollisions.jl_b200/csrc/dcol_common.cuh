@@ -52,6 +52,8 @@ struct QueryParams {
   const int32_t* perm;           // sorted position -> pair index
   const int32_t* shape1;
   const int32_t* shape2;
+  const int32_t* pose1;          // optional: row of (r1, att1) used by the pair; NULL = the pair's own row
+  const int32_t* pose2;
   const double* r1;  const double* att1;
   const double* r2;  const double* att2;
   int att_kind;                  // 0 quaternion (stride 4), 1 MRP (stride 3)

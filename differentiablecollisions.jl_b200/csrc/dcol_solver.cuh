@@ -687,6 +687,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
   const DevShape* S1 = p.shapes + p.shape1[pair];
   const DevShape* S2 = p.shapes + p.shape2[pair];
   const int na = (p.att_kind == 0) ? 4 : 3;
+  // pose rows: the pair's own row, or a row of a pose table (indexed queries: scenes, trajectory batches)
+  const int64_t i1 = p.pose1 ? (int64_t)p.pose1[pair] : (int64_t)pair;
+  const int64_t i2 = p.pose2 ? (int64_t)p.pose2[pair] : (int64_t)pair;
 
   RowStore rs{(int)threadIdx.x, (int)blockDim.x};
   P1 A; P2 B;
@@ -697,8 +700,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
   double R[3][3], t[3];
   {
     Frame F1, F2;
-    build_frame(S1, p.r1 + 3 * (int64_t)pair, p.att1 + na * (int64_t)pair, p.att_kind, F1);
-    build_frame(S2, p.r2 + 3 * (int64_t)pair, p.att2 + na * (int64_t)pair, p.att_kind, F2);
+    build_frame(S1, p.r1 + 3 * i1, p.att1 + na * i1, p.att_kind, F1);
+    build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
     double dr[3] = {F1.r[0] - F2.r[0], F1.r[1] - F2.r[1], F1.r[2] - F2.r[2]};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -821,7 +824,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
 
   // ---------------- outputs ----------------
   Frame F1, F2;
-  build_frame(S1, p.r1 + 3 * (int64_t)pair, p.att1 + na * (int64_t)pair, p.att_kind, F1);
+  build_frame(S1, p.r1 + 3 * i1, p.att1 + na * i1, p.att_kind, F1);
   p.alpha[pair] = y[3];
   if (p.x) {
 #pragma unroll
@@ -835,13 +838,13 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
     if (p.query == Q_GRAD) {
       double* g = p.deriv + (int64_t)nt * pair;
       if (status == ST_OK) {
-        build_frame(S2, p.r2 + 3 * (int64_t)pair, p.att2 + na * (int64_t)pair, p.att_kind, F2);
+        build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
         double y1[NV1], y2[NV2];
         PM::to_local(y, R, t, true, y1, y2);
         SideVecs V1, V2;
         A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
-        grad_side(S1, F1, p.att1 + na * (int64_t)pair, p.att_kind, V1, g);
-        grad_side(S2, F2, p.att2 + na * (int64_t)pair, p.att_kind, V2, g + 3 + na);
+        grad_side(S1, F1, p.att1 + na * i1, p.att_kind, V1, g);
+        grad_side(S2, F2, p.att2 + na * i2, p.att_kind, V2, g + 3 + na);
       } else {
         for (int j = 0; j < nt; j++) g[j] = __longlong_as_double(0x7ff8000000000000LL);
       }
@@ -851,7 +854,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
     double* Jo = p.deriv + (int64_t)4 * nt * pair;
     bool ok = (status == ST_OK);
     if (ok) {
-      build_frame(S2, p.r2 + 3 * (int64_t)pair, p.att2 + na * (int64_t)pair, p.att_kind, F2);
+      build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
       double K1[4][3], K2[4][3], Kb1[4][3], Kb2[4][3], Ye1[4][2], Ye2[4][2], Hw[4][3];
       SideVecs V1, V2;
       {
@@ -940,8 +943,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
         }
       }
       if (ok) {
-        jac_side<P1::NE>(S1, F1, p.att1 + na * (int64_t)pair, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo);
-        jac_side<P2::NE>(S2, F2, p.att2 + na * (int64_t)pair, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + 4 * (3 + na));
+        jac_side<P1::NE>(S1, F1, p.att1 + na * i1, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo);
+        jac_side<P2::NE>(S2, F2, p.att2 + na * i2, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + 4 * (3 + na));
       } else {
         status = ST_NUMERICAL;
       }

@@ -103,6 +103,29 @@ int dcol_proximity_jacobian(dcol_ctx* ctx, int64_t n, const int32_t* shape1, con
                             int att_kind, double pdip_tol, int mem,
                             double* alpha, double* x, double* J, int32_t* status, int32_t* iters);
 
+/* ---- next-tier operators: the callers' batch shapes, same kernels -------------------------
+ *
+ * Indexed query: r1/att1 and r2/att2 are pose TABLES of n_pose1 / n_pose2 rows; pair k uses rows pose1[k] and
+ * pose2[k].  query: 0 proximity (deriv unused), 1 gradient (x unused, deriv = grad), 2 jacobian (deriv = J).
+ * This is the call pattern of the trajectory-optimisation examples — one vehicle pose per (rollout, knot)
+ * against K static obstacles (examples/trajectory_optimization/piano_mover.jl:39-53, simple_altro.jl:79-83) —
+ * without replicating poses per pair. */
+int dcol_query_indexed(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                       const int32_t* pose1, const int32_t* pose2,
+                       int64_t n_pose1, const double* r1, const double* att1,
+                       int64_t n_pose2, const double* r2, const double* att2,
+                       int att_kind, double pdip_tol, int mem,
+                       double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
+
+/* All-pairs contact scene: every pair (i, j), i < j, of n_bodies bodies, in combinations(1:N, 2) order
+ * (examples/contact_physics/ncp_contact_simulation.jl:48, :86-89, :133-139).  The pair list is generated on the
+ * device; outputs have dcol_scene_pair_count(n_bodies) = N(N-1)/2 rows, derivative columns are
+ * [r_i; att_i; r_j; att_j].  shape[n_bodies], r[n_bodies*3], att[n_bodies*(4|3)]. */
+int64_t dcol_scene_pair_count(int n_bodies);
+int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* shape, const double* r, const double* att,
+                        int att_kind, double pdip_tol, int mem,
+                        double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
+
 /* Instrumentation for bench.py / tests. */
 /* kernels launched by this context since creation (solver + derivative + binning kernels) */
 int64_t dcol_launch_count(const dcol_ctx* ctx);

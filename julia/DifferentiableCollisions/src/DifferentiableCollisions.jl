@@ -231,6 +231,45 @@ proximity_gradient_batch(s1, s2, r1::Matrix{Float64}, a1::Matrix{Float64}, r2::M
 proximity_jacobian_batch(s1, s2, r1::Matrix{Float64}, a1::Matrix{Float64}, r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6) =
     _query(:dcol_proximity_jacobian, Int32.(s1), Int32.(s2), r1, a1, r2, a2, size(a1, 1) == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol))
 
+"""
+    scene_allpairs(kind, shape, r, att; pdip_tol) -> BatchResult
+
+All `i<j` pairs of a scene in `combinations(1:N,2)` order (the pair list of the contact example); `kind` 0/1/2 =
+proximity / gradient / jacobian, `shape` 0-based shape ids, `r` 3×N, `att` (4|3)×N.
+"""
+function scene_allpairs(kind::Integer, shape::Vector{Int32}, r::Matrix{Float64}, att::Matrix{Float64}; pdip_tol = 1e-6)
+    nb = length(shape); na = size(att, 1); nt = 6 + 2na
+    n = Int(ccall((:dcol_scene_pair_count, _lib[]), Int64, (Cint,), nb))
+    α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
+    x = Matrix{Float64}(undef, 3, kind == 1 ? 0 : n)
+    deriv = kind == 0 ? Float64[] : (kind == 1 ? Matrix{Float64}(undef, nt, n) : Array{Float64}(undef, 4, nt, n))
+    _check(ccall((:dcol_scene_allpairs, _lib[]), Cint,
+                 (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
+                  Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                 _ctx[], kind, nb, shape, r, att, na == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol), MEM_HOST,
+                 α, kind == 1 ? C_NULL : x, kind == 0 ? C_NULL : deriv, status, iters))
+    return BatchResult(α, x, deriv, status, iters)
+end
+
+"""
+    query_indexed(kind, shape1, shape2, pose1, pose2, r1, att1, r2, att2; pdip_tol) -> BatchResult
+
+Pose-table query: pair k uses column `pose1[k]+1` of `(r1, att1)` and `pose2[k]+1` of `(r2, att2)` (0-based indices, as in C).
+"""
+function query_indexed(kind::Integer, s1::Vector{Int32}, s2::Vector{Int32}, p1::Vector{Int32}, p2::Vector{Int32},
+                       r1::Matrix{Float64}, a1::Matrix{Float64}, r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6)
+    n = length(s1); na = size(a1, 1); nt = 6 + 2na
+    α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
+    x = Matrix{Float64}(undef, 3, kind == 1 ? 0 : n)
+    deriv = kind == 0 ? Float64[] : (kind == 1 ? Matrix{Float64}(undef, nt, n) : Array{Float64}(undef, 4, nt, n))
+    _check(ccall((:dcol_query_indexed, _lib[]), Cint,
+                 (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64},
+                  Int64, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                 _ctx[], kind, n, s1, s2, p1, p2, size(r1, 2), r1, a1, size(r2, 2), r2, a2, na == 4 ? ATT_QUAT : ATT_MRP,
+                 Float64(pdip_tol), MEM_HOST, α, kind == 1 ? C_NULL : x, kind == 0 ? C_NULL : deriv, status, iters))
+    return BatchResult(α, x, deriv, status, iters)
+end
+
 # ---------------------------------------------------------------------------------------------
 # single-pair drop-in calls: a batch of one through the same entry points
 # ---------------------------------------------------------------------------------------------

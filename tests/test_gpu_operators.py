@@ -1,0 +1,119 @@
+"""GPU (-m gpu): the next-tier operators of SURVEY.md §8f — pose-table (indexed) queries and the all-pairs contact scene —
+against the plain batched calls, the oracle, and at BASELINE config 4 / 5 sizes."""
+import itertools
+
+import numpy as np
+import pytest
+
+import dcol_b200 as dc
+import props
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def scene_bodies(n_bodies, att_kind, seed=3, spread=5.0):
+    """Types cycled over the 12-body list of examples/contact_physics/ncp_contact_simulation.jl:264-267, positions
+    spread*N(0,I) (:281 uses 5)."""
+    A1, b1, A2, b2 = util.load_polytopes()
+    A5, b5 = dc.create_n_sided(5, 0.6)
+    A8, b8 = dc.create_n_sided(8, 0.8)
+    g = lambda b: util.cls_name(att_kind, b)
+    protos = [g("Cylinder")(0.6, 3.0), g("Capsule")(0.2, 5.0), g("Sphere")(0.8), g("Cone")(2.0, np.deg2rad(22)),
+              g("Polytope")(A2, b2), g("Polygon")(A5, b5, 0.2), g("Cylinder")(1.1, 2.3), g("Capsule")(0.8, 1.0), g("Sphere")(0.5),
+              g("Cone")(3.0, np.deg2rad(18)), g("Polytope")(A1, b1), g("Polygon")(A8, b8, 0.15)]
+    t = dc.ShapeTable()
+    ids = np.array([t.add(p) for p in protos], np.int32)
+    shape = ids[np.arange(n_bodies) % len(ids)]
+    rg = util.rng(seed)
+    r = spread * rg.standard_normal((n_bodies, 3))
+    q = rg.standard_normal((n_bodies, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    if att_kind == dc.ATT_MRP:
+        q = np.where(q[:, :1] < 0, -q, q)
+        att = q[:, 1:] / (1 + q[:, :1])
+    else:
+        att = q
+    return t, shape, r, att
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_scene_allpairs_matches_explicit_pairs(ctx, oracle, att_kind, kind):
+    nb = 61
+    t, shape, r, att = scene_bodies(nb, att_kind, spread=2.0)
+    ctx.set_shape_arrays(*t.arrays())
+    s = ctx.scene_allpairs(kind, shape, r, att, att_kind)
+    ij = np.array(list(itertools.combinations(range(nb), 2)))          # Combinatorics.combinations order
+    assert s["alpha"].shape[0] == len(ij) == nb * (nb - 1) // 2
+    e = ctx._batch(kind, shape[ij[:, 0]], shape[ij[:, 1]], r[ij[:, 0]], att[ij[:, 0]], r[ij[:, 1]], att[ij[:, 1]], att_kind, 1e-6)
+    for k in e:
+        assert np.array_equal(s[k], e[k], equal_nan=True), k                # same kernels, same pairs, same order
+    o = oracle.query(kind, t.arrays(), shape[ij[:, 0]], shape[ij[:, 1]], r[ij[:, 0]], att[ij[:, 0]], r[ij[:, 1]], att[ij[:, 1]], att_kind, 1e-6)
+    ok = o["status"] == 0
+    assert (s["status"] == o["status"]).all()
+    assert util.rel_err(s["alpha"], o["alpha"])[ok].max() < 1e-6
+    assert ((s["alpha"] <= 1) == (o["alpha"] <= 1))[ok].all()
+    if kind == 1:
+        assert (util.rel_err(s["grad"], o["grad"])[ok] < 1e-5).mean() > 0.99
+    if kind == 2:
+        assert (util.rel_err(s["J"], o["J"])[ok] < 1e-5).mean() > 0.99
+
+
+def test_indexed_query_matches_replicated_poses(ctx, oracle):
+    """BASELINE config 5 shape: vehicle = create_rect_prism(2.5, .15, .01) against the three boxes of piano_mover.jl:74-82,
+    MRP p = (0, 0, tan(theta/4)) (:41); pose table = (rollout, knot), obstacle table = 3 static poses."""
+    B, N, K = 64, 100, 3
+    veh = dc.create_rect_prism(2.5, 0.15, 0.01)[0]
+    obs = [dc.create_rect_prism(3.0, 3.0, 0.02)[0], dc.create_rect_prism(4.0, 1.0, 0.02)[0], dc.create_rect_prism(1.0, 3.0, 0.02)[0]]
+    t = dc.ShapeTable()
+    sv = t.add(veh); so = [t.add(o) for o in obs]
+    ctx.set_shape_arrays(*t.arrays())
+    g = util.rng(17)
+    theta = g.uniform(-np.pi, np.pi, B * N)
+    r1 = np.stack([g.uniform(-4, 4, B * N), g.uniform(-4, 4, B * N), np.zeros(B * N)], axis=1)
+    p1 = np.stack([np.zeros(B * N), np.zeros(B * N), np.tan(theta / 4)], axis=1)
+    r2 = np.array([[-1.5, 1.5, 0.0], [2.0, -2.5, 0.0], [3.0, 2.5, 0.0]]); p2 = np.zeros((3, 3))
+    pose1 = np.repeat(np.arange(B * N, dtype=np.int32), K)
+    pose2 = np.tile(np.arange(K, dtype=np.int32), B * N)
+    s1 = np.full(B * N * K, sv, np.int32); s2 = np.array(so, np.int32)[pose2]
+    for kind in (0, 1, 2):
+        a = ctx.query_indexed(kind, s1, s2, pose1, pose2, r1, p1, r2, p2, dc.ATT_MRP)
+        b = ctx._batch(kind, s1, s2, r1[pose1], p1[pose1], r2[pose2], p2[pose2], dc.ATT_MRP, 1e-6)
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+    o = oracle.query(2, t.arrays(), s1, s2, r1[pose1], p1[pose1], r2[pose2], p2[pose2], dc.ATT_MRP, 1e-6)
+    ok = (o["status"] == 0)
+    assert (a["status"] == o["status"]).all() and ok.mean() > 0.99
+    assert util.rel_err(a["alpha"], o["alpha"])[ok].max() < 1e-6
+    # thin plates in a plane: many face-parallel (degenerate) configurations, so assert J on the pass fraction
+    assert (util.rel_err(a["J"], o["J"])[ok] < 1e-5).mean() > 0.97
+    with pytest.raises(IndexError):
+        ctx.query_indexed(0, s1, s2, pose1 + B * N, pose2, r1, p1, r2, p2, dc.ATT_MRP)
+
+
+def test_config4_full_size_scene(ctx):
+    """BASELINE config 4: 4096 mixed bodies, all 8 386 560 i<j pairs, proximity_gradient, quaternion.  Size-independent
+    properties: translation invariance (d alpha/d r_i + d alpha/d r_j = 0), tangency of the quaternion blocks, and
+    agreement with explicitly listed pairs on a random sample."""
+    nb = 4096
+    t, shape, r, att = scene_bodies(nb, 0, spread=5.0)
+    ctx.set_shape_arrays(*t.arrays())
+    s = ctx.scene_allpairs(1, shape, r, att, 0)
+    n = nb * (nb - 1) // 2
+    assert s["alpha"].shape == (n,) and s["grad"].shape == (n, 14)
+    ok = s["status"] == 0
+    assert ok.mean() > 0.9999
+    gsum = s["grad"][:, 0:3] + s["grad"][:, 7:10]
+    assert np.abs(gsum[ok]).max() < 1e-6 * max(1.0, np.abs(s["grad"][ok]).max())
+    rg = util.rng(5)
+    k = rg.integers(0, n, 20000)
+    # invert the combinations index on the host
+    i = np.floor(((2 * nb - 1) - np.sqrt((2 * nb - 1) ** 2 - 8.0 * k)) / 2).astype(np.int64)
+    i = np.where(i * (2 * nb - i - 1) // 2 > k, i - 1, i)
+    i = np.where((i + 1) * (2 * nb - i - 2) // 2 <= k, i + 1, i)
+    j = k - i * (2 * nb - i - 1) // 2 + i + 1
+    assert (i < j).all() and (j < nb).all()
+    e = ctx._batch(1, shape[i], shape[j], r[i], att[i], r[j], att[j], 0, 1e-6)
+    assert np.array_equal(s["alpha"][k], e["alpha"]) and np.array_equal(s["grad"][k], e["grad"], equal_nan=True)
+    tq = np.einsum("nj,nj->n", s["grad"][k, 3:7], att[i])
+    assert np.abs(tq[e["status"] == 0]).max() < 1e-8 * max(1.0, np.abs(e["grad"]).max())

@@ -17,7 +17,7 @@
 
 namespace dcol {
 const void* persistent_kernel_ptr(bool jac);                                                          // dcol_dispatch.cu
-cudaError_t launch_persistent(bool jac, int grid, int block, size_t smem, cudaStream_t st, const LaunchTable* tt, int* counter);
+cudaError_t launch_persistent(bool jac, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
 }
 using namespace dcol;
 
@@ -62,11 +62,11 @@ struct dcol_ctx {
   DevBuf d_shapes, d_rows, d_cls, d_keymap;
   // static launch plan derived from the shape table (dcol_set_shapes): one entry per shared-memory tier
   struct Tier { int n_bins = 0, rows_cap = 0, block = 0; size_t smem = 0; int grid[2] = {0, 0};
-                int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; };
+                int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; int ov_stride[MAX_BINS]; int max_stride = 0; };
   std::vector<Tier> tiers;
   // per-call scratch (one slot per pipelined chunk)
   static constexpr int MAX_CHUNKS = 8;
-  DevBuf d_in, d_out, d_perm, d_hist, d_tables, d_scene, d_pairs;
+  DevBuf d_in, d_out, d_perm, d_hist, d_tables, d_scene, d_pairs, d_ov;
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
   int n_sm = 148;
@@ -150,23 +150,49 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
   }
 }
 
-// single block: turns the static per-tier bin lists (key ranges parked in begin[]/end[]) into sorted-position ranges
-// and tile prefixes, from the bin offsets of this call — the host never needs the histogram.
+// single thread: turns the static per-tier bin lists (key ranges parked in begin[]/end[]) into sorted-position ranges
+// and tile prefixes, from the bin offsets of this call — the host never needs the histogram.  Also carves the
+// straggler overflow area: bin b gets tiles_b * spill_t records (a tile hands over at most spill_t pairs).
 __global__ void k_build_tables(LaunchTable* __restrict__ tables, int n_tiers, const int* __restrict__ tile_sz,
-                               const int* __restrict__ off) {
-  const int t = threadIdx.x;
-  if (t >= n_tiers) return;
-  LaunchTable& T = tables[t];
-  const int tile = tile_sz[t];
-  int tiles = 0;
-  for (int k = 0; k < T.n_bins; k++) {
-    const int b = off[T.begin[k]], e = off[T.end[k]];
-    T.begin[k] = b; T.end[k] = e;
-    T.tile_prefix[k] = tiles;
-    tiles += (e - b + tile - 1) / tile;
+                               const int* __restrict__ off, double* ov_base) {
+  if (threadIdx.x || blockIdx.x) return;
+  long long ov = 0;
+  for (int t = 0; t < n_tiers; t++) {
+    LaunchTable& T = tables[t];
+    const int tile = tile_sz[t];
+    int tiles = 0;
+    for (int k = 0; k < T.n_bins; k++) {
+      const int b = off[T.begin[k]], e = off[T.end[k]];
+      const int nt = (e - b + tile - 1) / tile;
+      T.begin[k] = b; T.end[k] = e;
+      T.tile_prefix[k] = tiles;
+      tiles += nt;
+      T.ov_cap[k] = nt * T.spill_t; T.ov_off[k] = ov; T.ov_count[k] = 0;
+      ov += (long long)T.ov_cap[k] * T.ov_stride[k];
+    }
+    for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
+    T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0;
   }
-  for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
-  T.n_tiles = tiles;
+}
+// resume-pass tables from the overflow counts the first pass left behind
+__global__ void k_build_tables2(const LaunchTable* __restrict__ tables, LaunchTable* __restrict__ tables2, int n_tiers,
+                                const int* __restrict__ tile_sz) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int t = 0; t < n_tiers; t++) {
+    const LaunchTable& T = tables[t];
+    LaunchTable& U = tables2[t];
+    const int tile = tile_sz[t];
+    int tiles = 0;
+    for (int k = 0; k < T.n_bins; k++) {
+      const int cnt = min(T.ov_count[k], T.ov_cap[k]);
+      U.begin[k] = 0; U.end[k] = cnt; U.cp[k] = T.cp[k];
+      U.tile_prefix[k] = tiles;
+      tiles += (cnt + tile - 1) / tile;
+      U.ov_cap[k] = T.ov_cap[k]; U.ov_off[k] = T.ov_off[k]; U.ov_count[k] = cnt; U.ov_stride[k] = T.ov_stride[k];
+    }
+    for (int k = T.n_bins; k <= MAX_BINS; k++) U.tile_prefix[k] = tiles;
+    U.n_bins = T.n_bins; U.n_tiles = tiles; U.ov_base = T.ov_base; U.mode = 1; U.spill_t = 0; U.rows_cap = T.rows_cap;
+  }
 }
 
 // (i, j), i < j in combinations(1:N, 2) order (the pair list of examples/contact_physics/ncp_contact_simulation.jl:48),
@@ -254,7 +280,7 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables, &ctx->d_scene, &ctx->d_pairs};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables, &ctx->d_scene, &ctx->d_pairs, &ctx->d_ov};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
@@ -405,6 +431,9 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
       for (auto& m : members) {
         int k = T.n_bins++;
         T.cp[k] = m.second; T.key_begin[k] = key_first[m.second]; T.key_end[k] = key_first[m.second + 1];
+        const int c1 = m.second / NCLS, c2 = m.second % NCLS;
+        T.ov_stride[k] = 3 + 4 + cls_ne(c1) + cls_ne(c2) + 2 * (ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]) + 2 * (cls_d(c1) + cls_d(c2));
+        T.max_stride = std::max(T.max_stride, T.ov_stride[k]);
       }
       int warps = std::min(DCOL_MAXTHREADS / 32, (MAX_SMEM - 1024) / (T.rows_cap * NFIELD * (int)sizeof(double) * 32));
       warps = std::max(1, warps);
@@ -496,11 +525,23 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   }
   const int nk = ctx->n_keys;
   const int nt_tiers = (int)ctx->tiers.size();
-  const size_t hist_ints = 3 * (size_t)nk + 16 + NSIDE;           // hist | off | cursor | bad | counters | tile sizes
+  const size_t hist_ints = 3 * (size_t)nk + 16 + 3 * NSIDE;       // hist | off | cursor | bad | counters (2 passes) | tile sizes
   const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
   CK(ctx->d_perm.need(sizeof(int32_t) * n));
   CK(ctx->d_hist.need(sizeof(int) * hist_stride * nchunks));
-  CK(ctx->d_tables.need(sizeof(LaunchTable) * std::max(1, nt_tiers) * nchunks));
+  CK(ctx->d_tables.need(sizeof(LaunchTable) * 2 * std::max(1, nt_tiers) * nchunks));
+  // straggler overflow area per chunk (upper bound: every tile hands over spill_t pairs of the widest record)
+  int spill_div = 8;
+  if (const char* e = getenv("DCOL_SPILL")) spill_div = atoi(e);          // 0 disables the hand-over; default tile/8
+  const int64_t chunk_max = (n + nchunks - 1) / nchunks;
+  size_t ov_doubles = 0;
+  for (int t = 0; t < nt_tiers; t++) {
+    const dcol_ctx::Tier& TR = ctx->tiers[t];
+    const int spill_t = spill_div > 0 ? TR.block / spill_div : 0;
+    ov_doubles += (size_t)(chunk_max / TR.block + TR.n_bins + 1) * spill_t * TR.max_stride;
+  }
+  ov_doubles = (ov_doubles + 31) & ~(size_t)31;
+  CK(ctx->d_ov.need(sizeof(double) * std::max<size_t>(ov_doubles, 32) * nchunks));
 
   size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
   size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0;
@@ -593,9 +634,12 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     int* d_cursor = d_off + nk + 1;      // nk
     int* d_bad = d_cursor + nk;          // 1
     int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier
-    int* d_tile = d_counter + NSIDE + 1; // tile size per tier
+    int* d_counter2 = d_counter + NSIDE; // same for the resume pass
+    int* d_tile = d_counter2 + NSIDE + 1; // tile size per tier
     int32_t* d_perm = (int32_t*)ctx->d_perm.p + c0;
-    LaunchTable* d_tab = (LaunchTable*)ctx->d_tables.p + (size_t)std::max(1, nt_tiers) * c;
+    LaunchTable* d_tab = (LaunchTable*)ctx->d_tables.p + (size_t)2 * std::max(1, nt_tiers) * c;
+    LaunchTable* d_tab2 = d_tab + std::max(1, nt_tiers);
+    double* d_ovc = (double*)ctx->d_ov.p + ov_doubles * c;
     P.perm = d_perm;
     CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
     CK(cudaMemcpyAsync(d_tile, h_tile.data(), sizeof(int) * NSIDE, cudaMemcpyHostToDevice, SC));
@@ -603,10 +647,11 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       const dcol_ctx::Tier& TR = ctx->tiers[t];
       LaunchTable& T = tables[t];
       memset(&T, 0, sizeof(T));
-      T.P = P; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap;
-      for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; }
+      T.P = P; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap; T.spill_t = spill_div > 0 ? TR.block / spill_div : 0;
+      for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; T.ov_stride[k] = TR.ov_stride[k]; }
     }
     CK(cudaMemcpyAsync(d_tab, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
+    CK(cudaMemcpyAsync(d_tab2, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
     const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
     {
       int threads = 256;
@@ -614,7 +659,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
       k_scan<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor);
       k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_perm);
-      k_build_tables<<<1, 32, 0, SC>>>(d_tab, nt_tiers, d_tile, d_off);
+      k_build_tables<<<1, 32, 0, SC>>>(d_tab, nt_tiers, d_tile, d_off, d_ovc);
       ctx->launches += 4;
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table
@@ -627,6 +672,19 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, d_tab + t, d_counter + t));
       ctx->launches++;
       if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
+    }
+    if (spill_div > 0) {        // resume pass: finish the handed-over stragglers in dense tiles
+      k_build_tables2<<<1, 32, 0, SC>>>(d_tab, d_tab2, nt_tiers, d_tile);
+      ctx->launches++;
+      if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
+      for (int t = 0; t < nt_tiers; t++) {
+        const dcol_ctx::Tier& TR = ctx->tiers[t];
+        cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
+        if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
+        CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, d_tab2 + t, d_counter2 + t));
+        ctx->launches++;
+        if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
+      }
     }
     CK(cudaEventRecord(ctx->ev_t1[c], SC));
     // ---- results of this chunk back (host mode), overlapping the next chunk's kernels

@@ -73,11 +73,28 @@ constexpr int MAX_BINS = NCLS * NCLS;
 constexpr int TILE = 32;
 struct LaunchTable {
   QueryParams P;
-  int n_bins, n_tiles, rows_cap, pad_;
+  int n_bins, n_tiles, rows_cap, mode;     // mode 0: first pass (may hand stragglers over), 1: resume pass
   int tile_prefix[MAX_BINS + 1];   // first tile of bin b
-  int begin[MAX_BINS];             // sorted-position range of bin b
+  int begin[MAX_BINS];             // sorted-position range of bin b (resume pass: 0 .. ov_count)
   int end[MAX_BINS];
   int cp[MAX_BINS];                // class pair c1*NCLS + c2
+  // straggler hand-over: when at most spill_t pairs of a tile are still iterating, they park their iterate in the
+  // bin's overflow list and the tile ends; a second (resume) launch finishes them in dense tiles
+  int spill_t;
+  double* ov_base;
+  long long ov_off[MAX_BINS];      // start of bin b's overflow records (doubles), SoA with stride ov_cap[b]
+  int ov_cap[MAX_BINS];            // record capacity of bin b
+  int ov_count[MAX_BINS];          // records written (first pass, atomics)
+  int ov_stride[MAX_BINS];         // doubles per record: 3 + nx + 2*rows + 2*(d1+d2)
+};
+
+// what one tile needs to know beyond the query parameters
+struct TileCtx {
+  int mode;                        // 0 first pass, 1 resume
+  int spill_t;                     // 0: never hand over
+  double* ov;                      // this bin's overflow records
+  int ov_cap;
+  int* ov_count;
 };
 
 }  // namespace dcol

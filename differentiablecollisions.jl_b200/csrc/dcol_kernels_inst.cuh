@@ -5,7 +5,7 @@
 
 namespace dcol {
 #define DCOL_INST(C2) \
-  template __device__ void solve_entry<DCOL_C1, C2, false>(const QueryParams*, int); \
-  template __device__ void solve_entry<DCOL_C1, C2, true>(const QueryParams*, int);
+  template __device__ void solve_entry<DCOL_C1, C2, false>(const QueryParams*, const TileCtx*, int); \
+  template __device__ void solve_entry<DCOL_C1, C2, true>(const QueryParams*, const TileCtx*, int);
 DCOL_INST(0) DCOL_INST(1) DCOL_INST(2) DCOL_INST(3) DCOL_INST(4) DCOL_INST(5)
 }  // namespace dcol

@@ -23,9 +23,9 @@
 #define DCOL_LOCKSTEP 1
 #endif
 #if DCOL_LOCKSTEP
-#define DCOL_VOTE(pred) __syncthreads_or(pred)
+#define DCOL_COUNT(pred) __syncthreads_count(pred)
 #else
-#define DCOL_VOTE(pred) __any_sync(0xffffffffu, pred)
+#define DCOL_COUNT(pred) __popc(__ballot_sync(0xffffffffu, pred))
 #endif
 
 namespace dcol {
@@ -678,12 +678,13 @@ struct PairMap {
 // JAC selects the kernel variant that carries the implicit-function-theorem epilogue; the
 // gradient epilogue is a few dozen flops and lives in the JAC=false variant behind p.query.
 template <int C1, int C2, bool JAC>
-__device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
+__device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& tc, int idx) {
   using P1 = Prim<C1>; using P2 = Prim<C2>;
   using PM = PairMap<P1::NE, P2::NE>;
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
 
-  const int pair = p.perm[idx];
+  // first pass: idx is a position of the sorted pair list; resume pass: idx is a slot of the bin's overflow list
+  const int pair = (tc.mode == 0) ? p.perm[idx] : (int)tc.ov[idx];
   const DevShape* S1 = p.shapes + p.shape1[pair];
   const DevShape* S2 = p.shapes + p.shape2[pair];
   const int na = (p.att_kind == 0) ? 4 : 3;
@@ -718,8 +719,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
   int cone_degree = A.n + B.n + (P1::D > 0 ? 1 : 0) + (P2::D > 0 ? 1 : 0);   // static_solver2.jl:124-130
   const double inv_deg = 1.0 / (double)cone_degree;
 
+  int k0 = 0;
   // ---------------- initialize (static_solver2.jl:86-103) ----------------
-  {
+  if (tc.mode == 0) {
     double N1[NV1][NV1], g1[NV1], N2[NV2][NV2], g2[NV2];
     double y1[NV1], y2[NV2];
 #pragma unroll
@@ -750,6 +752,27 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
     double sh_s = (a_s < 0.0) ? 0.0 : 1.0 + a_s, sh_z = (a_z < 0.0) ? 0.0 : 1.0 + a_z;
     sz = A.init_shift(rs, sh_s, sh_z) + B.init_shift(rs, sh_s, sh_z);
     if (!ok) status = ST_NUMERICAL;
+  } else {
+    // ---------------- resume: reload the iterate parked by the first pass ----------------
+    const double* rec = tc.ov + idx;
+    const int64_t st = tc.ov_cap;
+    k0 = (int)rec[1 * st]; sz = rec[2 * st];
+    int f = 3;
+#pragma unroll
+    for (int a = 0; a < NX; a++) y[a] = rec[(f + a) * st];
+    f += NX;
+    const int nr = A.n + B.n;
+    for (int i = 0; i < nr; i++) { rs(F_S, i) = rec[(f + i) * st]; rs(F_Z, i) = rec[(f + nr + i) * st]; }
+    f += 2 * nr;
+    if constexpr (P1::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { A.s[i] = rec[(f + i) * st]; A.z[i] = rec[(f + P1::D + i) * st]; }
+      f += 2 * P1::D;
+    }
+    if constexpr (P2::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { B.s[i] = rec[(f + i) * st]; B.z[i] = rec[(f + P2::D + i) * st]; }
+    }
   }
 
   // ---------------- main loop (static_solver2.jl:132-187) ----------------
@@ -758,15 +781,45 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
   // share each fetched instruction line instead of streaming the loop once per warp.
   int it = 0;
   bool active = (status == ST_OK);
+  bool parked = false;
   if (active) status = ST_PDIP_FAILED;
-  for (int k = 0;; k++) {
+  for (int k = k0;; k++) {
     const double mu = sz * inv_deg;
     if (active) {
       if (!(mu == mu)) { status = ST_NUMERICAL; active = false; it = k; }
       else if (mu < p.pdip_tol) { status = ST_OK; active = false; it = k; }
       else if (k == MAX_ITERS) { active = false; it = k; }
     }
-    if (!DCOL_VOTE(active)) break;
+    const int n_act = DCOL_COUNT(active);
+    if (n_act == 0) break;
+    if (n_act <= tc.spill_t && k > k0) {
+      // few stragglers left in this tile: park their iterates for the resume pass instead of keeping the whole CTA
+      // (and its idle lanes) in the loop until the slowest pair converges
+      if (active) {
+        const int slot = atomicAdd(tc.ov_count, 1);
+        double* rec = tc.ov + slot;
+        const int64_t st = tc.ov_cap;
+        rec[0] = (double)pair; rec[1 * st] = (double)k; rec[2 * st] = sz;
+        int f = 3;
+#pragma unroll
+        for (int a = 0; a < NX; a++) rec[(f + a) * st] = y[a];
+        f += NX;
+        const int nr = A.n + B.n;
+        for (int i = 0; i < nr; i++) { rec[(f + i) * st] = rs(F_S, i); rec[(f + nr + i) * st] = rs(F_Z, i); }
+        f += 2 * nr;
+        if constexpr (P1::D > 0) {
+#pragma unroll
+          for (int i = 0; i < P1::D; i++) { rec[(f + i) * st] = A.s[i]; rec[(f + P1::D + i) * st] = A.z[i]; }
+          f += 2 * P1::D;
+        }
+        if constexpr (P2::D > 0) {
+#pragma unroll
+          for (int i = 0; i < P2::D; i++) { rec[(f + i) * st] = B.s[i]; rec[(f + P2::D + i) * st] = B.z[i]; }
+        }
+        parked = true;
+      }
+      break;
+    }
     if (active) {
       double rhs[NX], dy[NX];
       double y1[NV1], y2[NV2];
@@ -821,6 +874,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
       }
     }
   }
+
+  if (parked) return;      // finished (and written) by the resume pass
 
   // ---------------- outputs ----------------
   Frame F1, F2;
@@ -957,8 +1012,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, int idx) {
 // Out-of-line entry of one specialisation (separate compilation: each class row lives in its own
 // translation unit and is device-linked into the persistent kernels of dcol_dispatch.cu).
 template <int C1, int C2, bool JAC>
-__device__ __noinline__ void solve_entry(const QueryParams* p, int idx) {
-  solve_pair<C1, C2, JAC>(*p, idx);
+__device__ __noinline__ void solve_entry(const QueryParams* p, const TileCtx* tc, int idx) {
+  solve_pair<C1, C2, JAC>(*p, *tc, idx);
 }
 
 }  // namespace dcol

@@ -213,6 +213,8 @@ __device__ __forceinline__ double soc_linesearch_m(const double (&y)[D], const d
 template <int CLS>
 struct Prim {
   static constexpr int NE = Cls<CLS>::NE, NV = 4 + Cls<CLS>::NE, D = Cls<CLS>::D, DD = (Cls<CLS>::D > 0 ? Cls<CLS>::D : 1);
+  // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes); elsewhere code size wins
+  static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE) ? 2 : 1;
   const double* rows; int n; int row0;
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
@@ -317,7 +319,7 @@ struct Prim {
     for (int a = 0; a < NV; a++) { g[a] = 0.0;
 #pragma unroll
       for (int b = a; b < NV; b++) N[a][b] = 0.0; }
-#pragma unroll 2
+#pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
@@ -399,7 +401,7 @@ struct Prim {
 
   // ---- pass B: affine direction; step bounds (reciprocal form: m = max -d/y); sums for rho; Mehrotra correction
   __device__ __forceinline__ void passB_rows(const RowStore& rs, const double (&dyh)[NV], double& m_s, double& m_z, double& dot1, double& dot2) {
-#pragma unroll 2
+#pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
 #pragma unroll
@@ -446,7 +448,7 @@ struct Prim {
   __device__ __forceinline__ void passC_rows(const RowStore& rs, double sigmu, double (&g2)[NV]) {
 #pragma unroll
     for (int a = 0; a < NV; a++) g2[a] = 0.0;
-#pragma unroll 2
+#pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       const double q = (sigmu - rs(F_P, row0 + i)) * rs(F_Z, row0 + i) * rs(F_R, row0 + i);
 #pragma unroll
@@ -478,7 +480,7 @@ struct Prim {
 
   // ---- pass D: final direction and step bounds; directions parked in F_RZ/F_P (rows) and rz/v (SOC)
   __device__ __forceinline__ void passD_rows(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& m_s, double& m_z) {
-#pragma unroll 2
+#pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
 #pragma unroll
@@ -514,7 +516,7 @@ struct Prim {
   // ---- pass E: take the step; returns the new s.z
   __device__ __forceinline__ double passE_rows(const RowStore& rs, double al) {
     double sz = 0.0;
-#pragma unroll 2
+#pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double a = rs(F_S, row0 + i) + al * rs(F_RZ, row0 + i), b = rs(F_Z, row0 + i) + al * rs(F_P, row0 + i);
       rs(F_S, row0 + i) = a; rs(F_Z, row0 + i) = b; sz += a * b;

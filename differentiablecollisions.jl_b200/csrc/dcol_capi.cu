@@ -571,7 +571,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     CK(ctx->d_out.need(b));
     dout = (char*)ctx->d_out.p;
   }
-  const bool jac = (query == Q_JAC);
+  const bool jac = (query != Q_PROX);          // derivative variant of the kernels (gradient and Jacobian)
   cudaStream_t S = ctx->stream();
   cudaStream_t SC = (nchunks > 1) ? ctx->s_comp : S;          // compute stream of the pipeline
   if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_fork, S)); CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(SC, ctx->ev_fork, 0)); }

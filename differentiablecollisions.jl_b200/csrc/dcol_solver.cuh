@@ -677,8 +677,8 @@ struct PairMap {
 };
 
 // One pair: relative pose -> initial point -> PDIP loop -> outputs (+ derivative epilogue).
-// JAC selects the kernel variant that carries the implicit-function-theorem epilogue; the
-// gradient epilogue is a few dozen flops and lives in the JAC=false variant behind p.query.
+// JAC selects the kernel variant that carries the derivative epilogues (gradient and implicit-function-theorem
+// Jacobian, chosen by p.query); the proximity variant has none, which keeps its code small.
 template <int C1, int C2, bool JAC>
 __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& tc, int idx) {
   using P1 = Prim<C1>; using P2 = Prim<C2>;
@@ -890,7 +890,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   if (p.iters) p.iters[pair] = it;
   const int nt = 6 + 2 * na;
 
-  if constexpr (!JAC) {
+  // The derivative variant (JAC = true) serves both derivative queries; the proximity variant carries no epilogue.
+  if constexpr (JAC) {
     // ---- proximity_gradient (src/proximity_gradient.jl:41-78): -z' du/dtheta
     if (p.query == Q_GRAD) {
       double* g = p.deriv + (int64_t)nt * pair;
@@ -905,8 +906,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
       } else {
         for (int j = 0; j < nt; j++) g[j] = __longlong_as_double(0x7ff8000000000000LL);
       }
+      if (p.status) p.status[pair] = status;
+      return;
     }
-  } else {
     // ---- proximity_jacobian (src/proximity.jl:71-134): reduced KKT solve in primitive-1's frame
     double* Jo = p.deriv + (int64_t)4 * nt * pair;
     bool ok = (status == ST_OK);

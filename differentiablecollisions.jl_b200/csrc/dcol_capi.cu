@@ -171,13 +171,15 @@ __global__ void k_build_tables(LaunchTable* __restrict__ tables, int n_tiers, co
       ov += (long long)T.ov_cap[k] * T.ov_stride[k];
     }
     for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
-    T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0;
+    T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0; T.in_base = ov_base;
   }
 }
-// resume-pass tables from the overflow counts the first pass left behind
+// resume-pass tables from the overflow counts the previous pass left behind; the resume pass may itself hand its
+// stragglers over (spill > 0) into the other overflow buffer
 __global__ void k_build_tables2(const LaunchTable* __restrict__ tables, LaunchTable* __restrict__ tables2, int n_tiers,
-                                const int* __restrict__ tile_sz) {
+                                const int* __restrict__ tile_sz, double* ov_next, int spill) {
   if (threadIdx.x || blockIdx.x) return;
+  long long ov = 0;
   for (int t = 0; t < n_tiers; t++) {
     const LaunchTable& T = tables[t];
     LaunchTable& U = tables2[t];
@@ -185,13 +187,17 @@ __global__ void k_build_tables2(const LaunchTable* __restrict__ tables, LaunchTa
     int tiles = 0;
     for (int k = 0; k < T.n_bins; k++) {
       const int cnt = min(T.ov_count[k], T.ov_cap[k]);
+      const int nt = (cnt + tile - 1) / tile;
       U.begin[k] = 0; U.end[k] = cnt; U.cp[k] = T.cp[k];
       U.tile_prefix[k] = tiles;
-      tiles += (cnt + tile - 1) / tile;
-      U.ov_cap[k] = T.ov_cap[k]; U.ov_off[k] = T.ov_off[k]; U.ov_count[k] = cnt; U.ov_stride[k] = T.ov_stride[k];
+      tiles += nt;
+      U.in_cap[k] = T.ov_cap[k]; U.in_off[k] = T.ov_off[k]; U.ov_stride[k] = T.ov_stride[k];
+      U.ov_cap[k] = spill ? nt * T.spill_t : 0; U.ov_off[k] = ov; U.ov_count[k] = 0;
+      ov += (long long)U.ov_cap[k] * U.ov_stride[k];
     }
     for (int k = T.n_bins; k <= MAX_BINS; k++) U.tile_prefix[k] = tiles;
-    U.n_bins = T.n_bins; U.n_tiles = tiles; U.ov_base = T.ov_base; U.mode = 1; U.spill_t = 0; U.rows_cap = T.rows_cap;
+    U.n_bins = T.n_bins; U.n_tiles = tiles; U.in_base = T.ov_base; U.ov_base = ov_next; U.mode = 1;
+    U.spill_t = spill ? T.spill_t : 0; U.rows_cap = T.rows_cap;
   }
 }
 
@@ -525,14 +531,17 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   }
   const int nk = ctx->n_keys;
   const int nt_tiers = (int)ctx->tiers.size();
-  const size_t hist_ints = 3 * (size_t)nk + 16 + 3 * NSIDE;       // hist | off | cursor | bad | counters (2 passes) | tile sizes
+  constexpr int MAX_LEVELS = 3;                                     // resume passes after the first pass
+  const size_t hist_ints = 3 * (size_t)nk + 16 + (2 + MAX_LEVELS) * NSIDE;   // hist | off | cursor | bad | counters per pass | tile sizes
   const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
   CK(ctx->d_perm.need(sizeof(int32_t) * n));
   CK(ctx->d_hist.need(sizeof(int) * hist_stride * nchunks));
-  CK(ctx->d_tables.need(sizeof(LaunchTable) * 2 * std::max(1, nt_tiers) * nchunks));
+  CK(ctx->d_tables.need(sizeof(LaunchTable) * (1 + MAX_LEVELS) * std::max(1, nt_tiers) * nchunks));
   // straggler overflow area per chunk (upper bound: every tile hands over spill_t pairs of the widest record)
   int spill_div = 8;
   if (const char* e = getenv("DCOL_SPILL")) spill_div = atoi(e);          // 0 disables the hand-over; default tile/8
+  int levels = 1;                                                           // resume passes (each may hand over again, except the last)
+  if (const char* e = getenv("DCOL_LEVELS")) levels = std::max(1, std::min(MAX_LEVELS, atoi(e)));
   const int64_t chunk_max = (n + nchunks - 1) / nchunks;
   size_t ov_doubles = 0;
   for (int t = 0; t < nt_tiers; t++) {
@@ -541,7 +550,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     ov_doubles += (size_t)(chunk_max / TR.block + TR.n_bins + 1) * spill_t * TR.max_stride;
   }
   ov_doubles = (ov_doubles + 31) & ~(size_t)31;
-  CK(ctx->d_ov.need(sizeof(double) * std::max<size_t>(ov_doubles, 32) * nchunks));
+  CK(ctx->d_ov.need(sizeof(double) * std::max<size_t>(ov_doubles, 32) * 2 * nchunks));
 
   size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
   size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0;
@@ -634,12 +643,10 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     int* d_cursor = d_off + nk + 1;      // nk
     int* d_bad = d_cursor + nk;          // 1
     int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier
-    int* d_counter2 = d_counter + NSIDE; // same for the resume pass
-    int* d_tile = d_counter2 + NSIDE + 1; // tile size per tier
+    int* d_tile = d_counter + (1 + MAX_LEVELS) * NSIDE + 1; // tile size per tier (after the per-pass counters)
     int32_t* d_perm = (int32_t*)ctx->d_perm.p + c0;
-    LaunchTable* d_tab = (LaunchTable*)ctx->d_tables.p + (size_t)2 * std::max(1, nt_tiers) * c;
-    LaunchTable* d_tab2 = d_tab + std::max(1, nt_tiers);
-    double* d_ovc = (double*)ctx->d_ov.p + ov_doubles * c;
+    LaunchTable* d_tab = (LaunchTable*)ctx->d_tables.p + (size_t)(1 + MAX_LEVELS) * std::max(1, nt_tiers) * c;
+    double* d_ovc = (double*)ctx->d_ov.p + 2 * ov_doubles * c;
     P.perm = d_perm;
     CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
     CK(cudaMemcpyAsync(d_tile, h_tile.data(), sizeof(int) * NSIDE, cudaMemcpyHostToDevice, SC));
@@ -651,7 +658,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; T.ov_stride[k] = TR.ov_stride[k]; }
     }
     CK(cudaMemcpyAsync(d_tab, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
-    CK(cudaMemcpyAsync(d_tab2, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
+    for (int lv = 1; lv <= levels && spill_div > 0; lv++)
+      CK(cudaMemcpyAsync(d_tab + (size_t)lv * std::max(1, nt_tiers), tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
     const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
     {
       int threads = 256;
@@ -673,15 +681,17 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       ctx->launches++;
       if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
     }
-    if (spill_div > 0) {        // resume pass: finish the handed-over stragglers in dense tiles
-      k_build_tables2<<<1, 32, 0, SC>>>(d_tab, d_tab2, nt_tiers, d_tile);
+    for (int lv = 1; lv <= levels && spill_div > 0; lv++) {        // resume passes: finish the handed-over stragglers in dense tiles
+      LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers);
+      LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers);
+      k_build_tables2<<<1, 32, 0, SC>>>(prev, cur, nt_tiers, d_tile, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
       ctx->launches++;
       if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
       for (int t = 0; t < nt_tiers; t++) {
         const dcol_ctx::Tier& TR = ctx->tiers[t];
         cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
         if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
-        CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, d_tab2 + t, d_counter2 + t));
+        CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, cur + t, d_counter + lv * NSIDE + t));
         ctx->launches++;
         if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
       }

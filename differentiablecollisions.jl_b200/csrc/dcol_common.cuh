@@ -81,20 +81,25 @@ struct LaunchTable {
   // straggler hand-over: when at most spill_t pairs of a tile are still iterating, they park their iterate in the
   // bin's overflow list and the tile ends; a second (resume) launch finishes them in dense tiles
   int spill_t;
-  double* ov_base;
+  double* ov_base;                 // records this pass WRITES (hand-over target)
   long long ov_off[MAX_BINS];      // start of bin b's overflow records (doubles), SoA with stride ov_cap[b]
   int ov_cap[MAX_BINS];            // record capacity of bin b
-  int ov_count[MAX_BINS];          // records written (first pass, atomics)
+  int ov_count[MAX_BINS];          // records written (atomics)
   int ov_stride[MAX_BINS];         // doubles per record: 3 + nx + 2*rows + 2*(d1+d2)
+  double* in_base;                 // records this pass READS (resume passes)
+  long long in_off[MAX_BINS];
+  int in_cap[MAX_BINS];
 };
 
 // what one tile needs to know beyond the query parameters
 struct TileCtx {
   int mode;                        // 0 first pass, 1 resume
   int spill_t;                     // 0: never hand over
-  double* ov;                      // this bin's overflow records
+  double* ov;                      // this bin's hand-over records (written)
   int ov_cap;
   int* ov_count;
+  const double* in;                // this bin's records to resume from (mode 1)
+  int in_cap;
 };
 
 }  // namespace dcol

@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(DCOL_MAXTHREADS, 1) proximity_persistent(Launc
     const int idx = min(__ldg(&tt->begin[b]) + (tile - __ldg(&tt->tile_prefix[b])) * tile_sz + (int)threadIdx.x, last);
     const int cp = __ldg(&tt->cp[b]);
     TileCtx tc;
-    tc.mode = tt->mode; tc.spill_t = (tt->mode == 0 && tt->ov_cap[b] > 0) ? tt->spill_t : 0;
+    tc.mode = tt->mode; tc.spill_t = (tt->ov_cap[b] > 0) ? tt->spill_t : 0;
     tc.ov = tt->ov_base + tt->ov_off[b]; tc.ov_cap = tt->ov_cap[b]; tc.ov_count = &tt->ov_count[b];
+    tc.in = tt->in_base + tt->in_off[b]; tc.in_cap = tt->in_cap[b];
     const int c1 = cp / NCLS, c2 = cp - c1 * NCLS;
     switch (c1) {
       case 0: dispatch_c2<0, JAC>(c2, &tt->P, &tc, idx); break;

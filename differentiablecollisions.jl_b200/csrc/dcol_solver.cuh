@@ -686,7 +686,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
 
   // first pass: idx is a position of the sorted pair list; resume pass: idx is a slot of the bin's overflow list
-  const int pair = (tc.mode == 0) ? p.perm[idx] : (int)tc.ov[idx];
+  const int pair = (tc.mode == 0) ? p.perm[idx] : (int)tc.in[idx];
   const DevShape* S1 = p.shapes + p.shape1[pair];
   const DevShape* S2 = p.shapes + p.shape2[pair];
   const int na = (p.att_kind == 0) ? 4 : 3;
@@ -756,8 +756,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     if (!ok) status = ST_NUMERICAL;
   } else {
     // ---------------- resume: reload the iterate parked by the first pass ----------------
-    const double* rec = tc.ov + idx;
-    const int64_t st = tc.ov_cap;
+    const double* rec = tc.in + idx;
+    const int64_t st = tc.in_cap;
     k0 = (int)rec[1 * st]; sz = rec[2 * st];
     int f = 3;
 #pragma unroll

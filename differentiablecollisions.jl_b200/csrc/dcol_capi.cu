@@ -61,7 +61,7 @@ struct dcol_ctx {
   int max_rows_cls[NCLS] = {};
   DevBuf d_shapes, d_rows, d_cls, d_keymap;
   // static launch plan derived from the shape table (dcol_set_shapes): one entry per shared-memory tier
-  struct Tier { int n_bins = 0, rows_cap = 0, block = 0; size_t smem = 0; int grid[2] = {0, 0};
+  struct Tier { int n_bins = 0, rows_cap = 0, block = 0, pitch = 1; size_t smem = 0; int grid[2] = {0, 0};
                 int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; int ov_stride[MAX_BINS]; int max_stride = 0; };
   std::vector<Tier> tiers;
   // per-call scratch (one slot per pipelined chunk)
@@ -412,7 +412,7 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   // capacity a pair of that class pair can need; inside a tier the heaviest class pairs are queued first
   ctx->tiers.clear();
   {
-    static const int tier_cap[] = {8, 16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32)};
+    static const int tier_cap[] = {8, 16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 1};
     constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
     bool present[NCLS] = {};
     for (int i = 0; i < n_shapes; i++) present[cls[i]] = true;
@@ -441,11 +441,12 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
         T.ov_stride[k] = 3 + 4 + cls_ne(c1) + cls_ne(c2) + 2 * (ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]) + 2 * (cls_d(c1) + cls_d(c2));
         T.max_stride = std::max(T.max_stride, T.ov_stride[k]);
       }
-      int warps = std::min(DCOL_MAXTHREADS / 32, (MAX_SMEM - 1024) / (T.rows_cap * NFIELD * (int)sizeof(double) * 32));
+      T.pitch = (T.rows_cap * NFIELD) | 1;      // odd pitch: conflict-free 64-bit shared-memory accesses
+      int warps = std::min(DCOL_MAXTHREADS / 32, (MAX_SMEM - 1024) / (T.pitch * (int)sizeof(double) * 32));
       warps = std::max(1, warps);
       if (const char* e = getenv("DCOL_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));   // tuning knob
       T.block = 32 * warps;
-      T.smem = (size_t)T.rows_cap * NFIELD * sizeof(double) * T.block;
+      T.smem = (size_t)T.pitch * sizeof(double) * T.block;
       for (int jac = 0; jac < 2; jac++) {
         const void* kfn = persistent_kernel_ptr(jac != 0);
         if (T.smem > 48 * 1024) CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_SMEM - 1024)));
@@ -654,7 +655,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       const dcol_ctx::Tier& TR = ctx->tiers[t];
       LaunchTable& T = tables[t];
       memset(&T, 0, sizeof(T));
-      T.P = P; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap; T.spill_t = spill_div > 0 ? TR.block / spill_div : 0;
+      T.P = P; T.P.row_pitch = TR.pitch; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap; T.spill_t = spill_div > 0 ? TR.block / spill_div : 0;
       for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; T.ov_stride[k] = TR.ov_stride[k]; }
     }
     CK(cudaMemcpyAsync(d_tab, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));

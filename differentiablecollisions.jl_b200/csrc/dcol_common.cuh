@@ -57,6 +57,7 @@ struct QueryParams {
   const double* r1;  const double* att1;
   const double* r2;  const double* att2;
   int att_kind;                  // 0 quaternion (stride 4), 1 MRP (stride 3)
+  int row_pitch;                 // doubles of shared-memory row store per thread (odd)
   double pdip_tol;
   double* alpha; double* x; int32_t* status; int32_t* iters;
   double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major

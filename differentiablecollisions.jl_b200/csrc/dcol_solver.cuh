@@ -65,9 +65,12 @@ __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 
 // The dynamic shared memory of the persistent kernel, declared here (not passed as a pointer through the
 // out-of-line entry) so that accesses compile to LDS/STS instead of generic loads and stores.
 extern __shared__ double dcol_dyn_smem[];
+// Each thread owns a contiguous run of `pitch` doubles (pitch odd, >= rows_cap*NFIELD): field f of row i is at
+// [threadIdx.x*pitch + i*NFIELD + f], so the field offset folds into the LDS/STS immediate and only the row index
+// costs an address instruction; an odd pitch spreads the 16 lanes of a 64-bit wavefront over all banks.
 struct RowStore {
-  int tid, stride;            // element (f, i) of this thread lives at [(i*NFIELD + f)*blockDim.x + threadIdx.x]
-  __device__ __forceinline__ double& operator()(int f, int i) const { return dcol_dyn_smem[(i * NFIELD + f) * stride + tid]; }
+  double* base;
+  __device__ __forceinline__ double& operator()(int f, int i) const { return base[i * NFIELD + f]; }
 };
 
 // ---------------------------------------------------------------------------
@@ -694,7 +697,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   const int64_t i1 = p.pose1 ? (int64_t)p.pose1[pair] : (int64_t)pair;
   const int64_t i2 = p.pose2 ? (int64_t)p.pose2[pair] : (int64_t)pair;
 
-  RowStore rs{(int)threadIdx.x, (int)blockDim.x};
+  RowStore rs{dcol_dyn_smem + (size_t)threadIdx.x * p.row_pitch};
   P1 A; P2 B;
   A.load(S1, p.rows, 0);
   B.load(S2, p.rows, A.n);

@@ -273,7 +273,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         threads = orc.max_threads()
-        sample = 400_000
+        sample = 250_000 * threads                     # ~10-20 s of CPU work in total across the threads
         t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sample, dc.ATT_QUAT, seed=1234, variant=args.variant)
         orc.query(0, t.arrays(), s1[:20000], s2[:20000], r1[:20000], a1[:20000], r2[:20000], a2[:20000], 0, PDIP_TOL)
         t0 = time.perf_counter()
@@ -281,11 +281,12 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{sample} pairs of the config-2 workload, C++ restatement of the Julia reference, std::thread x{threads}"}
-        sj = 200_000
+        sj = 100_000 * threads
         t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sj, dc.ATT_MRP, seed=4321, variant=args.variant)
         t0 = time.perf_counter()
         orc.query(2, t.arrays(), s1, s2, r1, a1, r2, a2, 1, PDIP_TOL)
         cpu["jacobian_value"] = sj / (time.perf_counter() - t0)
+        cpu["jacobian_sample"] = f"{sj} pairs of the config-3 workload (mixed, MRP)"
 
     if rank == 0:
         peaks = {}
@@ -296,12 +297,20 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
 
-        def roof(r):
+        traffic = {}
+        try:   # DRAM bytes per launch of the solver kernel from one `ncu --set full` capture of this workload (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+
+        def roof(r, key):
             ach = r["flops"] / (r["kernel_ms"] * 1e-3) / 1e12
             gbs = (r["in_bytes"] + r["out_bytes"]) / (r["kernel_ms"] * 1e-3) / 1e9
             return {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                     "peak_source": "DFMA micro-benchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
-                    "traffic": None, "kernel_ms_per_step": r["kernel_ms"], "algorithmic_flops_per_pair": r["flops"] / r["n"],
+                    "traffic": traffic.get(key, {}).get("dram_bytes_per_step") if traffic.get(key, {}).get("pairs") == r["n"] else None,
+                    "traffic_source": traffic.get(key, {}).get("source"),
+                    "kernel_ms_per_step": r["kernel_ms"], "algorithmic_flops_per_pair": r["flops"] / r["n"],
                     "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                             "peak_source": hbm_src, "algorithmic_bytes_per_pair": (r["in_bytes"] + r["out_bytes"]) / r["n"]}}
 
@@ -311,7 +320,7 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "e2e": {"value": world * prox["n"] * prox["e2e_steps"] / prox["e2e_s"], "unit": UNIT,
                         "h2d_bytes_per_step": prox["in_bytes"], "d2h_bytes_per_step": prox["out_bytes"]},
-                "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox),
+                "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox, "proximity"),
                 "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
         if cpu:
             line["cpu_baseline"] = cpu
@@ -324,7 +333,7 @@ def main():
                            "pairs_per_gpu": jac["n"], "global_pairs": jac["n"] * world},
                 "e2e": {"value": world * jac["n"] * jac["e2e_steps"] / jac["e2e_s"], "unit": UNIT,
                         "h2d_bytes_per_step": jac["in_bytes"], "d2h_bytes_per_step": jac["out_bytes"]},
-                "gpu_launches": jac["launches"], "clocks": jac["clocks"], "roofline": roof(jac),
+                "gpu_launches": jac["launches"], "clocks": jac["clocks"], "roofline": roof(jac, "jacobian"),
                 "solver": {"mean_iters": jac["mean_iters"], "max_iters": jac["max_iters"], "failed_pairs": jac["failed"]}}
         print(json.dumps(line), flush=True)
     ctx.close()

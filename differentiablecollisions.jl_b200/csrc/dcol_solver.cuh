@@ -32,26 +32,22 @@ namespace dcol {
 
 // ---------------------------------------------------------------------------
 // branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H,
-// ~20 good bits) + two Newton steps.  No slow-path calls: operands here are positive, normal
+// ~20 good bits) + one cubically convergent step.  No slow-path calls: operands here are positive, normal
 // numbers (failures are flagged by explicit `ok` tests before the result is used), and the
 // straight-line form keeps the solver passes in large basic blocks the scheduler can interleave.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-x, y, 1.0);            // seed error e ~ 2^-20
+  return fma(y, fma(e, e, e), y);              // y (1 + e + e^2): cubic step, error e^3 ~ 2^-60
 }
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double h = 0.5 * x;
-  double e = fma(-h * y, y, 0.5);      // 0.5 - 0.5 x y^2
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  return fma(y, e, y);
+  const double e = fma(-x * y, y, 1.0);        // 1 - x y^2
+  const double p = fma(e, 0.375, 0.5) * e;     // e/2 + 3 e^2 / 8
+  return fma(y, p, y);                         // cubic step
 }
 __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 0
   double r = fast_rsqrt(fmax(x, 1e-300));

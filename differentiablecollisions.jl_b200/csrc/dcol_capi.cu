@@ -412,7 +412,7 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   // capacity a pair of that class pair can need; inside a tier the heaviest class pairs are queued first
   ctx->tiers.clear();
   {
-    static const int tier_cap[] = {8, 16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 1};
+    static const int tier_cap[] = {8, 16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 4};
     constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
     bool present[NCLS] = {};
     for (int i = 0; i < n_shapes; i++) present[cls[i]] = true;
@@ -441,7 +441,7 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
         T.ov_stride[k] = 3 + 4 + cls_ne(c1) + cls_ne(c2) + 2 * (ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]) + 2 * (cls_d(c1) + cls_d(c2));
         T.max_stride = std::max(T.max_stride, T.ov_stride[k]);
       }
-      T.pitch = (T.rows_cap * NFIELD) | 1;      // odd pitch: conflict-free 64-bit shared-memory accesses
+      T.pitch = (12 + T.rows_cap * NFIELD) | 1; // relative pose (12) + rows; odd pitch: conflict-free 64-bit shared-memory accesses
       int warps = std::min(DCOL_MAXTHREADS / 32, (MAX_SMEM - 1024) / (T.pitch * (int)sizeof(double) * 32));
       warps = std::max(1, warps);
       if (const char* e = getenv("DCOL_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));   // tuning knob

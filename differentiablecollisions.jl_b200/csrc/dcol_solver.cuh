@@ -64,10 +64,15 @@ extern __shared__ double dcol_dyn_smem[];
 // Each thread owns a contiguous run of `pitch` doubles (pitch odd, >= rows_cap*NFIELD): field f of row i is at
 // [threadIdx.x*pitch + i*NFIELD + f], so the field offset folds into the LDS/STS immediate and only the row index
 // costs an address instruction; an odd pitch spreads the 16 lanes of a 64-bit wavefront over all banks.
+constexpr int POSE_SLOTS = 12;     // relative pose R (9, row-major) and t (3) of the pair, ahead of the rows
 struct RowStore {
   double* base;
-  __device__ __forceinline__ double& operator()(int f, int i) const { return base[i * NFIELD + f]; }
+  __device__ __forceinline__ double& operator()(int f, int i) const { return base[POSE_SLOTS + i * NFIELD + f]; }
 };
+// The relative pose is read 3-4 times per iteration but never written after set-up: it lives in shared memory
+// (LDS with immediate offsets) instead of 24 registers that the allocator would otherwise spill to local memory.
+struct RelPoseR { const double* p; __device__ __forceinline__ const double* operator[](int a) const { return p + 3 * a; } };
+struct RelPoseT { const double* p; __device__ __forceinline__ double operator[](int a) const { return p[9 + a]; } };
 
 // ---------------------------------------------------------------------------
 // small dense helpers (upper-triangular storage in full arrays; fully unrolled)
@@ -626,7 +631,9 @@ struct PairMap {
   __device__ static __forceinline__ constexpr int g2(int l) { return l < 4 ? l : 4 + NE1 + (l - 4); }   // prim-2 local -> pair index (l>=3)
 
   // local vectors from the pair vector; with_t adds the frame offset t to prim 2
-  __device__ static __forceinline__ void to_local(const double (&y)[NX], const double (&R)[3][3], const double (&t)[3], bool with_t,
+  // R and t are anything indexable as R[a][b], t[a]: register arrays or the shared-memory view RelPoseR / RelPoseT
+  template <class RM, class TV>
+  __device__ static __forceinline__ void to_local(const double (&y)[NX], const RM& R, const TV& t, bool with_t,
                                                   double (&y1)[NV1], double (&y2)[NV2]) {
 #pragma unroll
     for (int a = 0; a < NV1; a++) y1[a] = y[a];
@@ -637,7 +644,8 @@ struct PairMap {
     for (int a = 4; a < NV2; a++) y2[a] = y[g2(a)];
   }
   // M(upper) = embed(N1) + T' N2 T ; b = embed(g1) + T' g2
-  __device__ static __forceinline__ void assemble(const double (&N1)[NV1][NV1], const double (&N2)[NV2][NV2], const double (&R)[3][3],
+  template <class RM>
+  __device__ static __forceinline__ void assemble(const double (&N1)[NV1][NV1], const double (&N2)[NV2][NV2], const RM& R,
                                                   double (&M)[NX][NX]) {
 #pragma unroll
     for (int a = 0; a < NX; a++)
@@ -665,7 +673,8 @@ struct PairMap {
 #pragma unroll
       for (int m = l; m < NV2; m++) M[g2(l)][g2(m)] += N2[l][m];
   }
-  __device__ static __forceinline__ void assemble_vec(const double (&g1)[NV1], const double (&g2v)[NV2], const double (&R)[3][3], double (&b)[NX]) {
+  template <class RM>
+  __device__ static __forceinline__ void assemble_vec(const double (&g1)[NV1], const double (&g2v)[NV2], const RM& R, double (&b)[NX]) {
 #pragma unroll
     for (int a = 0; a < NX; a++) b[a] = (a < NV1) ? g1[a] : 0.0;
 #pragma unroll
@@ -698,9 +707,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   A.load(S1, p.rows, 0);
   B.load(S2, p.rows, A.n);
 
-  // relative pose
-  double R[3][3], t[3];
+  // relative pose (computed in registers, parked in shared memory for the rest of the solve)
   {
+    double R[3][3], t[3];
     Frame F1, F2;
     build_frame(S1, p.r1 + 3 * i1, p.att1 + na * i1, p.att_kind, F1);
     build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
@@ -711,7 +720,13 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
 #pragma unroll
       for (int b = 0; b < 3; b++) R[a][b] = F2.Q[0][a] * F1.Q[0][b] + F2.Q[1][a] * F1.Q[1][b] + F2.Q[2][a] * F1.Q[2][b];
     }
+  #pragma unroll
+    for (int a = 0; a < 3; a++) { rs.base[9 + a] = t[a];
+#pragma unroll
+      for (int b = 0; b < 3; b++) rs.base[3 * a + b] = R[a][b]; }
   }
+  const RelPoseR R{rs.base};
+  const RelPoseT t{rs.base};
 
   double y[NX];
   double M[NX][NX], idg[NX];

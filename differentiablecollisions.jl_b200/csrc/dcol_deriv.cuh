@@ -158,8 +158,65 @@ __device__ void grad_side(const DevShape* S, const Frame& F, const double* att, 
 //   Ye = P4 (A'^-1)[0:4, extras of k]             (4xNE; dR1/dtheta has extras rows for the ball block)
 //   Hw = P4 (A'^-1)[0:4,0:3] Q_1'                 (4x3)
 template <int NE>
-__device__ void jac_side(const DevShape* S, const Frame& F, const double* att, int att_kind,
-                         const double (&K)[4][3], const double (&Kb)[4][3], const double (&Ye)[4][2],
-                         const double (&Hw)[4][3], const SideVecs& V, double* out);
+__device__ __forceinline__ void jac_side(const DevShape* S, const Frame& F, const double* att, int att_kind,
+                                         const double (&K)[4][3], const double (&Kb)[4][3], const double (&Ye)[4][2],
+                                         const double (&Hw)[4][3], const SideVecs& V, double* out) {
+  const bool off = S->has_offset != 0;
+  double KW[4][3], KrQ[4][3], KrW[4][3], KbW[4][3], v[3], a[3], ob[3], gzb[3];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double Kr[3] = {K[i][0] - Kb[i][0], K[i][1] - Kb[i][1], K[i][2] - Kb[i][2]};
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      KrW[i][p] = Kr[0] * F.Q[p][0] + Kr[1] * F.Q[p][1] + Kr[2] * F.Q[p][2];
+      KbW[i][p] = Kb[i][0] * F.Q[p][0] + Kb[i][1] * F.Q[p][1] + Kb[i][2] * F.Q[p][2];
+      KW[i][p] = KrW[i][p] + KbW[i][p];
+      KrQ[i][p] = off ? (Kr[0] * S->Q_off[3 * p] + Kr[1] * S->Q_off[3 * p + 1] + Kr[2] * S->Q_off[3 * p + 2]) : Kr[p];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    v[i] = F.Q[i][0] * V.xt[0] + F.Q[i][1] * V.xt[1] + F.Q[i][2] * V.xt[2];
+    gzb[i] = F.Q[i][0] * V.zb[0] + F.Q[i][1] * V.zb[1] + F.Q[i][2] * V.zb[2];
+    a[i] = off ? (S->Q_off[3 * i] * V.wr[0] + S->Q_off[3 * i + 1] * V.wr[1] + S->Q_off[3 * i + 2] * V.wr[2]) : V.wr[i];
+    ob[i] = off ? (S->r_off[i] + S->Q_off[3 * i] * V.Be[0] + S->Q_off[3 * i + 1] * V.Be[1] + S->Q_off[3 * i + 2] * V.Be[2]) : V.Be[i];
+  }
+  double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+  for (int p = 0; p < 3; p++) { o2[2 * p] = make_double2(KW[0][p], KW[1][p]); o2[2 * p + 1] = make_double2(KW[2][p], KW[3][p]); }
+  const int na = (att_kind == 0) ? 4 : 3;
+  for (int j = 0; j < na; j++) {
+    double dQ[3][3];
+    dcm_partial(att, att_kind, j, dQ);
+    double tv[3], tg[3], da[3], dr[3], dob[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      tv[q] = dQ[0][q] * v[0] + dQ[1][q] * v[1] + dQ[2][q] * v[2];        // dQ' v
+      tg[q] = dQ[0][q] * gzb[0] + dQ[1][q] * gzb[1] + dQ[2][q] * gzb[2];  // dQ' (Q zb)
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      da[p] = dQ[p][0] * a[0] + dQ[p][1] * a[1] + dQ[p][2] * a[2];
+      dob[p] = dQ[p][0] * ob[0] + dQ[p][1] * ob[1] + dQ[p][2] * ob[2];      // dQ (r_off + Q_off B~ e)
+      dr[p] = off ? (dQ[p][0] * S->r_off[0] + dQ[p][1] * S->r_off[1] + dQ[p][2] * S->r_off[2]) : 0.0;
+    }
+    double em[2] = {0.0, 0.0};                                              // Q_off[:,m] . tg
+#pragma unroll
+    for (int m = 0; m < NE; m++) em[m] = off ? (S->Q_off[m] * tg[0] + S->Q_off[3 + m] * tg[1] + S->Q_off[6 + m] * tg[2]) : tg[m];
+    double c[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double acc = Hw[i][0] * da[0] + Hw[i][1] * da[1] + Hw[i][2] * da[2];
+      acc -= KrQ[i][0] * tv[0] + KrQ[i][1] * tv[1] + KrQ[i][2] * tv[2];
+      acc += KbW[i][0] * dob[0] + KbW[i][1] * dob[1] + KbW[i][2] * dob[2];
+      if (off) acc += KrW[i][0] * dr[0] + KrW[i][1] * dr[1] + KrW[i][2] * dr[2];
+#pragma unroll
+      for (int m = 0; m < NE; m++) acc -= Ye[i][m] * em[m];
+      c[i] = acc;
+    }
+    o2[2 * (3 + j)] = make_double2(c[0], c[1]); o2[2 * (3 + j) + 1] = make_double2(c[2], c[3]);
+  }
+}
+
 
 }  // namespace dcol

@@ -140,9 +140,10 @@ __device__ __forceinline__ bool ge_solve(double (&A)[N][N], double (&B)[N][NR]) 
 // block's z (body coords), Be = B~ e (body coords), xt = x~ (body coords).
 struct SideVecs { double wr[3], zb[3], Be[3], xt[3]; };
 
-// The three routines below are class-independent and are compiled ONCE (dcol_shared.cu, out of line):
-// every specialisation calls the same code, which therefore stays resident in the instruction caches
-// while the persistent kernel moves from one class pair to the next.
+// build_frame and grad_side are class-independent and are compiled ONCE (dcol_shared.cu, out of line): every
+// specialisation calls the same code, which therefore stays resident in the instruction caches while the
+// persistent kernel moves from one class pair to the next.  jac_side is inlined: its 4x3 operands would
+// otherwise travel through local memory (measured: -11 % Jacobian time on mixed batches).
 
 // r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
 __device__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F);

@@ -54,11 +54,4 @@ __device__ __noinline__ void grad_side(const DevShape* S, const Frame& F, const 
   }
 }
 
-// Jacobian columns of one primitive, written column-major (4 rows) at out[col*4 + row]:
-// columns 0..2 = d/d r_k, 3..3+na = d/d att_k.
-//   K  = P4 (A'^-1 T_k'' N_k[:,0:3])[0:4]        (4x3, N_k = rest + ball)
-//   Kb = same with the ball part of N_k only      (4x3)
-//   Ye = P4 (A'^-1)[0:4, extras of k]             (4xNE; dR1/dtheta has extras rows for the ball block)
-//   Hw = P4 (A'^-1)[0:4,0:3] Q_1'                 (4x3)
-
 }  // namespace dcol

@@ -543,7 +543,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (const char* e = getenv("DCOL_SPILL")) spill_div = atoi(e);          // 0 disables the hand-over; default tile/8
   int levels = 1;                                                           // resume passes (each may hand over again, except the last)
   if (const char* e = getenv("DCOL_LEVELS")) levels = std::max(1, std::min(MAX_LEVELS, atoi(e)));
-  const int64_t chunk_max = (n + nchunks - 1) / nchunks;
+  const int64_t chunk_max = (nchunks > 1) ? (n + nchunks - 2) / (nchunks - 1) : n;
   size_t ov_doubles = 0;
   for (int t = 0; t < nt_tiers; t++) {
     const dcol_ctx::Tier& TR = ctx->tiers[t];
@@ -596,8 +596,16 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     CK(cudaMemcpyAsync(di + o_r2, r2, sizeof(double) * 3 * np2, cudaMemcpyHostToDevice, SI));
     CK(cudaMemcpyAsync(di + o_a2, att2, sizeof(double) * na * np2, cudaMemcpyHostToDevice, SI));
   }
+  // chunk boundaries: a short first chunk lets the kernels start early while the bulk is still crossing PCIe
+  std::vector<int64_t> cb(nchunks + 1, 0);
+  {
+    const int64_t first = (nchunks > 1) ? std::min<int64_t>(n / (2 * nchunks), 120000) : n;
+    cb[nchunks] = n;
+    for (int c = 1; c < nchunks; c++) cb[c] = first + (n - first) * (c - 1) / (nchunks - 1);
+    if (nchunks > 1) cb[1] = first;
+  }
   for (int c = 0; c < nchunks; c++) {
-    const int64_t c0 = n * c / nchunks, c1 = n * (c + 1) / nchunks, nc = c1 - c0;
+    const int64_t c0 = cb[c], c1 = cb[c + 1], nc = c1 - c0;
     QueryParams P;
     memset(&P, 0, sizeof(P));
     P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;

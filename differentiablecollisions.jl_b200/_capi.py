@@ -35,6 +35,9 @@ SYMBOLS = {
     "dcol_scene_pair_count": (C.c_int64, [C.c_int]),
     "dcol_scene_allpairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "dcol_launch_count": (C.c_int64, [C.c_void_p]),
     "dcol_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),
@@ -54,6 +57,8 @@ def load():
             "(nvcc, sm_100a). dcol_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
+        if os.environ.get("DCOL_B200_LIB") and not hasattr(lib, name):
+            continue             # A/B runs against an older build selected through DCOL_B200_LIB
         fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args

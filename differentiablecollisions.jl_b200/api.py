@@ -106,6 +106,20 @@ class Context:
             rc = self._lib.dcol_proximity_jacobian(*args, _ptr(alpha), _ptr(x), _ptr(deriv), _ptr(status), _ptr(iters))
         self._check(rc)
 
+    # ---- asynchronous submissions (host buffers; keep them alive until wait) ---------------------------
+    def submit_raw(self, kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, alpha, x, deriv, status, iters) -> int:
+        """`dcol_submit`: enqueue one host-buffer query and return its ticket; up to two may be in flight."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        t = self._lib.dcol_submit(self._h, int(kind), int(n), _ptr(shape1), _ptr(shape2), _ptr(r1), _ptr(att1), _ptr(r2), _ptr(att2),
+                                  int(att_kind), float(pdip_tol), _ptr(alpha), _ptr(x), _ptr(deriv), _ptr(status), _ptr(iters))
+        if t < 0:
+            self._check(t)
+        return t
+
+    def wait(self, ticket: int):
+        self._check(self._lib.dcol_wait(self._h, int(ticket)))
+
     # ---- batched host API ----------------------------------------------------------------------
     def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol):
         shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)

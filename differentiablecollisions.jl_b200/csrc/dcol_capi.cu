@@ -64,11 +64,24 @@ struct dcol_ctx {
   struct Tier { int n_bins = 0, rows_cap = 0, block = 0, pitch = 1; size_t smem = 0; int grid[2] = {0, 0};
                 int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; int ov_stride[MAX_BINS]; int max_stride = 0; };
   std::vector<Tier> tiers;
-  // per-call scratch (one slot per pipelined chunk)
+  // per-call scratch.  Three slots, so that asynchronous submissions (dcol_submit) overlap: one staging its inputs,
+  // one computing, one returning results; the synchronous entry points use slot 0.
   static constexpr int MAX_CHUNKS = 8;
-  DevBuf d_in, d_out, d_perm, d_hist, d_tables, d_scene, d_pairs, d_ov;
+  static constexpr int N_SLOTS = 3;
+  struct Slot {
+    DevBuf d_in, d_out, d_perm, d_hist, d_tables, d_ov;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
+    cudaEvent_t ev_end = nullptr;       // recorded behind the last operation of the submission (its own join point)
+    bool pending = false; int ticket = -1, result = 0;
+    int nchunks = 0, nk = 0; size_t hist_stride = 0; bool piped = false;
+    // pinned landing area of the bad-index flags (a pageable destination would make the copy synchronous)
+    int* h_bad = nullptr;
+    double ms = -1.0;
+  };
+  Slot slots[N_SLOTS];
+  int next_ticket = 0;
+  DevBuf d_scene, d_pairs, d_plan;
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
-  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
   int n_sm = 148;
   int64_t launches = 0;
   double last_ms = -1.0;
@@ -150,16 +163,21 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
   }
 }
 
-// single thread: turns the static per-tier bin lists (key ranges parked in begin[]/end[]) into sorted-position ranges
-// and tile prefixes, from the bin offsets of this call — the host never needs the histogram.  Also carves the
-// straggler overflow area: bin b gets tiles_b * spill_t records (a tile hands over at most spill_t pairs).
-__global__ void k_build_tables(LaunchTable* __restrict__ tables, int n_tiers, const int* __restrict__ tile_sz,
-                               const int* __restrict__ off, double* ov_base) {
+// single thread: instantiates the static per-tier launch plan (uploaded once by dcol_set_shapes; key ranges parked in
+// begin[]/end[]) for this call — query parameters arrive as a kernel argument, bin offsets from the counting sort —
+// so that neither a host read of the histogram nor a host-to-device copy sits between the sort and the solver.
+// Also carves the straggler overflow area: bin b gets tiles_b * spill_t records (a tile hands over at most spill_t pairs).
+__global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
+                               const int* __restrict__ off, double* ov_base, QueryParams P, int spill_div) {
   if (threadIdx.x || blockIdx.x) return;
   long long ov = 0;
   for (int t = 0; t < n_tiers; t++) {
     LaunchTable& T = tables[t];
-    const int tile = tile_sz[t];
+    T = plan[t];
+    const int tile = T.n_tiles;            // the plan parks the tier's CTA size here
+    const int pitch = T.P.row_pitch;
+    T.P = P; T.P.row_pitch = pitch;
+    T.spill_t = spill_div > 0 ? tile / spill_div : 0;
     int tiles = 0;
     for (int k = 0; k < T.n_bins; k++) {
       const int b = off[T.begin[k]], e = off[T.end[k]];
@@ -172,18 +190,20 @@ __global__ void k_build_tables(LaunchTable* __restrict__ tables, int n_tiers, co
     }
     for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
     T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0; T.in_base = ov_base;
+    T.pad_tile = tile;
   }
 }
 // resume-pass tables from the overflow counts the previous pass left behind; the resume pass may itself hand its
 // stragglers over (spill > 0) into the other overflow buffer
 __global__ void k_build_tables2(const LaunchTable* __restrict__ tables, LaunchTable* __restrict__ tables2, int n_tiers,
-                                const int* __restrict__ tile_sz, double* ov_next, int spill) {
+                                double* ov_next, int spill) {
   if (threadIdx.x || blockIdx.x) return;
   long long ov = 0;
   for (int t = 0; t < n_tiers; t++) {
     const LaunchTable& T = tables[t];
     LaunchTable& U = tables2[t];
-    const int tile = tile_sz[t];
+    const int tile = T.pad_tile;
+    U.P = T.P; U.pad_tile = tile;
     int tiles = 0;
     for (int k = 0; k < T.n_bins; k++) {
       const int cnt = min(T.ov_count[k], T.ov_cap[k]);
@@ -269,11 +289,18 @@ int dcol_create(dcol_ctx** out, int device_id) {
   if ((e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-  for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-    if ((e = cudaEventCreate(&ctx->ev_t0[i])) != cudaSuccess) return fail("cudaEventCreate", e);
-    if ((e = cudaEventCreate(&ctx->ev_t1[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int k = 0; k < dcol_ctx::N_SLOTS; k++)
+    for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
+      dcol_ctx::Slot& L = ctx->slots[k];
+      if ((e = cudaEventCreateWithFlags(&L.ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+      if ((e = cudaEventCreateWithFlags(&L.ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+      if ((e = cudaEventCreate(&L.ev_t0[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+      if ((e = cudaEventCreate(&L.ev_t1[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+    }
+  for (int k = 0; k < dcol_ctx::N_SLOTS; k++) {
+    dcol_ctx::Slot& L = ctx->slots[k];
+    if ((e = cudaHostAlloc((void**)&L.h_bad, sizeof(int) * dcol_ctx::MAX_CHUNKS, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if ((e = cudaEventCreateWithFlags(&L.ev_end, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   }
   if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_k1)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -286,14 +313,21 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_in, &ctx->d_out, &ctx->d_perm, &ctx->d_hist, &ctx->d_tables, &ctx->d_scene, &ctx->d_pairs, &ctx->d_ov};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_scene, &ctx->d_pairs, &ctx->d_plan};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
-  for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
-    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
-    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
-    if (ctx->ev_t0[i]) cudaEventDestroy(ctx->ev_t0[i]);
-    if (ctx->ev_t1[i]) cudaEventDestroy(ctx->ev_t1[i]);
+  for (int k = 0; k < dcol_ctx::N_SLOTS; k++) {
+    dcol_ctx::Slot& L = ctx->slots[k];
+    for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
+      if (L.ev_in[i]) cudaEventDestroy(L.ev_in[i]);
+      if (L.ev_done[i]) cudaEventDestroy(L.ev_done[i]);
+      if (L.ev_t0[i]) cudaEventDestroy(L.ev_t0[i]);
+      if (L.ev_t1[i]) cudaEventDestroy(L.ev_t1[i]);
+    }
+    if (L.h_bad) cudaFreeHost(L.h_bad);
+    if (L.ev_end) cudaEventDestroy(L.ev_end);
+    DevBuf* lb[] = {&L.d_in, &L.d_out, &L.d_perm, &L.d_hist, &L.d_tables, &L.d_ov};
+    for (DevBuf* b : lb) b->release();
   }
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -456,6 +490,17 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
       }
       ctx->tiers.push_back(T);
     }
+    // device copy of the plan: one LaunchTable template per tier (key ranges in begin/end, CTA size in n_tiles, row pitch in P)
+    std::vector<LaunchTable> plan(std::max<size_t>(1, ctx->tiers.size()));
+    for (size_t t = 0; t < ctx->tiers.size(); t++) {
+      const dcol_ctx::Tier& TR = ctx->tiers[t];
+      LaunchTable& T = plan[t];
+      memset(&T, 0, sizeof(T));
+      T.P.row_pitch = TR.pitch; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap; T.n_tiles = TR.block;
+      for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; T.ov_stride[k] = TR.ov_stride[k]; }
+    }
+    CK(ctx->d_plan.need(sizeof(LaunchTable) * plan.size()));
+    CK(cudaMemcpy(ctx->d_plan.p, plan.data(), sizeof(LaunchTable) * plan.size(), cudaMemcpyHostToDevice));
   }
   return 0;
 }
@@ -491,6 +536,7 @@ double dcol_measure_fp64_tflops(dcol_ctx* ctx) {
 // query driver
 // ---------------------------------------------------------------------------
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+static int finish_query(dcol_ctx* ctx, int slot);
 
 // pose1/pose2 == NULL: r*/att* have one row per pair.  Otherwise they are tables of np1 / np2 rows and pair k uses
 // rows pose1[k] / pose2[k].  in_mem: where the INPUT arrays live (lets the scene operator feed device-generated
@@ -500,8 +546,10 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
                      int att_kind, double pdip_tol, int mem,
                      double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters,
                      const int32_t* pose1 = nullptr, const int32_t* pose2 = nullptr, int64_t np1 = 0, int64_t np2 = 0,
-                     int in_mem = -1) {
+                     int in_mem = -1, int slot = 0, bool async = false) {
   if (in_mem < 0) in_mem = mem;
+  dcol_ctx::Slot& L = ctx->slots[slot];
+  if (L.pending) { int rc = finish_query(ctx, slot); if (rc && !async) return rc; }
   const bool indexed = (pose1 != nullptr);
   if (!ctx) return -1;
   ctx->err.clear();
@@ -525,7 +573,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   // ---- chunking: device-pointer calls run as one chunk; host-pointer calls are split so that the H2D copy of
   // chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (three streams)
   int nchunks = 1;
-  if (mem == DCOL_MEM_HOST || in_mem == DCOL_MEM_HOST) {
+  if ((mem == DCOL_MEM_HOST || in_mem == DCOL_MEM_HOST) && !async) {      // asynchronous submissions overlap with each other instead
     int64_t target = 350000;
     if (const char* e = getenv("DCOL_CHUNK")) target = std::max<int64_t>(1024, atoll(e));
     nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(dcol_ctx::MAX_CHUNKS, (n + target / 2) / target));
@@ -535,9 +583,9 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   constexpr int MAX_LEVELS = 3;                                     // resume passes after the first pass
   const size_t hist_ints = 3 * (size_t)nk + 16 + (2 + MAX_LEVELS) * NSIDE;   // hist | off | cursor | bad | counters per pass | tile sizes
   const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
-  CK(ctx->d_perm.need(sizeof(int32_t) * n));
-  CK(ctx->d_hist.need(sizeof(int) * hist_stride * nchunks));
-  CK(ctx->d_tables.need(sizeof(LaunchTable) * (1 + MAX_LEVELS) * std::max(1, nt_tiers) * nchunks));
+  CK(L.d_perm.need(sizeof(int32_t) * n));
+  CK(L.d_hist.need(sizeof(int) * hist_stride * nchunks));
+  CK(L.d_tables.need(sizeof(LaunchTable) * (1 + MAX_LEVELS) * std::max(1, nt_tiers) * nchunks));
   // straggler overflow area per chunk (upper bound: every tile hands over spill_t pairs of the widest record)
   int spill_div = 8;
   if (const char* e = getenv("DCOL_SPILL")) spill_div = atoi(e);          // 0 disables the hand-over; default tile/8
@@ -551,7 +599,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     ov_doubles += (size_t)(chunk_max / TR.block + TR.n_bins + 1) * spill_t * TR.max_stride;
   }
   ov_doubles = (ov_doubles + 31) & ~(size_t)31;
-  CK(ctx->d_ov.need(sizeof(double) * std::max<size_t>(ov_doubles, 32) * 2 * nchunks));
+  CK(L.d_ov.need(sizeof(double) * std::max<size_t>(ov_doubles, 32) * 2 * nchunks));
 
   size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
   size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0;
@@ -568,8 +616,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     o_a1 = b; b += align256(sizeof(double) * na * rows1);
     o_r2 = b; b += align256(sizeof(double) * 3 * rows2);
     o_a2 = b; b += align256(sizeof(double) * na * rows2);
-    CK(ctx->d_in.need(b));
-    di = (char*)ctx->d_in.p;
+    CK(L.d_in.need(b));
+    di = (char*)L.d_in.p;
   }
   if (mem == DCOL_MEM_HOST) {
     size_t b = 0;
@@ -578,19 +626,17 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     o_der = b; b += align256(sizeof(double) * dsz * n);
     o_st = b; b += align256(sizeof(int32_t) * n);
     o_it = b; b += align256(sizeof(int32_t) * n);
-    CK(ctx->d_out.need(b));
-    dout = (char*)ctx->d_out.p;
+    CK(L.d_out.need(b));
+    dout = (char*)L.d_out.p;
   }
   const bool jac = (query != Q_PROX);          // derivative variant of the kernels (gradient and Jacobian)
   cudaStream_t S = ctx->stream();
-  cudaStream_t SC = (nchunks > 1) ? ctx->s_comp : S;          // compute stream of the pipeline
-  if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_fork, S)); CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(SC, ctx->ev_fork, 0)); }
-  std::vector<LaunchTable> tables(std::max(1, nt_tiers));
-  std::vector<int> h_tile(NSIDE, 0);
-  for (int t = 0; t < nt_tiers; t++) h_tile[t] = ctx->tiers[t].block;
+  const bool piped = (nchunks > 1) || async;                  // three-stream pipeline (always for asynchronous submissions)
+  cudaStream_t SC = piped ? ctx->s_comp : S;                  // compute stream of the pipeline
+  if (piped) { CK(cudaEventRecord(ctx->ev_fork, S)); CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(SC, ctx->ev_fork, 0)); }
 
   if (indexed && in_mem == DCOL_MEM_HOST) {       // pose tables go up once, ahead of the first chunk's pair lists
-    cudaStream_t SI = (nchunks > 1) ? ctx->s_copy : S;
+    cudaStream_t SI = piped ? ctx->s_copy : S;
     CK(cudaMemcpyAsync(di + o_r1, r1, sizeof(double) * 3 * np1, cudaMemcpyHostToDevice, SI));
     CK(cudaMemcpyAsync(di + o_a1, att1, sizeof(double) * na * np1, cudaMemcpyHostToDevice, SI));
     CK(cudaMemcpyAsync(di + o_r2, r2, sizeof(double) * 3 * np2, cudaMemcpyHostToDevice, SI));
@@ -611,7 +657,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
     P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query;
     if (in_mem == DCOL_MEM_HOST) {
-      cudaStream_t SI = (nchunks > 1) ? ctx->s_copy : S;
+      cudaStream_t SI = piped ? ctx->s_copy : S;
       CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       CK(cudaMemcpyAsync(di + o_s2 + sizeof(int32_t) * c0, shape2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       if (indexed) {
@@ -623,7 +669,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
         CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
         CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
       }
-      if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, ctx->ev_in[c], 0)); }
+      if (piped) { CK(cudaEventRecord(L.ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, L.ev_in[c], 0)); }
       P.shape1 = (const int32_t*)(di + o_s1) + c0; P.shape2 = (const int32_t*)(di + o_s2) + c0;
       if (indexed) {
         P.pose1 = (const int32_t*)(di + o_p1) + c0; P.pose2 = (const int32_t*)(di + o_p2) + c0;
@@ -647,28 +693,16 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       P.status = status ? status + c0 : nullptr; P.iters = iters ? iters + c0 : nullptr;
     }
     // ---- bin the chunk's pairs by key (device counting sort), build the tile tables on the device
-    int* d_hist = (int*)ctx->d_hist.p + hist_stride * c;
+    int* d_hist = (int*)L.d_hist.p + hist_stride * c;
     int* d_off = d_hist + nk;            // nk+1
     int* d_cursor = d_off + nk + 1;      // nk
     int* d_bad = d_cursor + nk;          // 1
     int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier
-    int* d_tile = d_counter + (1 + MAX_LEVELS) * NSIDE + 1; // tile size per tier (after the per-pass counters)
-    int32_t* d_perm = (int32_t*)ctx->d_perm.p + c0;
-    LaunchTable* d_tab = (LaunchTable*)ctx->d_tables.p + (size_t)(1 + MAX_LEVELS) * std::max(1, nt_tiers) * c;
-    double* d_ovc = (double*)ctx->d_ov.p + 2 * ov_doubles * c;
+    int32_t* d_perm = (int32_t*)L.d_perm.p + c0;
+    LaunchTable* d_tab = (LaunchTable*)L.d_tables.p + (size_t)(1 + MAX_LEVELS) * std::max(1, nt_tiers) * c;
+    double* d_ovc = (double*)L.d_ov.p + 2 * ov_doubles * c;
     P.perm = d_perm;
     CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
-    CK(cudaMemcpyAsync(d_tile, h_tile.data(), sizeof(int) * NSIDE, cudaMemcpyHostToDevice, SC));
-    for (int t = 0; t < nt_tiers; t++) {
-      const dcol_ctx::Tier& TR = ctx->tiers[t];
-      LaunchTable& T = tables[t];
-      memset(&T, 0, sizeof(T));
-      T.P = P; T.P.row_pitch = TR.pitch; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap; T.spill_t = spill_div > 0 ? TR.block / spill_div : 0;
-      for (int k = 0; k < TR.n_bins; k++) { T.cp[k] = TR.cp[k]; T.begin[k] = TR.key_begin[k]; T.end[k] = TR.key_end[k]; T.ov_stride[k] = TR.ov_stride[k]; }
-    }
-    CK(cudaMemcpyAsync(d_tab, tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
-    for (int lv = 1; lv <= levels && spill_div > 0; lv++)
-      CK(cudaMemcpyAsync(d_tab + (size_t)lv * std::max(1, nt_tiers), tables.data(), sizeof(LaunchTable) * nt_tiers, cudaMemcpyHostToDevice, SC));
     const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
     {
       int threads = 256;
@@ -676,11 +710,11 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
       k_scan<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor);
       k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_perm);
-      k_build_tables<<<1, 32, 0, SC>>>(d_tab, nt_tiers, d_tile, d_off, d_ovc);
+      k_build_tables<<<1, 32, 0, SC>>>((const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_off, d_ovc, P, spill_div);
       ctx->launches += 4;
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table
-    CK(cudaEventRecord(ctx->ev_t0[c], SC));
+    CK(cudaEventRecord(L.ev_t0[c], SC));
     if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
     for (int t = 0; t < nt_tiers; t++) {
       const dcol_ctx::Tier& TR = ctx->tiers[t];
@@ -693,7 +727,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     for (int lv = 1; lv <= levels && spill_div > 0; lv++) {        // resume passes: finish the handed-over stragglers in dense tiles
       LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers);
       LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers);
-      k_build_tables2<<<1, 32, 0, SC>>>(prev, cur, nt_tiers, d_tile, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
+      k_build_tables2<<<1, 32, 0, SC>>>(prev, cur, nt_tiers, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
       ctx->launches++;
       if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
       for (int t = 0; t < nt_tiers; t++) {
@@ -705,11 +739,11 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
         if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
       }
     }
-    CK(cudaEventRecord(ctx->ev_t1[c], SC));
+    CK(cudaEventRecord(L.ev_t1[c], SC));
     // ---- results of this chunk back (host mode), overlapping the next chunk's kernels
     if (mem == DCOL_MEM_HOST) {
-      cudaStream_t SO = (nchunks > 1) ? ctx->s_out : S;
-      if (nchunks > 1) { CK(cudaEventRecord(ctx->ev_done[c], SC)); CK(cudaStreamWaitEvent(SO, ctx->ev_done[c], 0)); }
+      cudaStream_t SO = piped ? ctx->s_out : S;
+      if (piped) { CK(cudaEventRecord(L.ev_done[c], SC)); CK(cudaStreamWaitEvent(SO, L.ev_done[c], 0)); }
       CK(cudaMemcpyAsync(alpha + c0, dout + o_alpha + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
       if (x) CK(cudaMemcpyAsync(x + 3 * c0, dout + o_x + sizeof(double) * 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, SO));
       if (dsz) CK(cudaMemcpyAsync(deriv + dsz * c0, dout + o_der + sizeof(double) * dsz * c0, sizeof(double) * dsz * nc, cudaMemcpyDeviceToHost, SO));
@@ -717,24 +751,38 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (iters) CK(cudaMemcpyAsync(iters + c0, dout + o_it + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
     }
   }
-  // ---- join; the only host synchronisation of the call
-  std::vector<int> h_bad(nchunks, 0);
-  cudaStream_t SL = (nchunks > 1) ? ctx->s_out : S;
+  // ---- the bad-shape flags come back with the results; the join is finish_query (the only host synchronisation)
+  for (int c = 0; c < nchunks; c++) L.h_bad[c] = 0;
+  cudaStream_t SL = piped ? ctx->s_out : S;
+  if (piped && mem != DCOL_MEM_HOST) { CK(cudaEventRecord(L.ev_done[0], SC)); CK(cudaStreamWaitEvent(SL, L.ev_done[0], 0)); }
   for (int c = 0; c < nchunks; c++)
-    CK(cudaMemcpyAsync(&h_bad[c], (int*)ctx->d_hist.p + hist_stride * c + 3 * (size_t)nk + 1, sizeof(int), cudaMemcpyDeviceToHost, SL));
-  if (nchunks > 1) {
-    CK(cudaStreamSynchronize(ctx->s_out));
-    CK(cudaStreamSynchronize(SC));
-  }
-  CK(cudaStreamSynchronize(S));
+    CK(cudaMemcpyAsync(&L.h_bad[c], (int*)L.d_hist.p + hist_stride * c + 3 * (size_t)nk + 1, sizeof(int), cudaMemcpyDeviceToHost, SL));
+  // join point of THIS submission: everything it enqueued precedes ev_end on SL (the compute stream's last work
+  // is ordered before it through ev_done), so waiting for it does not wait for later submissions
+  if (piped) { CK(cudaEventRecord(L.ev_done[nchunks - 1], SC)); CK(cudaStreamWaitEvent(SL, L.ev_done[nchunks - 1], 0)); }
+  CK(cudaEventRecord(L.ev_end, SL));
+  L.pending = true; L.nchunks = nchunks; L.piped = piped; L.result = 0;
+  if (async) return 0;
+  return finish_query(ctx, slot);
+}
+
+// Join one submission: wait for its streams, collect the kernel time and the bad-index flags.
+static int finish_query(dcol_ctx* ctx, int slot) {
+  dcol_ctx::Slot& L = ctx->slots[slot];
+  if (!L.pending) return L.result;
+  L.pending = false;
+  auto fail = [&](const char* what, cudaError_t e) { ctx->err = std::string(what) + ": " + cudaGetErrorString(e); L.result = -2; return -2; };
+  cudaError_t e;
+  if ((e = cudaEventSynchronize(L.ev_end)) != cudaSuccess) return fail("cudaEventSynchronize", e);
   double total_ms = 0.0;
-  for (int c = 0; c < nchunks; c++) {
+  for (int c = 0; c < L.nchunks; c++) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev_t0[c], ctx->ev_t1[c]) == cudaSuccess) total_ms += ms;
+    if (cudaEventElapsedTime(&ms, L.ev_t0[c], L.ev_t1[c]) == cudaSuccess) total_ms += ms;
   }
-  ctx->last_ms = total_ms;
-  for (int c = 0; c < nchunks; c++)
-    if (h_bad[c]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; return -1; }
+  L.ms = total_ms; ctx->last_ms = total_ms;
+  for (int c = 0; c < L.nchunks; c++)
+    if (L.h_bad[c]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; L.result = -1; return -1; }
+  L.result = 0;
   return 0;
 }
 
@@ -815,6 +863,32 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
   ctx->launches++;
   return run_query(ctx, query, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, mem, alpha, x, deriv, status, iters,
                    p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE);
+}
+
+
+// ---- asynchronous submissions (host buffers): up to three in flight; inputs of submission k+1 cross PCIe while
+// submission k computes and submission k-1's results go back
+int dcol_submit(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                const double* r1, const double* att1, const double* r2, const double* att2,
+                int att_kind, double pdip_tol,
+                double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  if (check_query_kind(ctx, query)) return -1;
+  const int ticket = ctx->next_ticket;
+  const int slot = ticket % dcol_ctx::N_SLOTS;
+  int rc = run_query(ctx, query, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, DCOL_MEM_HOST,
+                     alpha, x, deriv, status, iters, nullptr, nullptr, 0, 0, -1, slot, true);
+  if (rc) return rc;
+  ctx->slots[slot].ticket = ticket;
+  ctx->next_ticket = (ticket + 1) & 0x3fffffff;
+  return ticket;
+}
+
+int dcol_wait(dcol_ctx* ctx, int ticket) {
+  if (!ctx) return -1;
+  for (int k = 0; k < dcol_ctx::N_SLOTS; k++)
+    if (ctx->slots[k].ticket == ticket) return finish_query(ctx, k);
+  ctx->err = "dcol_wait: unknown ticket (only the last three submissions are kept)";
+  return -1;
 }
 
 }  // extern "C"

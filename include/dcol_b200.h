@@ -126,6 +126,19 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
                         int att_kind, double pdip_tol, int mem,
                         double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
 
+/* ---- asynchronous submissions (host buffers) -------------------------------------------------------------
+ * dcol_submit enqueues one query (query: 0 proximity, 1 gradient, 2 jacobian; buffers as in the synchronous
+ * calls, all HOST memory, pinned for the copies to overlap) and returns a ticket >= 0 without waiting; dcol_wait
+ * blocks until that submission's results are in the caller's buffers and returns its status (0 / <0).  Three
+ * submissions may be in flight: the inputs of submission k+1 cross PCIe while submission k computes and the
+ * results of submission k-1 go back.  Submitting a fourth waits for the oldest.  The caller's input and output
+ * buffers must stay valid and untouched until the matching dcol_wait returns. */
+int dcol_submit(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                const double* r1, const double* att1, const double* r2, const double* att2,
+                int att_kind, double pdip_tol,
+                double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
+int dcol_wait(dcol_ctx* ctx, int ticket);
+
 /* Instrumentation for bench.py / tests. */
 /* kernels launched by this context since creation (solver + derivative + binning kernels) */
 int64_t dcol_launch_count(const dcol_ctx* ctx);

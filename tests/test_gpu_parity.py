@@ -262,3 +262,38 @@ def test_full_size_properties(ctx):
     j = ctx._batch(2, s1[:m], s2[:m], r1[:m], a1[:m], r2[:m], a2[:m], 0, 1e-6)
     np.testing.assert_allclose(j["alpha"], a["alpha"][:m], rtol=1e-10)   # different kernel variant, same algorithm
     props.structural_jacobian_properties(j, a1[:m], a2[:m], 0)
+
+
+def test_async_submit_matches_sync(ctx):
+    """dcol_submit / dcol_wait with three submissions in flight return the same bits as the synchronous calls."""
+    import torch
+    n = 300000
+    sets = []
+    for k, (kind, att) in enumerate(((0, 0), (2, 1), (1, 0), (0, 0), (2, 0))):
+        t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, att, seed=50 + k)
+        sets.append((kind, att, t, s1, s2, r1, a1, r2, a2))
+    ctx.set_shape_arrays(*sets[0][2].arrays())          # all sets use the same 7 shapes per attitude kind
+    outs, tickets = [], []
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    for kind, att, t, s1, s2, r1, a1, r2, a2 in sets:
+        na = 4 if att == 0 else 3; nt = 6 + 2 * na
+        ins = [pin(a) for a in (s1, s2, r1, a1, r2, a2)]
+        o = {"alpha": torch.empty(n, dtype=torch.float64).pin_memory(), "x": torch.empty((n, 3), dtype=torch.float64).pin_memory(),
+             "deriv": (torch.empty((n, nt) if kind == 1 else (n, nt, 4), dtype=torch.float64).pin_memory() if kind else None),
+             "status": torch.empty(n, dtype=torch.int32).pin_memory(), "iters": torch.empty(n, dtype=torch.int32).pin_memory(), "ins": ins}
+        if len(tickets) >= 3:
+            ctx.wait(tickets[-3])
+        tickets.append(ctx.submit_raw(kind, n, *ins, att, 1e-6, o["alpha"], o["x"] if kind != 1 else None, o["deriv"], o["status"], o["iters"]))
+        outs.append(o)
+    for tk in tickets[-3:]:
+        ctx.wait(tk)
+    for (kind, att, t, s1, s2, r1, a1, r2, a2), o in zip(sets, outs):
+        ref = ctx._batch(kind, s1, s2, r1, a1, r2, a2, att, 1e-6)
+        assert np.array_equal(o["alpha"].numpy(), ref["alpha"]) and np.array_equal(o["status"].numpy(), ref["status"])
+        assert np.array_equal(o["iters"].numpy(), ref["iters"])
+        if kind == 0:
+            assert np.array_equal(o["x"].numpy(), ref["x"])
+        if kind == 1:
+            assert np.array_equal(o["deriv"].numpy(), ref["grad"], equal_nan=True)
+        if kind == 2:
+            assert np.array_equal(o["deriv"].numpy().transpose(0, 2, 1), ref["J"], equal_nan=True)

@@ -278,6 +278,18 @@ def main():
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        # optional result gather over NVLink: all-gather of the alpha rows, outside the timed step
+        gather = None
+        if world > 1:
+            parts = [torch.empty_like(d_alpha) for _ in range(world)]
+            dist.all_gather(parts, d_alpha)
+            barrier()
+            g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(5):
+                dist.all_gather(parts, d_alpha)
+            g1.record(); torch.cuda.synchronize()
+            gather = {"op": "nccl all_gather of alpha", "bytes_per_rank": int(d_alpha.numel() * 8), "ms": max_over_ranks(g0.elapsed_time(g1) / 5)}
         iters = d_it.cpu().numpy()
         status = d_st.cpu().numpy()
         types, offs, params = table.arrays()
@@ -287,7 +299,7 @@ def main():
         out_b = n * (8 + 8 * (1 + 3 + (4 * nt if kind == 2 else 0)))
         return {"n": n, "dev_ms": dev_ms, "steps": steps, "kernel_ms": float(np.mean(kms)), "launches": launches, "clocks": clocks,
                 "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s, "e2e_steps": e2e_steps, "flops": flops, "in_bytes": in_b, "out_bytes": out_b,
-                "mean_iters": float(iters.mean()), "max_iters": int(iters.max()), "failed": int((status != 0).sum())}
+                "mean_iters": float(iters.mean()), "max_iters": int(iters.max()), "failed": int((status != 0).sum()), "gather": gather}
 
     fp64_peak = ctx.measure_fp64_tflops()
     prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234)
@@ -350,6 +362,8 @@ def main():
                         "one_call_at_a_time": world * prox["n"] * prox["e2e_steps"] / prox["e2e_sync_s"]},
                 "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox, "proximity"),
                 "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
+        if prox.get("gather"):
+            line["gather"] = prox["gather"]
         if cpu:
             line["cpu_baseline"] = cpu
         if jac:

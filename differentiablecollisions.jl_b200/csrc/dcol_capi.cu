@@ -190,7 +190,7 @@ __global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable
     }
     for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
     T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0; T.in_base = ov_base;
-    T.pad_tile = tile;
+    T.tile = tile;
   }
 }
 // resume-pass tables from the overflow counts the previous pass left behind; the resume pass may itself hand its
@@ -202,8 +202,8 @@ __global__ void k_build_tables2(const LaunchTable* __restrict__ tables, LaunchTa
   for (int t = 0; t < n_tiers; t++) {
     const LaunchTable& T = tables[t];
     LaunchTable& U = tables2[t];
-    const int tile = T.pad_tile;
-    U.P = T.P; U.pad_tile = tile;
+    const int tile = T.tile;
+    U.P = T.P; U.tile = tile;
     int tiles = 0;
     for (int k = 0; k < T.n_bins; k++) {
       const int cnt = min(T.ov_count[k], T.ov_cap[k]);
@@ -581,7 +581,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   const int nk = ctx->n_keys;
   const int nt_tiers = (int)ctx->tiers.size();
   constexpr int MAX_LEVELS = 3;                                     // resume passes after the first pass
-  const size_t hist_ints = 3 * (size_t)nk + 16 + (2 + MAX_LEVELS) * NSIDE;   // hist | off | cursor | bad | counters per pass | tile sizes
+  const size_t hist_ints = 3 * (size_t)nk + 16 + (2 + MAX_LEVELS) * NSIDE;   // hist | off | cursor | bad | tile counters per pass and tier
   const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
   CK(L.d_perm.need(sizeof(int32_t) * n));
   CK(L.d_hist.need(sizeof(int) * hist_stride * nchunks));

@@ -75,7 +75,7 @@ constexpr int TILE = 32;
 struct LaunchTable {
   QueryParams P;
   int n_bins, n_tiles, rows_cap, mode;     // mode 0: first pass (may hand stragglers over), 1: resume pass
-  int pad_tile;                    // CTA size (= tile size) of the tier
+  int tile;                        // CTA size (= pairs per tile) of the tier
   int tile_prefix[MAX_BINS + 1];   // first tile of bin b
   int begin[MAX_BINS];             // sorted-position range of bin b (resume pass: 0 .. ov_count)
   int end[MAX_BINS];

@@ -297,3 +297,36 @@ def test_async_submit_matches_sync(ctx):
             assert np.array_equal(o["deriv"].numpy(), ref["grad"], equal_nan=True)
         if kind == 2:
             assert np.array_equal(o["deriv"].numpy().transpose(0, 2, 1), ref["J"], equal_nan=True)
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+def test_random_shape_parameters(ctx, oracle, att_kind):
+    """Random geometry instead of the reference's fixed test shapes: 6 shapes per kind with random sizes, random bounded
+    polytopes (5-20 faces) and polygons (3-9 sides), half of them with random r_offset / Q_offset."""
+    g = util.rng(2025 + att_kind)
+    C = lambda b: util.cls_name(att_kind, b)
+    shapes = []
+    for k in range(6):
+        nf = int(g.integers(5, 21))
+        dirs = np.vstack([np.eye(3), -np.eye(3), g.standard_normal((max(nf - 6, 0), 3))])[:max(nf, 6)]
+        dirs = dirs * (0.5 + g.random((dirs.shape[0], 1)))                  # rows are NOT unit-normalised (like the fixtures)
+        shapes.append(C("Polytope")(dirs, (0.3 + g.random(dirs.shape[0])) * np.linalg.norm(dirs, axis=1)))
+        shapes.append(C("Capsule")(0.1 + g.random(), 0.2 + 3 * g.random()))
+        shapes.append(C("Cylinder")(0.1 + g.random(), 0.2 + 3 * g.random()))
+        shapes.append(C("Cone")(0.5 + 2.5 * g.random(), np.deg2rad(10 + 40 * g.random())))
+        shapes.append(C("Sphere")(0.1 + g.random()))
+        M = g.standard_normal((3, 3)); shapes.append(C("Ellipsoid")(M @ M.T + 0.3 * np.eye(3)))
+        nh = int(g.integers(3, 10)); A, b = dc.create_n_sided(nh, 0.2 + g.random())
+        shapes.append(C("Polygon")(A, b * (0.7 + 0.6 * g.random(nh)), 0.05 + 0.3 * g.random()))
+    for s in shapes[::2]:
+        s.r_offset = 0.2 * g.standard_normal(3)
+        s.Q_offset = dc.dcm_from_q(g.standard_normal(4))
+    t = dc.ShapeTable(); ids = np.array([t.add(s) for s in shapes], np.int32)
+    n = 30000
+    s1 = ids[g.integers(0, len(ids), n)]; s2 = ids[g.integers(0, len(ids), n)]
+    r1, a1, r2, a2 = util.random_poses(n, att_kind, 314)
+    for kind in (0, 1, 2):
+        gg = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
+        o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
+        assert (o["status"] == 0).mean() > 0.999
+        compare(gg, o, kind, strict_frac=0.99)

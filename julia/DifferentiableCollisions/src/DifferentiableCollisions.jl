@@ -270,6 +270,25 @@ function query_indexed(kind::Integer, s1::Vector{Int32}, s2::Vector{Int32}, p1::
     return BatchResult(α, x, deriv, status, iters)
 end
 
+"""
+    submit!(res::BatchResult, kind, s1, s2, r1, a1, r2, a2; pdip_tol) -> ticket ;  wait!(ticket)
+
+Asynchronous form (`dcol_submit` / `dcol_wait`): up to three submissions in flight, so that the PCIe copies of one
+batch overlap the kernels of the previous one.  `res` and the input arrays must stay alive and untouched until
+`wait!(ticket)` returns (use pinned memory, e.g. `CUDA.pin`, for the copies to be truly asynchronous).
+"""
+function submit!(res::BatchResult, kind::Integer, s1::Vector{Int32}, s2::Vector{Int32}, r1::Matrix{Float64}, a1::Matrix{Float64},
+                 r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6)
+    t = ccall((:dcol_submit, _lib[]), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
+               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+              _ctx[], kind, length(s1), s1, s2, r1, a1, r2, a2, size(a1, 1) == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol),
+              res.α, kind == 1 ? C_NULL : res.x, kind == 0 ? C_NULL : res.deriv, res.status, res.iters)
+    t >= 0 || _check(t)
+    return t
+end
+wait!(ticket::Integer) = (_check(ccall((:dcol_wait, _lib[]), Cint, (Ptr{Cvoid}, Cint), _ctx[], ticket)); nothing)
+
 # ---------------------------------------------------------------------------------------------
 # single-pair drop-in calls: a batch of one through the same entry points
 # ---------------------------------------------------------------------------------------------

@@ -170,6 +170,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; dcol_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = dc.bind_to_gpu_numa_node(local)          # pinned buffers local to the GPU's PCIe root (end-to-end path at N > 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -364,6 +365,7 @@ def main():
                 "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
         if prox.get("gather"):
             line["gather"] = prox["gather"]
+        line["host_affinity"] = numa
         if cpu:
             line["cpu_baseline"] = cpu
         if jac:

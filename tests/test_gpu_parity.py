@@ -244,10 +244,10 @@ def test_device_memory_mode(ctx, oracle):
     assert ctx.launch_count() > 0 and ctx.last_kernel_ms() > 0
 
 
-def test_full_size_properties(ctx):
-    """BASELINE config 2 at full size (1M mixed pairs): size-independent properties instead of the oracle —
-    argument-order symmetry of alpha (test/proximity_test.jl:12-15), structural Jacobian identities,
-    permutation invariance (binning must not change per-pair results)."""
+def test_full_size_properties(ctx, oracle):
+    """BASELINE config 2 at full size (1M mixed pairs): size-independent properties — argument-order symmetry of alpha
+    (test/proximity_test.jl:12-15), structural Jacobian identities, permutation invariance (binning must not change
+    per-pair results) — and, because the GPU box's host cores make it affordable, the oracle on all 1M pairs."""
     n = 1_000_000
     t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, 0, seed=2024)
     ctx.set_shape_arrays(*t.arrays())
@@ -262,6 +262,15 @@ def test_full_size_properties(ctx):
     j = ctx._batch(2, s1[:m], s2[:m], r1[:m], a1[:m], r2[:m], a2[:m], 0, 1e-6)
     np.testing.assert_allclose(j["alpha"], a["alpha"][:m], rtol=1e-10)   # different kernel variant, same algorithm
     props.structural_jacobian_properties(j, a1[:m], a2[:m], 0)
+    o = oracle.query(0, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    assert (o["status"] == 0).all() and (a["iters"] == o["iters"]).mean() > 0.9999
+    assert util.rel_err(a["alpha"], o["alpha"]).max() < TOL_AX
+    assert ((a["alpha"] <= 1) == (o["alpha"] <= 1)).all()
+    ex = util.rel_err(a["x"], o["x"])
+    assert (ex < TOL_AX).mean() > 0.9999 and ex.max() < 1e-3
+    oj = oracle.query(2, t.arrays(), s1[:m], s2[:m], r1[:m], a1[:m], r2[:m], a2[:m], 0, 1e-6)
+    ej = util.rel_err(j["J"], oj["J"])
+    assert (ej < TOL_J).mean() > 0.9999 and np.quantile(ej, 0.99999) < 1e-2
 
 
 def test_async_submit_matches_sync(ctx):

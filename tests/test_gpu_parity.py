@@ -339,3 +339,28 @@ def test_random_shape_parameters(ctx, oracle, att_kind):
         o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
         assert (o["status"] == 0).mean() > 0.999
         compare(gg, o, kind, strict_frac=0.99)
+
+
+def test_straggler_handover_is_bit_identical(ctx):
+    """Parking the last stragglers of a tile and finishing them in resume passes must not change a single bit:
+    no hand-over (DCOL_SPILL=0), the default (one resume level) and three resume levels give identical outputs."""
+    import os
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(300000, 0, seed=99, variant="scene")
+    ctx.set_shape_arrays(*t.arrays())
+    outs = []
+    saved = {k: os.environ.get(k) for k in ("DCOL_SPILL", "DCOL_LEVELS")}
+    try:
+        for env in ({"DCOL_SPILL": "0"}, {}, {"DCOL_LEVELS": "3"}, {"DCOL_SPILL": "2", "DCOL_LEVELS": "2"}):
+            for k in saved:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            outs.append([ctx._batch(kind, s1, s2, r1, a1, r2, a2, 0, 1e-6) for kind in (0, 2)])
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            for key in a:
+                assert np.array_equal(a[key], b[key], equal_nan=True), key

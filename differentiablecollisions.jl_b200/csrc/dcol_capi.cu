@@ -193,32 +193,27 @@ __global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable
     T.tile = tile;
   }
 }
-// resume-pass tables from the overflow counts the previous pass left behind; the resume pass may itself hand its
-// stragglers over (spill > 0) into the other overflow buffer
-__global__ void k_build_tables2(const LaunchTable* __restrict__ tables, LaunchTable* __restrict__ tables2, int n_tiers,
-                                double* ov_next, int spill) {
+// resume-pass table of ONE tier from the overflow counts its previous pass left behind (launched right behind that
+// pass on the tier's stream, so the resume pass of one tier overlaps the first pass of the next); the resume pass may
+// itself hand its stragglers over (spill > 0) into the other overflow buffer, which reuses the previous layout
+__global__ void k_build_tables2(const LaunchTable* __restrict__ Tp, LaunchTable* __restrict__ Up, double* ov_next, int spill) {
   if (threadIdx.x || blockIdx.x) return;
-  long long ov = 0;
-  for (int t = 0; t < n_tiers; t++) {
-    const LaunchTable& T = tables[t];
-    LaunchTable& U = tables2[t];
-    const int tile = T.tile;
-    U.P = T.P; U.tile = tile;
-    int tiles = 0;
-    for (int k = 0; k < T.n_bins; k++) {
-      const int cnt = min(T.ov_count[k], T.ov_cap[k]);
-      const int nt = (cnt + tile - 1) / tile;
-      U.begin[k] = 0; U.end[k] = cnt; U.cp[k] = T.cp[k];
-      U.tile_prefix[k] = tiles;
-      tiles += nt;
-      U.in_cap[k] = T.ov_cap[k]; U.in_off[k] = T.ov_off[k]; U.ov_stride[k] = T.ov_stride[k];
-      U.ov_cap[k] = spill ? nt * T.spill_t : 0; U.ov_off[k] = ov; U.ov_count[k] = 0;
-      ov += (long long)U.ov_cap[k] * U.ov_stride[k];
-    }
-    for (int k = T.n_bins; k <= MAX_BINS; k++) U.tile_prefix[k] = tiles;
-    U.n_bins = T.n_bins; U.n_tiles = tiles; U.in_base = T.ov_base; U.ov_base = ov_next; U.mode = 1;
-    U.spill_t = spill ? T.spill_t : 0; U.rows_cap = T.rows_cap;
+  const LaunchTable& T = *Tp;
+  LaunchTable& U = *Up;
+  const int tile = T.tile;
+  U.P = T.P; U.tile = tile;
+  int tiles = 0;
+  for (int k = 0; k < T.n_bins; k++) {
+    const int cnt = min(T.ov_count[k], T.ov_cap[k]);
+    U.begin[k] = 0; U.end[k] = cnt; U.cp[k] = T.cp[k];
+    U.tile_prefix[k] = tiles;
+    tiles += (cnt + tile - 1) / tile;
+    U.in_cap[k] = T.ov_cap[k]; U.in_off[k] = T.ov_off[k]; U.ov_stride[k] = T.ov_stride[k];
+    U.ov_cap[k] = spill ? T.ov_cap[k] : 0; U.ov_off[k] = T.ov_off[k]; U.ov_count[k] = 0;
   }
+  for (int k = T.n_bins; k <= MAX_BINS; k++) U.tile_prefix[k] = tiles;
+  U.n_bins = T.n_bins; U.n_tiles = tiles; U.in_base = T.ov_base; U.ov_base = ov_next; U.mode = 1;
+  U.spill_t = spill ? T.spill_t : 0; U.rows_cap = T.rows_cap;
 }
 
 // (i, j), i < j in combinations(1:N, 2) order (the pair list of examples/contact_physics/ncp_contact_simulation.jl:48),
@@ -715,6 +710,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table
     CK(cudaEventRecord(L.ev_t0[c], SC));
+    // per tier, on the tier's stream: first pass, then (right behind it) the resume passes that finish the handed-over
+    // stragglers in dense tiles — the resume pass of one tier overlaps the first pass of the next
     if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
     for (int t = 0; t < nt_tiers; t++) {
       const dcol_ctx::Tier& TR = ctx->tiers[t];
@@ -722,22 +719,14 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
       CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, d_tab + t, d_counter + t));
       ctx->launches++;
-      if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
-    }
-    for (int lv = 1; lv <= levels && spill_div > 0; lv++) {        // resume passes: finish the handed-over stragglers in dense tiles
-      LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers);
-      LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers);
-      k_build_tables2<<<1, 32, 0, SC>>>(prev, cur, nt_tiers, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
-      ctx->launches++;
-      if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
-      for (int t = 0; t < nt_tiers; t++) {
-        const dcol_ctx::Tier& TR = ctx->tiers[t];
-        cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
-        if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
-        CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, cur + t, d_counter + lv * NSIDE + t));
-        ctx->launches++;
-        if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
+      for (int lv = 1; lv <= levels && spill_div > 0; lv++) {
+        LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers) + t;
+        LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers) + t;
+        k_build_tables2<<<1, 32, 0, st>>>(prev, cur, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
+        CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, cur, d_counter + lv * NSIDE + t));
+        ctx->launches += 2;
       }
+      if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
     }
     CK(cudaEventRecord(L.ev_t1[c], SC));
     // ---- results of this chunk back (host mode), overlapping the next chunk's kernels

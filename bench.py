@@ -312,7 +312,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         threads = orc.max_threads()
-        sample = 250_000 * threads                     # ~10-20 s of CPU work in total across the threads
+        sample = min(250_000 * threads, 8_000_000)     # ~10-30 s of CPU work in total across the threads, bounded
         t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sample, dc.ATT_QUAT, seed=1234, variant=args.variant)
         orc.query(0, t.arrays(), s1[:20000], s2[:20000], r1[:20000], a1[:20000], r2[:20000], a2[:20000], 0, PDIP_TOL)
         t0 = time.perf_counter()
@@ -320,7 +320,7 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{sample} pairs of the config-2 workload, C++ restatement of the Julia reference, std::thread x{threads}"}
-        sj = 100_000 * threads
+        sj = min(100_000 * threads, 3_000_000)
         t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sj, dc.ATT_MRP, seed=4321, variant=args.variant)
         t0 = time.perf_counter()
         orc.query(2, t.arrays(), s1, s2, r1, a1, r2, a2, 1, PDIP_TOL)

@@ -16,8 +16,8 @@
 #include <vector>
 
 namespace dcol {
-const void* persistent_kernel_ptr(bool jac);                                                          // dcol_dispatch.cu
-cudaError_t launch_persistent(bool jac, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
+const void* persistent_kernel_ptr(int var);                                                          // dcol_dispatch.cu
+cudaError_t launch_persistent(int var, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
 }
 using namespace dcol;
 
@@ -61,7 +61,7 @@ struct dcol_ctx {
   int max_rows_cls[NCLS] = {};
   DevBuf d_shapes, d_rows, d_cls, d_keymap;
   // static launch plan derived from the shape table (dcol_set_shapes): one entry per shared-memory tier
-  struct Tier { int n_bins = 0, rows_cap = 0, block = 0, pitch = 1; size_t smem = 0; int grid[2] = {0, 0};
+  struct Tier { int n_bins = 0, rows_cap = 0, block = 0, pitch = 1; size_t smem = 0; int grid[3] = {0, 0, 0};
                 int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; int ov_stride[MAX_BINS]; int max_stride = 0; };
   std::vector<Tier> tiers;
   // per-call scratch.  Three slots, so that asynchronous submissions (dcol_submit) overlap: one staging its inputs,
@@ -476,8 +476,8 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
       if (const char* e = getenv("DCOL_WARPS")) warps = std::max(1, std::min(warps, atoi(e)));   // tuning knob
       T.block = 32 * warps;
       T.smem = (size_t)T.pitch * sizeof(double) * T.block;
-      for (int jac = 0; jac < 2; jac++) {
-        const void* kfn = persistent_kernel_ptr(jac != 0);
+      for (int jac = 0; jac < 3; jac++) {
+        const void* kfn = persistent_kernel_ptr(jac);
         if (T.smem > 48 * 1024) CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_SMEM - 1024)));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, T.block, T.smem));
@@ -624,7 +624,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     CK(L.d_out.need(b));
     dout = (char*)L.d_out.p;
   }
-  const bool jac = (query != Q_PROX);          // derivative variant of the kernels (gradient and Jacobian)
+  const int jac = query;                       // kernel variant = query kind
   cudaStream_t S = ctx->stream();
   const bool piped = (nchunks > 1) || async;                  // three-stream pipeline (always for asynchronous submissions)
   cudaStream_t SC = piped ? ctx->s_comp : S;                  // compute stream of the pipeline
@@ -717,13 +717,13 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       const dcol_ctx::Tier& TR = ctx->tiers[t];
       cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
       if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
-      CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, d_tab + t, d_counter + t));
+      CK(launch_persistent(jac, TR.grid[jac], TR.block, TR.smem, st, d_tab + t, d_counter + t));
       ctx->launches++;
       for (int lv = 1; lv <= levels && spill_div > 0; lv++) {
         LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers) + t;
         LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers) + t;
         k_build_tables2<<<1, 32, 0, st>>>(prev, cur, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
-        CK(launch_persistent(jac, TR.grid[jac ? 1 : 0], TR.block, TR.smem, st, cur, d_counter + lv * NSIDE + t));
+        CK(launch_persistent(jac, TR.grid[jac], TR.block, TR.smem, st, cur, d_counter + lv * NSIDE + t));
         ctx->launches += 2;
       }
       if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }

@@ -8,22 +8,22 @@
 #endif
 namespace dcol {
 
-template <int C1, int C2, bool JAC>
+template <int C1, int C2, int VAR>
 __device__ void solve_entry(const QueryParams* p, const TileCtx* tc, int idx);   // dcol_kernels_c*.cu
 
-template <int C1, bool JAC>
+template <int C1, int VAR>
 __device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, const TileCtx* tc, int idx) {
   switch (c2) {
-    case 0: solve_entry<C1, 0, JAC>(p, tc, idx); break;
-    case 1: solve_entry<C1, 1, JAC>(p, tc, idx); break;
-    case 2: solve_entry<C1, 2, JAC>(p, tc, idx); break;
-    case 3: solve_entry<C1, 3, JAC>(p, tc, idx); break;
-    case 4: solve_entry<C1, 4, JAC>(p, tc, idx); break;
-    case 5: solve_entry<C1, 5, JAC>(p, tc, idx); break;
+    case 0: solve_entry<C1, 0, VAR>(p, tc, idx); break;
+    case 1: solve_entry<C1, 1, VAR>(p, tc, idx); break;
+    case 2: solve_entry<C1, 2, VAR>(p, tc, idx); break;
+    case 3: solve_entry<C1, 3, VAR>(p, tc, idx); break;
+    case 4: solve_entry<C1, 4, VAR>(p, tc, idx); break;
+    case 5: solve_entry<C1, 5, VAR>(p, tc, idx); break;
   }
 }
 
-template <bool JAC>
+template <int VAR>
 __global__ void __launch_bounds__(DCOL_MAXTHREADS, 1) proximity_persistent(LaunchTable* __restrict__ tt, int* __restrict__ counter) {
   __shared__ int s_tile;
   const int n_tiles = tt->n_tiles;
@@ -49,22 +49,23 @@ __global__ void __launch_bounds__(DCOL_MAXTHREADS, 1) proximity_persistent(Launc
     tc.in = tt->in_base + tt->in_off[b]; tc.in_cap = tt->in_cap[b];
     const int c1 = cp / NCLS, c2 = cp - c1 * NCLS;
     switch (c1) {
-      case 0: dispatch_c2<0, JAC>(c2, &tt->P, &tc, idx); break;
-      case 1: dispatch_c2<1, JAC>(c2, &tt->P, &tc, idx); break;
-      case 2: dispatch_c2<2, JAC>(c2, &tt->P, &tc, idx); break;
-      case 3: dispatch_c2<3, JAC>(c2, &tt->P, &tc, idx); break;
-      case 4: dispatch_c2<4, JAC>(c2, &tt->P, &tc, idx); break;
-      case 5: dispatch_c2<5, JAC>(c2, &tt->P, &tc, idx); break;
+      case 0: dispatch_c2<0, VAR>(c2, &tt->P, &tc, idx); break;
+      case 1: dispatch_c2<1, VAR>(c2, &tt->P, &tc, idx); break;
+      case 2: dispatch_c2<2, VAR>(c2, &tt->P, &tc, idx); break;
+      case 3: dispatch_c2<3, VAR>(c2, &tt->P, &tc, idx); break;
+      case 4: dispatch_c2<4, VAR>(c2, &tt->P, &tc, idx); break;
+      case 5: dispatch_c2<5, VAR>(c2, &tt->P, &tc, idx); break;
     }
   }
 }
 
-const void* persistent_kernel_ptr(bool jac) {
-  return jac ? (const void*)proximity_persistent<true> : (const void*)proximity_persistent<false>;
+const void* persistent_kernel_ptr(int var) {
+  return var == 2 ? (const void*)proximity_persistent<2> : (var == 1 ? (const void*)proximity_persistent<1> : (const void*)proximity_persistent<0>);
 }
-cudaError_t launch_persistent(bool jac, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter) {
-  if (jac) proximity_persistent<true><<<grid, block, smem, st>>>(tt, counter);
-  else proximity_persistent<false><<<grid, block, smem, st>>>(tt, counter);
+cudaError_t launch_persistent(int var, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter) {
+  if (var == 2) proximity_persistent<2><<<grid, block, smem, st>>>(tt, counter);
+  else if (var == 1) proximity_persistent<1><<<grid, block, smem, st>>>(tt, counter);
+  else proximity_persistent<0><<<grid, block, smem, st>>>(tt, counter);
   return cudaGetLastError();
 }
 }  // namespace dcol

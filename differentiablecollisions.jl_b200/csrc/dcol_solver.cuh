@@ -685,9 +685,10 @@ struct PairMap {
 };
 
 // One pair: relative pose -> initial point -> PDIP loop -> outputs (+ derivative epilogue).
-// JAC selects the kernel variant that carries the derivative epilogues (gradient and implicit-function-theorem
-// Jacobian, chosen by p.query); the proximity variant has none, which keeps its code small.
-template <int C1, int C2, bool JAC>
+// VAR (= the query kind: Q_PROX, Q_GRAD, Q_JAC) selects the kernel variant: the proximity variant carries no epilogue,
+// the gradient variant the small envelope-theorem epilogue, the Jacobian variant the implicit-function-theorem one
+// (whose register pressure would otherwise slow the other two queries' solver loops).
+template <int C1, int C2, int VAR>
 __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& tc, int idx) {
   using P1 = Prim<C1>; using P2 = Prim<C2>;
   using PM = PairMap<P1::NE, P2::NE>;
@@ -915,10 +916,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   if (p.iters) p.iters[pair] = it;
   const int nt = 6 + 2 * na;
 
-  // The derivative variant (JAC = true) serves both derivative queries; the proximity variant carries no epilogue.
-  if constexpr (JAC) {
+  if constexpr (VAR == Q_GRAD) {
     // ---- proximity_gradient (src/proximity_gradient.jl:41-78): -z' du/dtheta
-    if (p.query == Q_GRAD) {
+    {
       double* g = p.deriv + (int64_t)nt * pair;
       if (status == ST_OK) {
         build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
@@ -931,9 +931,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
       } else {
         for (int j = 0; j < nt; j++) g[j] = __longlong_as_double(0x7ff8000000000000LL);
       }
-      if (p.status) p.status[pair] = status;
-      return;
     }
+  }
+  if constexpr (VAR == Q_JAC) {
     // ---- proximity_jacobian (src/proximity.jl:71-134): reduced KKT solve in primitive-1's frame
     double* Jo = p.deriv + (int64_t)4 * nt * pair;
     bool ok = (status == ST_OK);
@@ -1040,9 +1040,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
 
 // Out-of-line entry of one specialisation (separate compilation: each class row lives in its own
 // translation unit and is device-linked into the persistent kernels of dcol_dispatch.cu).
-template <int C1, int C2, bool JAC>
+template <int C1, int C2, int VAR>
 __device__ __noinline__ void solve_entry(const QueryParams* p, const TileCtx* tc, int idx) {
-  solve_pair<C1, C2, JAC>(*p, *tc, idx);
+  solve_pair<C1, C2, VAR>(*p, *tc, idx);
 }
 
 }  // namespace dcol

@@ -66,12 +66,11 @@ struct QueryParams {
 
 
 // Work description of one persistent launch (lives in global memory, written by the host per call).
-// Tiles are warp-sized (32 consecutive sorted positions of one class-pair bin); tiles of a bin are
-// contiguous in the queue and bins are queued heaviest first, so at any moment the warps in flight
+// Tiles are CTA-sized (consecutive sorted positions of one class-pair bin); tiles of a bin are
+// contiguous in the queue and bins are queued heaviest first, so at any moment the CTAs in flight
 // execute (nearly) the same specialisation — instruction-cache friendly — and only the end of the
 // queue has a tail.
 constexpr int MAX_BINS = NCLS * NCLS;
-constexpr int TILE = 32;
 struct LaunchTable {
   QueryParams P;
   int n_bins, n_tiles, rows_cap, mode;     // mode 0: first pass (may hand stragglers over), 1: resume pass

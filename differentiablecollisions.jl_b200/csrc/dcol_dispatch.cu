@@ -1,5 +1,6 @@
-// Persistent proximity kernels: every warp pulls 32-pair tiles from a global queue and dispatches to
-// the class-pair specialisation of the tile's bin (device-linked entries from dcol_kernels_c*.cu).
+// Persistent proximity kernels (one per query kind): every CTA (1 per SM, 8 warps in lockstep) pulls CTA-sized
+// tiles from a global queue ordered by class pair and dispatches to the class-pair specialisation of the tile's
+// bin (device-linked entries from dcol_kernels_c*.cu).
 #include "dcol_common.cuh"
 #include <cuda_runtime.h>
 

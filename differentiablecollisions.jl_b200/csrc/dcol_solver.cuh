@@ -11,10 +11,13 @@
 //     algebraically identical to the NT-scaled ones for the nonnegative orthant;
 //   * SOC blocks use the closed form W^-1 = (1/eta) J Wbar J instead of a dense
 //     Cholesky of W (NT_scaling_chol_2.jl:126) — same operator, fewer flops;
-//   * per-row state (s, z, 1/s, rz, scratch) lives in shared memory, strided by
-//     thread so a warp touches consecutive 8-byte words (no bank conflicts);
-//     everything else (y, Gram matrix, SOC blocks, relative pose) is in registers.
-// Warps are independent (persistent warps pulling 32-pair tiles from a queue, dcol_dispatch.cu).
+//   * per-row state (s, z, 1/(s z), rz|ds, p|dz) and the pair's relative pose live in a contiguous,
+//     odd-pitch slice of shared memory per thread (conflict-free, field offsets as immediates);
+//     everything else (y, KKT matrix, SOC blocks) is in registers;
+//   * SOC search directions are accumulated in the NT-scaled space and all reciprocals / rsqrts are
+//     branch-free (hardware seed + one cubic step).
+// The warps of a CTA advance through the interior-point iterations in lockstep (dcol_dispatch.cu pulls CTA-sized
+// tiles from a queue), so that they share instruction-cache lines.
 #pragma once
 #include "dcol_common.cuh"
 #include "dcol_deriv.cuh"

@@ -146,7 +146,7 @@ class Context:
         if kind == 1:
             out["grad"] = deriv
         elif kind == 2:
-            out["J"] = np.ascontiguousarray(deriv.transpose(0, 2, 1))  # (n, 4, nt)
+            out["J"] = deriv.transpose(0, 2, 1)  # (n, 4, nt) view of the column-major C layout, no copy
         return out
 
     def _alloc_out(self, kind, n, nt):
@@ -162,7 +162,7 @@ class Context:
         if kind == 1:
             out["grad"] = deriv
         elif kind == 2:
-            out["J"] = np.ascontiguousarray(deriv.transpose(0, 2, 1))  # (n, 4, nt)
+            out["J"] = deriv.transpose(0, 2, 1)  # (n, 4, nt) view of the column-major C layout, no copy
         return out
 
     def query_indexed(self, kind, shape1, shape2, pose1, pose2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):

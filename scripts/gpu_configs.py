@@ -1,0 +1,55 @@
+"""Throughput of the five BASELINE.json configs through the public Python API (host buffers, one blocking call at a time)
+and, where it exists, the kernel time of the same call.  Informational: bench.py reports configs 2 and 3."""
+import sys, os, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import dcol_b200 as dc
+import util
+from test_gpu_operators import scene_bodies
+
+ctx = dc.Context(0)
+
+def timed(fn, reps=5):
+    fn(); best = 1e9; kms = None
+    for _ in range(reps):
+        t0 = time.perf_counter(); out = fn(); best = min(best, time.perf_counter() - t0); kms = ctx.last_kernel_ms()
+    return best, kms, out
+
+# 1: cube-cube, 10k random poses, proximity
+t, s1, s2, r1, a1, r2, a2 = util.cube_batch(10000, 0)
+ctx.set_shape_arrays(*t.arrays())
+w, k, o = timed(lambda: ctx._batch(0, s1, s2, r1, a1, r2, a2, 0, 1e-6))
+print(f"config 1  cube-cube proximity, 10k pairs:            call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {10000/w/1e6:8.2f} Mpairs/s  (mean iters {o['iters'].mean():.2f})")
+# 2: 7x7 mixed, 1M, proximity
+t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(1000000, 0)
+ctx.set_shape_arrays(*t.arrays())
+w, k, o = timed(lambda: ctx._batch(0, s1, s2, r1, a1, r2, a2, 0, 1e-6), 3)
+print(f"config 2  7x7 mixed proximity, 1M pairs:             call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {1e6/w/1e6:8.2f} Mpairs/s")
+# 3: mixed MRP jacobian, 2M per GPU
+t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(2000000, 1, seed=4321)
+ctx.set_shape_arrays(*t.arrays())
+w, k, o = timed(lambda: ctx._batch(2, s1, s2, r1, a1, r2, a2, 1, 1e-6), 2)
+print(f"config 3  mixed MRP jacobian, 2M pairs (1 of 8 GPUs): call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {2e6/w/1e6:8.2f} Mpairs/s")
+# 4: 4096-body scene, all pairs, gradient
+nb = 4096
+t, shape, r, att = scene_bodies(nb, 0, spread=5.0)
+ctx.set_shape_arrays(*t.arrays())
+w, k, o = timed(lambda: ctx.scene_allpairs(1, shape, r, att, 0), 2)
+npairs = nb * (nb - 1) // 2
+print(f"config 4  4096-body scene, {npairs} gradient pairs:  call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {npairs/w/1e6:8.2f} Mpairs/s  (collisions {int((o['alpha'] <= 1).sum())})")
+# 5: piano mover batch: 1024 rollouts x 100 knots x 3 obstacles, jacobian, MRP p = (0,0,tan(theta/4))
+B, N, K = 1024, 100, 3
+veh = dc.create_rect_prism(2.5, 0.15, 0.01)[0]
+obs = [dc.create_rect_prism(3.0, 3.0, 0.02)[0], dc.create_rect_prism(4.0, 1.0, 0.02)[0], dc.create_rect_prism(1.0, 3.0, 0.02)[0]]
+t = dc.ShapeTable(); sv = t.add(veh); so = [t.add(x) for x in obs]
+ctx.set_shape_arrays(*t.arrays())
+g = util.rng(17)
+theta = g.uniform(-np.pi, np.pi, B * N)
+r1 = np.stack([g.uniform(-4, 4, B * N), g.uniform(-4, 4, B * N), np.zeros(B * N)], axis=1)
+p1 = np.stack([np.zeros(B * N), np.zeros(B * N), np.tan(theta / 4)], axis=1)
+r2 = np.array([[-1.5, 1.5, 0.0], [2.0, -2.5, 0.0], [3.0, 2.5, 0.0]]); p2 = np.zeros((3, 3))
+pose1 = np.repeat(np.arange(B * N, dtype=np.int32), K); pose2 = np.tile(np.arange(K, dtype=np.int32), B * N)
+s1 = np.full(B * N * K, sv, np.int32); s2 = np.array(so, np.int32)[pose2]
+w, k, o = timed(lambda: ctx.query_indexed(2, s1, s2, pose1, pose2, r1, p1, r2, p2, dc.ATT_MRP), 3)
+print(f"config 5  piano-mover batch, {B*N*K} box-box MRP jacobians: call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {B*N*K/w/1e6:8.2f} Mpairs/s  (failed {int((o['status'] != 0).sum())})")

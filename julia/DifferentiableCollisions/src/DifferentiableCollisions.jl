@@ -17,7 +17,8 @@ module DifferentiableCollisions
 using LinearAlgebra
 using StaticArrays
 
-export *, \
+# (The reference exports only its NT-scaling operators `*` and `\`, src/DifferentiableCollisions.jl:36; users call `dc.name`.
+#  Those operators belong to the CPU solver and have no counterpart here, so nothing is exported.)
 
 const _lib = Ref{String}("")
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)

@@ -7,7 +7,7 @@ from .primitives import (  # noqa: F401
     ATT_MRP, ATT_QUAT, AbstractPrimitive, AbstractPrimitiveMRP,
     Polytope, Capsule, Cylinder, Cone, Sphere, Polygon, Ellipsoid,
     PolytopeMRP, CapsuleMRP, CylinderMRP, ConeMRP, SphereMRP, PolygonMRP, EllipsoidMRP,
-    create_rect_prism, create_n_sided, mrp_from_q, q_from_mrp, dcm_from_q, dcm_from_mrp,
+    create_rect_prism, create_n_sided, mass_properties, mrp_from_q, q_from_mrp, dcm_from_q, dcm_from_mrp,
 )
 from .shapes import ShapeTable  # noqa: F401
 from .api import (  # noqa: F401

@@ -190,6 +190,35 @@ def create_n_sided(N, d):  # :28-33
     return A, b
 
 
+# --- mass properties: src/mass_properties.jl:2-48 (cone, capsule, cylinder only; host scalars, not on the query path) ---
+def mass_properties(prim, rho: float = 1.0):
+    """(mass, 3x3 diagonal inertia about the body axes) for a uniform-density Cone, Capsule or Cylinder, with the
+    reference's conventions: x is the symmetry axis; the cone's base radius is H*tan(beta); the capsule is a cylinder
+    of length L plus two hemispherical caps.  The cylinder's transverse inertia keeps the reference's coefficient
+    m/12*(2R^2 + L^2) (src/mass_properties.jl:44-45; the textbook value has 3R^2) so that simulations built on it
+    reproduce the reference's trajectories."""
+    t = prim.shape_type
+    if t == CONE:
+        rad = math.tan(prim.beta) * prim.H
+        m = rho * math.pi * rad**2 * prim.H / 3.0
+        ixx = 0.3 * m * rad**2
+        iyy = m * (3.0 / 20.0 * rad**2 + 3.0 / 80.0 * prim.H**2)
+        return m, np.diag([ixx, iyy, iyy])
+    if t == CAPSULE:
+        R, L = prim.R, prim.L
+        m_cyl = rho * math.pi * R**2 * L
+        m_cap = rho * 2.0 * math.pi * R**3 / 3.0          # one hemisphere
+        ixx = 0.5 * m_cyl * R**2 + 2.0 * m_cap * (0.4 * R**2)
+        iyy = m_cyl * (L**2 / 12.0 + R**2 / 4.0) + 2.0 * m_cap * (0.4 * R**2 + L**2 / 2.0 + 3.0 * L * R / 8.0)
+        return m_cyl + 2.0 * m_cap, np.diag([ixx, iyy, iyy])
+    if t == CYLINDER:
+        R, L = prim.R, prim.L
+        m = rho * math.pi * R**2 * L
+        iyy = m / 12.0 * (2.0 * R**2 + L**2)
+        return m, np.diag([0.5 * m * R**2, iyy, iyy])
+    raise TypeError("mass_properties is defined for Cone, Capsule and Cylinder only (as in the reference)")
+
+
 # --- attitude helpers: src/problem_matrices.jl:1-27 (host convenience; not on the device path) ----
 def mrp_from_q(q):
     q = _vec(q, 4)

@@ -131,6 +131,27 @@ function create_n_sided(N, d)
     return SMatrix{N,2}(A), SVector{N}(d * ones(N))
 end
 
+# mass and diagonal body-frame inertia (x = symmetry axis) of uniform-density cones, capsules and cylinders — the three
+# shapes the reference covers (src/mass_properties.jl:2-48); the cylinder keeps the reference's 2R^2 coefficient
+function mass_properties(c::Union{Cone,ConeMRP}; ρ = 1.0)
+    rad = tan(c.β) * c.H
+    m = ρ * π * rad^2 * c.H / 3
+    it = m * (3rad^2 / 20 + 3c.H^2 / 80)
+    return m, Diagonal(SA[0.3m * rad^2, it, it])
+end
+function mass_properties(c::Union{Capsule,CapsuleMRP}; ρ = 1.0)
+    R, L = c.R, c.L
+    mc = ρ * π * R^2 * L
+    mh = ρ * 2π * R^3 / 3
+    it = mc * (L^2 / 12 + R^2 / 4) + 2mh * (0.4R^2 + L^2 / 2 + 3L * R / 8)
+    return mc + 2mh, Diagonal(SA[0.5mc * R^2 + 2mh * 0.4R^2, it, it])
+end
+function mass_properties(c::Union{Cylinder,CylinderMRP}; ρ = 1.0)
+    m = ρ * π * c.R^2 * c.L
+    it = m / 12 * (2c.R^2 + c.L^2)
+    return m, Diagonal(SA[0.5m * c.R^2, it, it])
+end
+
 # ---------------------------------------------------------------------------------------------
 # shape table packing (include/dcol_b200.h: dcol_set_shapes)
 # ---------------------------------------------------------------------------------------------

@@ -67,3 +67,19 @@ def test_flops_model_matches_survey_examples():
     fm = dc.flops_model
     assert fm.f_iter(4, 12, []) == pytest.approx(1585, abs=1)       # SURVEY §8d cube-cube
     assert fm.f_fixed(4, 12) == 1224
+
+
+def test_mass_properties_host_helper():
+    """src/mass_properties.jl:2-48 conventions (x = symmetry axis); checked against independently computed numbers."""
+    import math
+    m, I = dc.mass_properties(dc.Cylinder(0.6, 3.0), rho=2.0)
+    assert m == pytest.approx(2.0 * math.pi * 0.36 * 3.0) and I[0, 0] == pytest.approx(0.5 * m * 0.36)
+    assert I[1, 1] == pytest.approx(m / 12 * (2 * 0.36 + 9.0)) and I[2, 2] == I[1, 1]
+    m, I = dc.mass_properties(dc.CapsuleMRP(0.3, 1.2))
+    vol = math.pi * 0.09 * 1.2 + 4.0 / 3.0 * math.pi * 0.027
+    assert m == pytest.approx(vol) and I[0, 0] < I[1, 1]
+    m, I = dc.mass_properties(dc.Cone(2.0, math.radians(22)))
+    rad = 2.0 * math.tan(math.radians(22))
+    assert m == pytest.approx(math.pi * rad**2 * 2.0 / 3) and I[0, 0] == pytest.approx(0.3 * m * rad**2)
+    with pytest.raises(TypeError):
+        dc.mass_properties(dc.Sphere(1.0))

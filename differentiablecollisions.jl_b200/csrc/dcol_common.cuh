@@ -21,13 +21,22 @@ enum { SOC_NONE = 0, SOC_BALL = 1, SOC_CONE = 2, SOC_ELL = 3 };
 enum { ST_OK = 0, ST_PDIP_FAILED = 1, ST_NUMERICAL = 2 };
 enum { Q_PROX = 0, Q_GRAD = 1, Q_JAC = 2 };
 
+// nz(a): can coefficient a of an orthant row c = [c_x(3), c_alpha, c_e(NE)] be non-zero for this class?  The rows of
+// capsules / cylinders (axis = body x), cones (base plane normal = body x) and polygons (planar constraints on the
+// slack e only) are structurally sparse; the row passes skip the zero columns at compile time.
 template <int CLS> struct Cls;
-template <> struct Cls<CLS_POLYTOPE> { static constexpr int NE = 0, SOC = SOC_NONE, D = 0; };
-template <> struct Cls<CLS_SPHERE>   { static constexpr int NE = 0, SOC = SOC_BALL, D = 4; };
-template <> struct Cls<CLS_CAPCYL>   { static constexpr int NE = 1, SOC = SOC_BALL, D = 4; };
-template <> struct Cls<CLS_POLYGON>  { static constexpr int NE = 2, SOC = SOC_BALL, D = 4; };
-template <> struct Cls<CLS_CONE>     { static constexpr int NE = 0, SOC = SOC_CONE, D = 3; };
-template <> struct Cls<CLS_ELL>      { static constexpr int NE = 0, SOC = SOC_ELL, D = 4; };
+template <> struct Cls<CLS_POLYTOPE> { static constexpr int NE = 0, SOC = SOC_NONE, D = 0;
+  __host__ __device__ static constexpr bool nz(int) { return true; } };
+template <> struct Cls<CLS_SPHERE>   { static constexpr int NE = 0, SOC = SOC_BALL, D = 4;
+  __host__ __device__ static constexpr bool nz(int) { return true; } };
+template <> struct Cls<CLS_CAPCYL>   { static constexpr int NE = 1, SOC = SOC_BALL, D = 4;
+  __host__ __device__ static constexpr bool nz(int a) { return a == 0 || a >= 3; } };
+template <> struct Cls<CLS_POLYGON>  { static constexpr int NE = 2, SOC = SOC_BALL, D = 4;
+  __host__ __device__ static constexpr bool nz(int a) { return a >= 3; } };
+template <> struct Cls<CLS_CONE>     { static constexpr int NE = 0, SOC = SOC_CONE, D = 3;
+  __host__ __device__ static constexpr bool nz(int a) { return a == 0 || a == 3; } };
+template <> struct Cls<CLS_ELL>      { static constexpr int NE = 0, SOC = SOC_ELL, D = 4;
+  __host__ __device__ static constexpr bool nz(int) { return true; } };
 
 __host__ __device__ inline int cls_ne(int c) { return c == CLS_CAPCYL ? 1 : (c == CLS_POLYGON ? 2 : 0); }
 __host__ __device__ inline int cls_d(int c) { return c == CLS_POLYTOPE ? 0 : (c == CLS_CONE ? 3 : 4); }

@@ -222,6 +222,7 @@ struct Prim {
   static constexpr int NE = Cls<CLS>::NE, NV = 4 + Cls<CLS>::NE, D = Cls<CLS>::D, DD = (Cls<CLS>::D > 0 ? Cls<CLS>::D : 1);
   // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes); elsewhere code size wins
   static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE) ? 2 : 1;
+  __device__ static constexpr bool nz(int a) { return Cls<CLS>::nz(a); }   // structurally non-zero row coefficient
   const double* rows; int n; int row0;
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
@@ -260,15 +261,15 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
-      for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
+      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
       double u = 0.0;
       if (has_off) {
 #pragma unroll
-        for (int a = 0; a < NV; a++) u += c[a] * yh0[a]; }
+        for (int a = 0; a < NV; a++) if (nz(a)) u += c[a] * yh0[a]; }
 #pragma unroll
-      for (int a = 0; a < NV; a++) { g[a] += u * c[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) { g[a] += u * c[a];
 #pragma unroll
-        for (int b = a; b < NV; b++) N[a][b] += c[a] * c[b]; }
+        for (int b = a; b < NV; b++) if (nz(b)) N[a][b] += c[a] * c[b]; }
     }
     if constexpr (D > 0) {
       double I[D][D];
@@ -286,7 +287,7 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double us = 0.0, uz = 0.0;
 #pragma unroll
-      for (int a = 0; a < NV; a++) { double c = __ldg(rows + i * NV + a); us += c * yh[a]; uz += c * dh[a]; }
+      for (int a = 0; a < NV; a++) if (nz(a)) { double c = __ldg(rows + i * NV + a); us += c * yh[a]; uz += c * dh[a]; }
       rs(F_S, row0 + i) = -us; rs(F_Z, row0 + i) = uz;
       min_s = fmin(min_s, -us); min_z = fmin(min_z, uz);
     }
@@ -330,21 +331,21 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
-      for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
+      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i);
       double u = 0.0;
 #pragma unroll
-      for (int a = 0; a < NV; a++) u += c[a] * yh[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) u += c[a] * yh[a];
       const double r = si - u;
       const double rr = fast_rcp(si * zi);     // 1/(s z): 1/s = z*rr, 1/z = s*rr
       const double d = zi * zi * rr;           // z/s
       const double dr = d * r;
 #pragma unroll
-      for (int a = 0; a < NV; a++) {
+      for (int a = 0; a < NV; a++) if (nz(a)) {
         const double dc = d * c[a];
         g[a] += dr * c[a];
 #pragma unroll
-        for (int b = a; b < NV; b++) N[a][b] += dc * c[b];
+        for (int b = a; b < NV; b++) if (nz(b)) N[a][b] += dc * c[b];
       }
       rs(F_R, row0 + i) = rr; rs(F_RZ, row0 + i) = r;
     }
@@ -412,7 +413,7 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
 #pragma unroll
-      for (int a = 0; a < NV; a++) cd += __ldg(rows + i * NV + a) * dyh[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) cd += __ldg(rows + i * NV + a) * dyh[a];
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i);
       const double t = r - cd;                  // -ds
       const double is = zi * rr;
@@ -459,7 +460,7 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       const double q = (sigmu - rs(F_P, row0 + i)) * rs(F_Z, row0 + i) * rs(F_R, row0 + i);
 #pragma unroll
-      for (int a = 0; a < NV; a++) g2[a] += q * __ldg(rows + i * NV + a);
+      for (int a = 0; a < NV; a++) if (nz(a)) g2[a] += q * __ldg(rows + i * NV + a);
     }
   }
   __device__ __forceinline__ void passC_soc(double sigmu, double (&g2)[NV]) {
@@ -491,7 +492,7 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
 #pragma unroll
-      for (int a = 0; a < NV; a++) cd += __ldg(rows + i * NV + a) * dyh[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) cd += __ldg(rows + i * NV + a) * dyh[a];
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i), pp = rs(F_P, row0 + i);
       const double t = r - cd;
       const double is = zi * rr, iz = si * rr;
@@ -549,7 +550,7 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double zi = rs(F_Z, row0 + i);
 #pragma unroll
-      for (int a = 0; a < 3; a++) w[a] += zi * __ldg(rows + i * NV + a);
+      for (int a = 0; a < 3; a++) if (nz(a)) w[a] += zi * __ldg(rows + i * NV + a);
     }
     constexpr int SOC = Cls<CLS>::SOC;
     if constexpr (D > 0 && SOC != SOC_BALL) soc_applyT<CLS, NV, D>(sc, z, w);
@@ -573,12 +574,12 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
-      for (int a = 0; a < NV; a++) c[a] = __ldg(rows + i * NV + a);
+      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
       double d = rs(F_Z, row0 + i) / rs(F_S, row0 + i);
 #pragma unroll
-      for (int a = 0; a < NV; a++) { double dc = d * c[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) { double dc = d * c[a];
 #pragma unroll
-        for (int b = a; b < NV; b++) Nf[a][b] += dc * c[b]; }
+        for (int b = a; b < NV; b++) if (nz(b)) Nf[a][b] += dc * c[b]; }
     }
 #pragma unroll
     for (int a = 0; a < NV; a++) {

@@ -221,7 +221,10 @@ template <int CLS>
 struct Prim {
   static constexpr int NE = Cls<CLS>::NE, NV = 4 + Cls<CLS>::NE, D = Cls<CLS>::D, DD = (Cls<CLS>::D > 0 ? Cls<CLS>::D : 1);
   // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes); elsewhere code size wins
-  static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE) ? 2 : 1;
+#ifndef DCOL_ROW_UNROLL_SMALL
+#define DCOL_ROW_UNROLL_SMALL 1
+#endif
+  static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE) ? 2 : DCOL_ROW_UNROLL_SMALL;
   __device__ static constexpr bool nz(int a) { return Cls<CLS>::nz(a); }   // structurally non-zero row coefficient
   const double* rows; int n; int row0;
   double sc[9];
@@ -243,7 +246,8 @@ struct Prim {
   }
 
   __device__ __forceinline__ void load(const DevShape* S, const double* rows_base, int row0_) {
-    n = S->n_ort; rows = rows_base + S->rows_off; row0 = row0_;
+    n = (CLS == CLS_CONE) ? 1 : S->n_ort;      // a cone has exactly one orthant row (its base plane)
+    rows = rows_base + S->rows_off; row0 = row0_;
     constexpr int SOC = Cls<CLS>::SOC;
     if constexpr (SOC == SOC_BALL) sc[0] = S->soc[0];
     if constexpr (SOC == SOC_CONE) { sc[0] = S->soc[0]; sc[1] = S->soc[1]; }

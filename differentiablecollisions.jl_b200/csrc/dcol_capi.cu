@@ -163,57 +163,84 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
   }
 }
 
-// single thread: instantiates the static per-tier launch plan (uploaded once by dcol_set_shapes; key ranges parked in
+// one small block: instantiates the static per-tier launch plan (uploaded once by dcol_set_shapes; key ranges parked in
 // begin[]/end[]) for this call — query parameters arrive as a kernel argument, bin offsets from the counting sort —
 // so that neither a host read of the histogram nor a host-to-device copy sits between the sort and the solver.
 // Also carves the straggler overflow area: bin b gets tiles_b * spill_t records (a tile hands over at most spill_t pairs).
+// The kernel sits on the critical path of every call (sort -> tables -> solver): the plan is copied by all threads,
+// one thread per bin fetches the bin's range, and only the two short prefix sums are serial (in shared memory).
+constexpr int TABLE_THREADS = 64;
+static_assert(MAX_BINS <= TABLE_THREADS, "one thread per bin");
 __global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
                                const int* __restrict__ off, double* ov_base, QueryParams P, int spill_div) {
-  if (threadIdx.x || blockIdx.x) return;
-  long long ov = 0;
+  __shared__ int s_nt[MAX_BINS];
+  __shared__ long long s_ovsz[MAX_BINS];
+  __shared__ long long s_ov;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_ov = 0;
   for (int t = 0; t < n_tiers; t++) {
-    LaunchTable& T = tables[t];
-    T = plan[t];
-    const int tile = T.n_tiles;            // the plan parks the tier's CTA size here
-    const int pitch = T.P.row_pitch;
-    T.P = P; T.P.row_pitch = pitch;
-    T.spill_t = spill_div > 0 ? tile / spill_div : 0;
-    int tiles = 0;
-    for (int k = 0; k < T.n_bins; k++) {
-      const int b = off[T.begin[k]], e = off[T.end[k]];
-      const int nt = (e - b + tile - 1) / tile;
-      T.begin[k] = b; T.end[k] = e;
-      T.tile_prefix[k] = tiles;
-      tiles += nt;
-      T.ov_cap[k] = nt * T.spill_t; T.ov_off[k] = ov; T.ov_count[k] = 0;
-      ov += (long long)T.ov_cap[k] * T.ov_stride[k];
+    {
+      const int* src = reinterpret_cast<const int*>(plan + t);
+      int* dst = reinterpret_cast<int*>(tables + t);
+      for (int i = tid; i < (int)(sizeof(LaunchTable) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
-    for (int k = T.n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
-    T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0; T.in_base = ov_base;
-    T.tile = tile;
+    __syncthreads();
+    LaunchTable& T = tables[t];
+    const int tile = T.n_tiles;            // the plan parks the tier's CTA size here
+    const int spill_t = spill_div > 0 ? tile / spill_div : 0;
+    const int n_bins = T.n_bins;
+    if (tid < n_bins) {
+      const int b = off[T.begin[tid]], e = off[T.end[tid]];
+      const int nt = (e - b + tile - 1) / tile;
+      T.begin[tid] = b; T.end[tid] = e;
+      T.ov_cap[tid] = nt * spill_t; T.ov_count[tid] = 0;
+      s_nt[tid] = nt; s_ovsz[tid] = (long long)nt * spill_t * T.ov_stride[tid];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tiles = 0;
+      long long ov = s_ov;
+      for (int k = 0; k < n_bins; k++) {
+        T.tile_prefix[k] = tiles; T.ov_off[k] = ov;
+        tiles += s_nt[k]; ov += s_ovsz[k];
+      }
+      for (int k = n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
+      s_ov = ov;
+      const int pitch = T.P.row_pitch;
+      T.P = P; T.P.row_pitch = pitch;
+      T.spill_t = spill_t;
+      T.n_tiles = tiles; T.ov_base = ov_base; T.mode = 0; T.in_base = ov_base;
+      T.tile = tile;
+    }
+    __syncthreads();
   }
 }
 // resume-pass table of ONE tier from the overflow counts its previous pass left behind (launched right behind that
 // pass on the tier's stream, so the resume pass of one tier overlaps the first pass of the next); the resume pass may
 // itself hand its stragglers over (spill > 0) into the other overflow buffer, which reuses the previous layout
 __global__ void k_build_tables2(const LaunchTable* __restrict__ Tp, LaunchTable* __restrict__ Up, double* ov_next, int spill) {
-  if (threadIdx.x || blockIdx.x) return;
+  __shared__ int s_nt[MAX_BINS];
   const LaunchTable& T = *Tp;
   LaunchTable& U = *Up;
-  const int tile = T.tile;
-  U.P = T.P; U.tile = tile;
-  int tiles = 0;
-  for (int k = 0; k < T.n_bins; k++) {
+  const int tid = threadIdx.x;
+  const int tile = T.tile, n_bins = T.n_bins;
+  if (tid < n_bins) {
+    const int k = tid;
     const int cnt = min(T.ov_count[k], T.ov_cap[k]);
     U.begin[k] = 0; U.end[k] = cnt; U.cp[k] = T.cp[k];
-    U.tile_prefix[k] = tiles;
-    tiles += (cnt + tile - 1) / tile;
+    s_nt[k] = (cnt + tile - 1) / tile;
     U.in_cap[k] = T.ov_cap[k]; U.in_off[k] = T.ov_off[k]; U.ov_stride[k] = T.ov_stride[k];
     U.ov_cap[k] = spill ? T.ov_cap[k] : 0; U.ov_off[k] = T.ov_off[k]; U.ov_count[k] = 0;
   }
-  for (int k = T.n_bins; k <= MAX_BINS; k++) U.tile_prefix[k] = tiles;
-  U.n_bins = T.n_bins; U.n_tiles = tiles; U.in_base = T.ov_base; U.ov_base = ov_next; U.mode = 1;
-  U.spill_t = spill ? T.spill_t : 0; U.rows_cap = T.rows_cap;
+  __syncthreads();
+  if (tid == 0) {
+    int tiles = 0;
+    for (int k = 0; k < n_bins; k++) { U.tile_prefix[k] = tiles; tiles += s_nt[k]; }
+    for (int k = n_bins; k <= MAX_BINS; k++) U.tile_prefix[k] = tiles;
+    U.P = T.P; U.tile = tile;
+    U.n_bins = n_bins; U.n_tiles = tiles; U.in_base = T.ov_base; U.ov_base = ov_next; U.mode = 1;
+    U.spill_t = spill ? T.spill_t : 0; U.rows_cap = T.rows_cap;
+  }
 }
 
 // (i, j), i < j in combinations(1:N, 2) order (the pair list of examples/contact_physics/ncp_contact_simulation.jl:48),
@@ -715,7 +742,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
       k_scan<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor);
       k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_perm);
-      k_build_tables<<<1, 32, 0, SC>>>((const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_off, d_ovc, P, spill_div);
+      k_build_tables<<<1, TABLE_THREADS, 0, SC>>>((const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_off, d_ovc, P, spill_div);
       ctx->launches += 4;
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table
@@ -732,7 +759,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       for (int lv = 1; lv <= levels && spill_div > 0; lv++) {
         LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers) + t;
         LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers) + t;
-        k_build_tables2<<<1, 32, 0, st>>>(prev, cur, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
+        k_build_tables2<<<1, TABLE_THREADS, 0, st>>>(prev, cur, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
         CK(launch_persistent(jac, TR.grid[jac], TR.block, TR.smem, st, cur, d_counter + lv * NSIDE + t));
         ctx->launches += 2;
       }

@@ -1,4 +1,4 @@
-// Persistent proximity kernels (one per query kind): every CTA (1 per SM, 8 warps in lockstep) pulls CTA-sized
+// Persistent proximity kernels (one per query kind): every CTA (2 per SM, 4 warps in lockstep each) pulls CTA-sized
 // tiles from a global queue ordered by class pair and dispatches to the class-pair specialisation of the tile's
 // bin (device-linked entries from dcol_kernels_c*.cu).
 #include "dcol_common.cuh"

@@ -120,8 +120,37 @@ class Context:
     def wait(self, ticket: int):
         self._check(self._lib.dcol_wait(self._h, int(ticket)))
 
+    # ---- pinned host memory (`dcol_host_register`) ---------------------------------------------
+    def pin(self, arr: np.ndarray) -> np.ndarray:
+        """Page-lock a C-contiguous numpy array in place: host-pointer calls then move it by DMA (55 GB/s measured on
+        B200) instead of through the driver's staging copies (4 GB/s device-to-host).  Pin once, reuse across calls,
+        `unpin` before the array is freed."""
+        if not arr.flags["C_CONTIGUOUS"]:
+            raise ValueError("pin: array must be C-contiguous")
+        self._check(self._lib.dcol_host_register(self._h, arr.ctypes.data, arr.nbytes))
+        return arr
+
+    def unpin(self, arr: np.ndarray):
+        self._check(self._lib.dcol_host_unregister(self._h, arr.ctypes.data))
+
+    def alloc_outputs(self, kind, n, att_kind=ATT_QUAT, pinned=True):
+        """Output buffers of one batched query (`out=` of the *_batch methods), page-locked by default."""
+        nt = 6 + 2 * (4 if att_kind == ATT_QUAT else 3)
+        out = {"alpha": np.empty(n), "status": np.empty(n, dtype=np.int32), "iters": np.empty(n, dtype=np.int32)}
+        if kind != 1:
+            out["x"] = np.empty((n, 3))
+        if kind == 1:
+            out["deriv"] = np.empty((n, nt))
+        elif kind == 2:
+            out["deriv"] = np.empty((n, nt, 4))
+        if pinned:
+            for a in out.values():
+                if a.nbytes:
+                    self.pin(a)
+        return out
+
     # ---- batched host API ----------------------------------------------------------------------
-    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol):
+    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out=None):
         shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
         shape2 = np.ascontiguousarray(shape2, dtype=np.int32).reshape(-1)
         n = shape1.shape[0]
@@ -133,11 +162,18 @@ class Context:
         att2 = np.ascontiguousarray(att2, dtype=np.float64).reshape(n, na)
         if shape2.shape[0] != n:
             raise ValueError("shape1 and shape2 must have the same length")
-        alpha = np.empty(n)
-        x = np.empty((n, 3)) if kind != 1 else None
-        deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
-        status = np.empty(n, dtype=np.int32)
-        iters = np.empty(n, dtype=np.int32)
+        if out is not None:        # caller-owned (e.g. pinned) buffers from alloc_outputs
+            alpha, status, iters = out["alpha"], out["status"], out["iters"]
+            x, deriv = out.get("x"), out.get("deriv")
+            want = (n, nt) if kind == 1 else (n, nt, 4)
+            if alpha.shape != (n,) or (kind != 1 and x.shape != (n, 3)) or (kind != 0 and deriv.shape != want):
+                raise ValueError("out: buffers do not match this query (use alloc_outputs with the same kind, n, att_kind)")
+        else:
+            alpha = np.empty(n)
+            x = np.empty((n, 3)) if kind != 1 else None
+            deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
+            status = np.empty(n, dtype=np.int32)
+            iters = np.empty(n, dtype=np.int32)
         self.query_raw(kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, MEM_HOST,
                        alpha, x, deriv, status, iters)
         out = {"alpha": alpha, "status": status, "iters": iters}
@@ -202,14 +238,14 @@ class Context:
                                                   MEM_HOST, _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
         return self._finish(out, kind, x, deriv)
 
-    def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
-        return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+    def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
+        return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 
-    def proximity_gradient_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
-        return self._batch(1, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+    def proximity_gradient_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
+        return self._batch(1, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 
-    def proximity_jacobian_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
-        return self._batch(2, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+    def proximity_jacobian_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
+        return self._batch(2, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 
 
 _default_ctx = None

@@ -369,6 +369,32 @@ int dcol_set_stream(dcol_ctx* ctx, void* cuda_stream) {
   return 0;
 }
 
+// Page-lock caller-owned host memory (thin wrappers for callers without CUDA bindings: Julia Arrays, numpy arrays).
+int dcol_host_register(dcol_ctx* ctx, void* ptr, int64_t bytes) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  if (!ptr || bytes <= 0) { ctx->err = "dcol_host_register: bad arguments"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();      // not sticky: clear it so that the next launch check does not report it
+    ctx->err = std::string("dcol_host_register: ") + cudaGetErrorString(e); return -2;
+  }
+  return 0;
+}
+int dcol_host_unregister(dcol_ctx* ctx, void* ptr) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  if (!ptr) { ctx->err = "dcol_host_unregister: bad arguments"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx->err = std::string("dcol_host_unregister: ") + cudaGetErrorString(e); return -2;
+  }
+  return 0;
+}
+
 int64_t dcol_launch_count(const dcol_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double dcol_last_kernel_ms(const dcol_ctx* ctx) { return ctx ? ctx->last_ms : -1.0; }
 

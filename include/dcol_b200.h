@@ -139,6 +139,16 @@ int dcol_submit(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1, cons
                 double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
 int dcol_wait(dcol_ctx* ctx, int ticket);
 
+/* ---- pinned host memory -----------------------------------------------------------------------------------
+ * Host-pointer calls accept any host memory, but pageable memory travels through the driver's staging copies
+ * (measured on B200: 4 GB/s device-to-host instead of 55 GB/s, and the call cannot overlap its copies with its
+ * kernels).  dcol_host_register page-locks a caller-owned buffer in place (cudaHostRegister) so that every later call
+ * using it moves it by DMA; register the input and output arrays once and reuse them across calls (registration
+ * itself costs milliseconds).  dcol_host_unregister must be called before the memory is freed.  Callers with their
+ * own CUDA bindings may pin memory any other way. */
+int dcol_host_register(dcol_ctx* ctx, void* ptr, int64_t bytes);
+int dcol_host_unregister(dcol_ctx* ctx, void* ptr);
+
 /* Instrumentation for bench.py / tests. */
 /* kernels launched by this context since creation (solver + derivative + binning kernels) */
 int64_t dcol_launch_count(const dcol_ctx* ctx);

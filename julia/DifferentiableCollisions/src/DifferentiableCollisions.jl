@@ -297,7 +297,7 @@ end
 
 Asynchronous form (`dcol_submit` / `dcol_wait`): up to three submissions in flight, so that the PCIe copies of one
 batch overlap the kernels of the previous one.  `res` and the input arrays must stay alive and untouched until
-`wait!(ticket)` returns (use pinned memory, e.g. `CUDA.pin`, for the copies to be truly asynchronous).
+`wait!(ticket)` returns (use pinned memory, `pin!`, for the copies to be truly asynchronous).
 """
 function submit!(res::BatchResult, kind::Integer, s1::Vector{Int32}, s2::Vector{Int32}, r1::Matrix{Float64}, a1::Matrix{Float64},
                  r2::Matrix{Float64}, a2::Matrix{Float64}; pdip_tol = 1e-6)
@@ -310,6 +310,19 @@ function submit!(res::BatchResult, kind::Integer, s1::Vector{Int32}, s2::Vector{
     return t
 end
 wait!(ticket::Integer) = (_check(ccall((:dcol_wait, _lib[]), Cint, (Ptr{Cvoid}, Cint), _ctx[], ticket)); nothing)
+
+"""
+    pin!(a::Array) -> a ;  unpin!(a::Array)
+
+Page-lock a Julia array in place (`dcol_host_register`): host-pointer calls then move it by DMA at the full PCIe rate
+instead of through the driver's staging copies.  Pin input and output arrays once, reuse them across calls, and
+`unpin!` them before they can be garbage-collected.
+"""
+function pin!(a::Array)
+    _check(ccall((:dcol_host_register, _lib[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), _ctx[], a, sizeof(a)))
+    return a
+end
+unpin!(a::Array) = (_check(ccall((:dcol_host_unregister, _lib[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), _ctx[], a)); nothing)
 
 # ---------------------------------------------------------------------------------------------
 # single-pair drop-in calls: a batch of one through the same entry points

@@ -308,6 +308,38 @@ def test_async_submit_matches_sync(ctx):
             assert np.array_equal(o["deriv"].numpy().transpose(0, 2, 1), ref["J"], equal_nan=True)
 
 
+def test_registered_host_buffers(ctx):
+    """dcol_host_register: numpy arrays page-locked in place give the same bits as pageable ones (and may be reused);
+    bad arguments are API errors, not crashes."""
+    import time
+    n = 200000
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, 1, seed=77)
+    ctx.set_shape_arrays(*t.arrays())
+    ref = ctx.proximity_jacobian_batch(s1, s2, r1, a1, r2, a2, att_kind=1)
+    ins = [ctx.pin(np.ascontiguousarray(a)) for a in (s1, s2, r1, a1, r2, a2)]
+    out = ctx.alloc_outputs(2, n, att_kind=1, pinned=True)
+    try:
+        t_pin = []
+        for rep in range(3):
+            for a in out.values():
+                a.fill(0)
+            t0 = time.perf_counter()
+            res = ctx.proximity_jacobian_batch(*ins, att_kind=1, out=out)
+            t_pin.append(time.perf_counter() - t0)
+            assert res["alpha"] is out["alpha"]
+            assert np.array_equal(res["alpha"], ref["alpha"]) and np.array_equal(res["x"], ref["x"])
+            assert np.array_equal(res["J"], ref["J"], equal_nan=True) and np.array_equal(res["iters"], ref["iters"])
+        with pytest.raises(RuntimeError):
+            ctx.pin(out["alpha"])                       # already registered
+        with pytest.raises(ValueError):
+            ctx.proximity_gradient_batch(*ins, att_kind=1, out=out)   # buffers of another query kind
+    finally:
+        for a in ins + list(out.values()):
+            ctx.unpin(a)
+    with pytest.raises(RuntimeError):
+        ctx.unpin(out["alpha"])                         # not registered any more
+
+
 @pytest.mark.parametrize("att_kind", [0, 1])
 def test_random_shape_parameters(ctx, oracle, att_kind):
     """Random geometry instead of the reference's fixed test shapes: 6 shapes per kind with random sizes, random bounded

@@ -220,7 +220,10 @@ __device__ __forceinline__ double soc_linesearch_m(const double (&y)[D], const d
 template <int CLS>
 struct Prim {
   static constexpr int NE = Cls<CLS>::NE, NV = 4 + Cls<CLS>::NE, D = Cls<CLS>::D, DD = (Cls<CLS>::D > 0 ? Cls<CLS>::D : 1);
-  // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes); elsewhere code size wins
+  // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes); elsewhere code size wins.
+  // The once-per-pair row loops (initial point, hand-over records, derivative epilogue) are never unrolled: the
+  // compiler's default (x4) made the code ahead of the main loop 40 KB, which the other CTA of the SM pays for in
+  // instruction-cache misses on its loop body.
 #ifndef DCOL_ROW_UNROLL_SMALL
 #define DCOL_ROW_UNROLL_SMALL 1
 #endif
@@ -262,6 +265,7 @@ struct Prim {
     for (int a = 0; a < NV; a++) { g[a] = 0.0;
 #pragma unroll
       for (int b = a; b < NV; b++) N[a][b] = 0.0; }
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
@@ -288,6 +292,7 @@ struct Prim {
   // s~ = -u(yh), z~ = C*dh ; returns the bring2cone violations (static_solver2.jl:52-85)
   __device__ __forceinline__ void init_rows(const RowStore& rs, const double (&yh)[NV], const double (&dh)[NV],
                                             double& min_s, double& min_z, double& a_s, double& a_z) {
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       double us = 0.0, uz = 0.0;
 #pragma unroll
@@ -311,6 +316,7 @@ struct Prim {
   }
   __device__ __forceinline__ double init_shift(const RowStore& rs, double sh_s, double sh_z) {   // + (1+a)*e ; returns s.z
     double sz = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       double a = rs(F_S, row0 + i) + sh_s, b = rs(F_Z, row0 + i) + sh_z;
       rs(F_S, row0 + i) = a; rs(F_Z, row0 + i) = b; sz += a * b;
@@ -551,6 +557,7 @@ struct Prim {
     double w[NV];
 #pragma unroll
     for (int a = 0; a < NV; a++) w[a] = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       double zi = rs(F_Z, row0 + i);
 #pragma unroll
@@ -575,6 +582,7 @@ struct Prim {
     for (int a = 0; a < NV; a++)
 #pragma unroll
       for (int b = 0; b < NV; b++) Nf[a][b] = 0.0;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       double c[NV];
 #pragma unroll
@@ -798,6 +806,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     for (int a = 0; a < NX; a++) y[a] = rec[(f + a) * st];
     f += NX;
     const int nr = A.n + B.n;
+#pragma unroll 1
     for (int i = 0; i < nr; i++) { rs(F_S, i) = rec[(f + i) * st]; rs(F_Z, i) = rec[(f + nr + i) * st]; }
     f += 2 * nr;
     if constexpr (P1::D > 0) {
@@ -841,6 +850,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
         for (int a = 0; a < NX; a++) rec[(f + a) * st] = y[a];
         f += NX;
         const int nr = A.n + B.n;
+#pragma unroll 1
         for (int i = 0; i < nr; i++) { rec[(f + i) * st] = rs(F_S, i); rec[(f + nr + i) * st] = rs(F_Z, i); }
         f += 2 * nr;
         if constexpr (P1::D > 0) {

@@ -798,25 +798,30 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     if (!ok) status = ST_NUMERICAL;
   } else {
     // ---------------- resume: reload the iterate parked by the first pass ----------------
-    const double* rec = tc.in + idx;
+    // record layout (field-major, stride = the bin's record capacity): pair, k, s.z, y[NX], rows s, rows z, SOC s|z of
+    // prim 1, SOC s|z of prim 2; read with one walking pointer (no per-field 64-bit index arithmetic)
     const int64_t st = tc.in_cap;
-    k0 = (int)rec[1 * st]; sz = rec[2 * st];
-    int f = 3;
+    const double* q = tc.in + idx + st;
+    k0 = (int)q[0]; q += st;
+    sz = q[0]; q += st;
 #pragma unroll
-    for (int a = 0; a < NX; a++) y[a] = rec[(f + a) * st];
-    f += NX;
+    for (int a = 0; a < NX; a++) { y[a] = q[0]; q += st; }
     const int nr = A.n + B.n;
 #pragma unroll 1
-    for (int i = 0; i < nr; i++) { rs(F_S, i) = rec[(f + i) * st]; rs(F_Z, i) = rec[(f + nr + i) * st]; }
-    f += 2 * nr;
+    for (int i = 0; i < nr; i++) { rs(F_S, i) = q[0]; q += st; }
+#pragma unroll 1
+    for (int i = 0; i < nr; i++) { rs(F_Z, i) = q[0]; q += st; }
     if constexpr (P1::D > 0) {
 #pragma unroll
-      for (int i = 0; i < P1::D; i++) { A.s[i] = rec[(f + i) * st]; A.z[i] = rec[(f + P1::D + i) * st]; }
-      f += 2 * P1::D;
+      for (int i = 0; i < P1::D; i++) { A.s[i] = q[0]; q += st; }
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { A.z[i] = q[0]; q += st; }
     }
     if constexpr (P2::D > 0) {
 #pragma unroll
-      for (int i = 0; i < P2::D; i++) { B.s[i] = rec[(f + i) * st]; B.z[i] = rec[(f + P2::D + i) * st]; }
+      for (int i = 0; i < P2::D; i++) { B.s[i] = q[0]; q += st; }
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { B.z[i] = q[0]; q += st; }
     }
   }
 
@@ -842,25 +847,29 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
       // (and its idle lanes) in the loop until the slowest pair converges
       if (active) {
         const int slot = atomicAdd(tc.ov_count, 1);
-        double* rec = tc.ov + slot;
         const int64_t st = tc.ov_cap;
-        rec[0] = (double)pair; rec[1 * st] = (double)k; rec[2 * st] = sz;
-        int f = 3;
+        double* q = tc.ov + slot;
+        q[0] = (double)pair; q += st;
+        q[0] = (double)k; q += st;
+        q[0] = sz; q += st;
 #pragma unroll
-        for (int a = 0; a < NX; a++) rec[(f + a) * st] = y[a];
-        f += NX;
+        for (int a = 0; a < NX; a++) { q[0] = y[a]; q += st; }
         const int nr = A.n + B.n;
 #pragma unroll 1
-        for (int i = 0; i < nr; i++) { rec[(f + i) * st] = rs(F_S, i); rec[(f + nr + i) * st] = rs(F_Z, i); }
-        f += 2 * nr;
+        for (int i = 0; i < nr; i++) { q[0] = rs(F_S, i); q += st; }
+#pragma unroll 1
+        for (int i = 0; i < nr; i++) { q[0] = rs(F_Z, i); q += st; }
         if constexpr (P1::D > 0) {
 #pragma unroll
-          for (int i = 0; i < P1::D; i++) { rec[(f + i) * st] = A.s[i]; rec[(f + P1::D + i) * st] = A.z[i]; }
-          f += 2 * P1::D;
+          for (int i = 0; i < P1::D; i++) { q[0] = A.s[i]; q += st; }
+#pragma unroll
+          for (int i = 0; i < P1::D; i++) { q[0] = A.z[i]; q += st; }
         }
         if constexpr (P2::D > 0) {
 #pragma unroll
-          for (int i = 0; i < P2::D; i++) { rec[(f + i) * st] = B.s[i]; rec[(f + P2::D + i) * st] = B.z[i]; }
+          for (int i = 0; i < P2::D; i++) { q[0] = B.s[i]; q += st; }
+#pragma unroll
+          for (int i = 0; i < P2::D; i++) { q[0] = B.z[i]; q += st; }
         }
         parked = true;
       }

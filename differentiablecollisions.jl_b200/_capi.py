@@ -38,6 +38,8 @@ SYMBOLS = {
     "dcol_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcol_scene_wrench": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "dcol_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcol_launch_count": (C.c_int64, [C.c_void_p]),

@@ -238,6 +238,27 @@ class Context:
                                                   MEM_HOST, _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
         return self._finish(out, kind, x, deriv)
 
+    def scene_wrench(self, shape, r, att, lam, att_kind=ATT_QUAT, pdip_tol=1e-6, per_pair=True):
+        """`dcol_scene_wrench`: alpha of all i<j pairs and, per body, sum_k lam[k] * [d alpha_k/d r_b ; G(q_b)' d alpha_k/d q_b]
+        (the accumulation loop of examples/contact_physics/ncp_contact_simulation.jl:133-139); the gradient rows stay on
+        the device.  per_pair=False skips the alpha / status / iters arrays."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(-1)
+        nb = shape.shape[0]
+        na = 4 if att_kind == ATT_QUAT else 3
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(nb, 3); att = np.ascontiguousarray(att, dtype=np.float64).reshape(nb, na)
+        n = int(self._lib.dcol_scene_pair_count(nb))
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1)
+        if lam.shape[0] != n:
+            raise ValueError(f"scene_wrench: lam must have one entry per pair ({n})")
+        out = {"wrench": np.empty((nb, 6))}
+        if per_pair:
+            out.update(alpha=np.empty(n), status=np.empty(n, dtype=np.int32), iters=np.empty(n, dtype=np.int32))
+        self._check(self._lib.dcol_scene_wrench(self._h, nb, _ptr(shape), _ptr(r), _ptr(att), _ptr(lam), int(att_kind), float(pdip_tol),
+                                                MEM_HOST, _ptr(out.get("alpha")), _ptr(out["wrench"]), _ptr(out.get("status")), _ptr(out.get("iters"))))
+        return out
+
     def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
         return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 

@@ -80,7 +80,7 @@ struct dcol_ctx {
   };
   Slot slots[N_SLOTS];
   int next_ticket = 0;
-  DevBuf d_scene, d_pairs, d_plan;
+  DevBuf d_scene, d_pairs, d_plan, d_wrench;
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   int n_sm = 148;
   int64_t launches = 0;
@@ -258,6 +258,54 @@ __global__ void k_allpairs(int n_bodies, int64_t n_pairs, const int32_t* __restr
   }
 }
 
+// Per-body accumulation of the weighted pair gradients of an all-pairs scene (the loop of
+// examples/contact_physics/ncp_contact_simulation.jl:133-139):  out[b] = sum over pairs k containing body b of
+// lambda[k] * [ d alpha_k / d r_b ; P(att_b)' d alpha_k / d att_b ],  P = G(q) = L(q) H for quaternions
+// (variational_utils.jl:24-26), identity for MRPs.  One block per body, no atomics: the pairs (b, j), j > b are the
+// contiguous run starting at k_b = b(2N-b-1)/2 (body b is side 1), the pairs (i, b), i < b sit at k_i + (b-i-1)
+// (body b is side 2).  Fixed summation order, so the result is reproducible.
+__global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, const double* __restrict__ lambda,
+                               const double* __restrict__ att, int att_kind, double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int na = (att_kind == 0) ? 4 : 3, nt = 6 + 2 * na, ns = 3 + na;
+  const int64_t N = n_bodies;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int j = threadIdx.x; j < n_bodies; j += blockDim.x) {
+    if (j == b) continue;
+    int64_t k; int side;
+    if (j > b) { k = (int64_t)b * (2 * N - b - 1) / 2 + (j - b - 1); side = 0; }
+    else       { k = (int64_t)j * (2 * N - j - 1) / 2 + (b - j - 1); side = 1; }
+    const double w = lambda[k];
+    const double* g = grad + k * nt + side * ns;
+    for (int a = 0; a < ns; a++) acc[a] += w * g[a];
+  }
+  __shared__ double red[7][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int a = 0; a < 7; a++) {
+    double v = acc[a];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[a][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[7];
+    for (int a = 0; a < 7; a++) { double v = 0.0; for (int w = 0; w < nw; w++) v += red[a][w]; t[a] = v; }
+    double* o = out + 6 * (int64_t)b;
+    o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+    if (att_kind == 0) {
+      // G(q)' g = -v g0 + s gv - v x gv   (q = [s; v], g = [g0; gv])
+      const double* q = att + 4 * (int64_t)b;
+      const double s0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+      const double g0 = t[3], g1 = t[4], g2 = t[5], g3 = t[6];
+      o[3] = -v1 * g0 + s0 * g1 - (v2 * g3 - v3 * g2);
+      o[4] = -v2 * g0 + s0 * g2 - (v3 * g1 - v1 * g3);
+      o[5] = -v3 * g0 + s0 * g3 - (v1 * g2 - v2 * g1);
+    } else {
+      o[3] = t[3]; o[4] = t[4]; o[5] = t[5];
+    }
+  }
+}
+
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -335,7 +383,7 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_scene, &ctx->d_pairs, &ctx->d_plan};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_scene, &ctx->d_pairs, &ctx->d_plan, &ctx->d_wrench};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   for (int k = 0; k < dcol_ctx::N_SLOTS; k++) {
@@ -917,6 +965,74 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
                    p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE);
 }
 
+
+int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const double* r, const double* att, const double* lambda,
+                      int att_kind, double pdip_tol, int mem,
+                      double* alpha, double* wrench, int32_t* status, int32_t* iters) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  if (n_bodies < 0 || !shape || !r || !att || !lambda || !wrench) { ctx->err = "dcol_scene_wrench: bad arguments"; return -1; }
+  if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { ctx->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
+  if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
+  const int64_t np = dcol_scene_pair_count(n_bodies);
+  if (np > 0x7fffffff) { ctx->err = "dcol_scene_wrench: too many pairs for one call"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t S = ctx->stream();
+  const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3, nt = 6 + 2 * na;
+  if (np == 0) {
+    if (n_bodies > 0) {
+      if (mem == DCOL_MEM_HOST) memset(wrench, 0, sizeof(double) * 6 * n_bodies);
+      else { CK(cudaMemsetAsync(wrench, 0, sizeof(double) * 6 * n_bodies, S)); CK(cudaStreamSynchronize(S)); }
+    }
+    return 0;
+  }
+  // per-pair results stay on the device: gradient rows always; alpha / status / iters too when the caller's are host memory
+  const size_t w0 = align256(sizeof(double) * nt * (size_t)np), w1 = align256(sizeof(double) * (size_t)np),
+               w2 = align256(sizeof(int32_t) * (size_t)np), w3 = align256(sizeof(double) * 6 * (size_t)n_bodies);
+  CK(ctx->d_wrench.need(w0 + 2 * w1 + 2 * w2 + w3));
+  char* wb = (char*)ctx->d_wrench.p;
+  double* d_grad = (double*)wb;
+  double* d_lambda = (double*)(wb + w0);
+  double* d_alpha = (double*)(wb + w0 + w1);
+  int32_t* d_status = (int32_t*)(wb + w0 + 2 * w1);
+  int32_t* d_iters = (int32_t*)(wb + w0 + 2 * w1 + w2);
+  double* d_out = (double*)(wb + w0 + 2 * w1 + 2 * w2);
+  const int32_t* d_shape = shape; const double* d_r = r; const double* d_att = att; const double* d_lam = lambda;
+  if (mem == DCOL_MEM_HOST) {
+    size_t b0 = align256(sizeof(int32_t) * n_bodies), b1 = align256(sizeof(double) * 3 * n_bodies), b2 = align256(sizeof(double) * na * n_bodies);
+    CK(ctx->d_scene.need(b0 + b1 + b2));
+    char* d = (char*)ctx->d_scene.p;
+    CK(cudaMemcpyAsync(d, shape, sizeof(int32_t) * n_bodies, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0, r, sizeof(double) * 3 * n_bodies, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0 + b1, att, sizeof(double) * na * n_bodies, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d_lambda, lambda, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, S));
+    d_shape = (const int32_t*)d; d_r = (const double*)(d + b0); d_att = (const double*)(d + b0 + b1); d_lam = d_lambda;
+  }
+  CK(ctx->d_pairs.need(sizeof(int32_t) * 4 * (size_t)np));
+  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* p1 = s2 + np; int32_t* p2 = p1 + np;
+  k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  const bool host = (mem == DCOL_MEM_HOST);
+  double* q_alpha = (host || !alpha) ? d_alpha : alpha;
+  int32_t* q_status = host ? (status ? d_status : nullptr) : status;
+  int32_t* q_iters = host ? (iters ? d_iters : nullptr) : iters;
+  int rc = run_query(ctx, Q_GRAD, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE,
+                     q_alpha, nullptr, d_grad, q_status, q_iters, p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE);
+  if (rc) return rc;
+  double* o = host ? d_out : wrench;
+  k_scene_wrench<<<n_bodies, 128, 0, S>>>(n_bodies, d_grad, d_lam, d_att, att_kind, o);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (host) {
+    CK(cudaMemcpyAsync(wrench, d_out, sizeof(double) * 6 * n_bodies, cudaMemcpyDeviceToHost, S));
+    if (alpha) CK(cudaMemcpyAsync(alpha, d_alpha, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
+    if (status) CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+    if (iters) CK(cudaMemcpyAsync(iters, d_iters, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+  }
+  CK(cudaStreamSynchronize(S));
+  return 0;
+}
 
 // ---- asynchronous submissions (host buffers): up to three in flight; inputs of submission k+1 cross PCIe while
 // submission k computes and submission k-1's results go back

@@ -126,6 +126,20 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
                         int att_kind, double pdip_tol, int mem,
                         double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
 
+/* Contact-scene accumulation: the loop of examples/contact_physics/ncp_contact_simulation.jl:133-139 as one call.  For
+ * all pairs k = (i, j), i < j (order as above) with weights lambda[k] (the contact impulses of the caller's NCP):
+ *     alpha[k]  = proximity_gradient(P_i, P_j)[1]
+ *     wrench[b] = sum over pairs k containing body b of lambda[k] * [ d alpha_k / d r_b ; P(att_b)' d alpha_k / d att_b ]
+ * with P = G(q) = L(q) H, the 4 x 3 attitude Jacobian of examples/contact_physics/variational_utils.jl:24-26, for
+ * quaternions (att_kind 0) and the identity for MRPs (att_kind 1): 6 numbers per body, the generalised force the
+ * example adds to each body's discrete Euler-Lagrange residual (before its constant factors h and tau_mod).  The
+ * n_pairs x 14 gradient rows never leave the device (config 4: 0.94 GB that the per-pair form returns to the host).
+ * lambda f64[n_pairs]; wrench f64[n_bodies*6]; alpha, status, iters [n_pairs], each may be NULL.  Pairs that fail
+ * (status != 0) contribute NaN, as the reference would throw. */
+int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const double* r, const double* att, const double* lambda,
+                      int att_kind, double pdip_tol, int mem,
+                      double* alpha, double* wrench, int32_t* status, int32_t* iters);
+
 /* ---- asynchronous submissions (host buffers) -------------------------------------------------------------
  * dcol_submit enqueues one query (query: 0 proximity, 1 gradient, 2 jacobian; buffers as in the synchronous
  * calls, all HOST memory, pinned for the copies to overlap) and returns a ticket >= 0 without waiting; dcol_wait

@@ -274,6 +274,28 @@ function scene_allpairs(kind::Integer, shape::Vector{Int32}, r::Matrix{Float64},
 end
 
 """
+    scene_wrench(shape, r, att, λ; pdip_tol) -> (α, wrench, status, iters)
+
+The accumulation loop of the contact example (`DELs[i] += E[1:6]; DELs[j] += E[7:12]` over all pairs, without its
+constant factors `h * τ_mod`) as one call: `wrench[:, b] = Σ_k λ[k] * [∂α_k/∂r_b ; G(q_b)' ∂α_k/∂q_b]` over the pairs `k`
+containing body `b`, `G(q) = L(q) * H`; for MRP attitudes the attitude part is the plain sum of `∂α_k/∂p_b`.
+`λ` has one entry per pair in `combinations(1:N,2)` order.  The per-pair gradient rows stay on the GPU.
+"""
+function scene_wrench(shape::Vector{Int32}, r::Matrix{Float64}, att::Matrix{Float64}, λ::Vector{Float64}; pdip_tol = 1e-6)
+    nb = length(shape); na = size(att, 1)
+    n = Int(ccall((:dcol_scene_pair_count, _lib[]), Int64, (Cint,), nb))
+    length(λ) == n || error("scene_wrench: λ must have one entry per pair ($n)")
+    α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
+    wrench = Matrix{Float64}(undef, 6, nb)
+    _check(ccall((:dcol_scene_wrench, _lib[]), Cint,
+                 (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
+                  Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                 _ctx[], nb, shape, r, att, λ, na == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol), MEM_HOST,
+                 α, wrench, status, iters))
+    return α, wrench, status, iters
+end
+
+"""
     query_indexed(kind, shape1, shape2, pose1, pose2, r1, att1, r2, att2; pdip_tol) -> BatchResult
 
 Pose-table query: pair k uses column `pose1[k]+1` of `(r1, att1)` and `pose2[k]+1` of `(r2, att2)` (0-based indices, as in C).

@@ -38,6 +38,11 @@ ctx.set_shape_arrays(*t.arrays())
 w, k, o = timed(lambda: ctx.scene_allpairs(1, shape, r, att, 0), 2)
 npairs = nb * (nb - 1) // 2
 print(f"config 4  4096-body scene, {npairs} gradient pairs:  call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {npairs/w/1e6:8.2f} Mpairs/s  (collisions {int((o['alpha'] <= 1).sum())})")
+lam = util.rng(5).uniform(0.0, 1.0, npairs)
+w2, k2, o2 = timed(lambda: ctx.scene_wrench(shape, r, att, lam, 0, per_pair=False), 2)
+print(f"config 4f same scene through dcol_scene_wrench (per-body sums only): call {w2*1e3:8.3f} ms  {npairs/w2/1e6:8.2f} Mpairs/s")
+w3, k3, o3 = timed(lambda: ctx.scene_wrench(shape, r, att, lam, 0, per_pair=True), 2)
+print(f"config 4f same, alpha/status/iters per pair returned as well:        call {w3*1e3:8.3f} ms  {npairs/w3/1e6:8.2f} Mpairs/s")
 # 5: piano mover batch: 1024 rollouts x 100 knots x 3 obstacles, jacobian, MRP p = (0,0,tan(theta/4))
 B, N, K = 1024, 100, 3
 veh = dc.create_rect_prism(2.5, 0.15, 0.01)[0]

@@ -117,3 +117,82 @@ def test_config4_full_size_scene(ctx):
     assert np.array_equal(s["alpha"][k], e["alpha"]) and np.array_equal(s["grad"][k], e["grad"], equal_nan=True)
     tq = np.einsum("nj,nj->n", s["grad"][k, 3:7], att[i])
     assert np.abs(tq[e["status"] == 0]).max() < 1e-8 * max(1.0, np.abs(e["grad"]).max())
+
+
+def wrench_reference(grad, lam, att, ij, att_kind):
+    """The accumulation of examples/contact_physics/ncp_contact_simulation.jl:133-139 written as the example writes it
+    (dense Gbar = blockdiag(I3, G(q_i), I3, G(q_j)), G = L(q) H from variational_utils.jl:1-26), per pair, in float64."""
+    nb = att.shape[0]
+    out = np.zeros((nb, 6))
+
+    def hat(w):
+        return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+
+    def G(q):
+        L = np.zeros((4, 4)); L[0, 0] = q[0]; L[0, 1:] = -q[1:]; L[1:, 0] = q[1:]; L[1:, 1:] = q[0] * np.eye(3) + hat(q[1:])
+        H = np.vstack([np.zeros((1, 3)), np.eye(3)])
+        return L @ H
+    for k, (i, j) in enumerate(ij):
+        if att_kind == dc.ATT_QUAT:
+            Gbar = np.zeros((14, 12)); Gbar[0:3, 0:3] = np.eye(3); Gbar[3:7, 3:6] = G(att[i]); Gbar[7:10, 6:9] = np.eye(3); Gbar[10:14, 9:12] = G(att[j])
+            E = (grad[k][None, :] @ Gbar).T[:, 0] * lam[k]
+        else:
+            E = grad[k] * lam[k]
+        out[i] += E[:6]; out[j] += E[6:]
+    return out
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+def test_scene_wrench_matches_per_pair_accumulation(ctx, oracle, att_kind):
+    """dcol_scene_wrench against (a) the same accumulation done on the host from dcol_scene_allpairs' gradient rows and
+    (b) the oracle's gradients pushed through the example's dense formula."""
+    nb = 47
+    t, shape, r, att = scene_bodies(nb, att_kind, spread=2.0)
+    ctx.set_shape_arrays(*t.arrays())
+    ij = np.array(list(itertools.combinations(range(nb), 2)))
+    lam = util.rng(11).uniform(0.0, 2.0, len(ij))
+    w = ctx.scene_wrench(shape, r, att, lam, att_kind)
+    s = ctx.scene_allpairs(1, shape, r, att, att_kind)
+    assert np.array_equal(w["alpha"], s["alpha"]) and np.array_equal(w["status"], s["status"]) and np.array_equal(w["iters"], s["iters"])
+    assert (s["status"] == 0).all()
+    ref = wrench_reference(s["grad"], lam, att, ij, att_kind)
+    scale = np.abs(ref).max()
+    assert np.abs(w["wrench"] - ref).max() < 1e-12 * scale            # same gradients, different summation order
+    o = oracle.query(1, t.arrays(), shape[ij[:, 0]], shape[ij[:, 1]], r[ij[:, 0]], att[ij[:, 0]], r[ij[:, 1]], att[ij[:, 1]], att_kind, 1e-6)
+    ref_o = wrench_reference(o["grad"], lam, att, ij, att_kind)
+    assert np.abs(w["wrench"] - ref_o).max() < 1e-5 * scale
+    w2 = ctx.scene_wrench(shape, r, att, lam, att_kind, per_pair=False)          # NULL per-pair outputs
+    assert np.array_equal(w2["wrench"], w["wrench"]) and "alpha" not in w2
+    # degenerate scenes
+    one = ctx.scene_wrench(shape[:1], r[:1], att[:1], np.zeros(0), att_kind)
+    assert one["wrench"].shape == (1, 6) and (one["wrench"] == 0).all()
+    with pytest.raises(ValueError):
+        ctx.scene_wrench(shape, r, att, lam[:-1], att_kind)
+
+
+def test_scene_wrench_config4_size(ctx):
+    """BASELINE config 4 (4096 bodies, 8 386 560 pairs) through the fused operator: finite, and equal to the accumulation
+    of the per-pair rows on a sample of bodies."""
+    nb = 4096
+    t, shape, r, att = scene_bodies(nb, 0, spread=30.0)
+    ctx.set_shape_arrays(*t.arrays())
+    n = nb * (nb - 1) // 2
+    lam = util.rng(5).uniform(0.0, 1.0, n)
+    w = ctx.scene_wrench(shape, r, att, lam, 0, per_pair=True)
+    assert (w["status"] == 0).mean() > 0.9999
+    ok_body = np.isfinite(w["wrench"]).all(axis=1)
+    assert ok_body.mean() > 0.99
+    s = ctx.scene_allpairs(1, shape, r, att, 0)
+    assert np.array_equal(s["alpha"], w["alpha"])
+    k_of = lambda i, j: i * (2 * nb - i - 1) // 2 + (j - i - 1)
+    for b in (0, 1, 2047, 4095):
+        acc = np.zeros(7)
+        for j in range(nb):
+            if j == b:
+                continue
+            k = k_of(b, j) if j > b else k_of(j, b)
+            acc += lam[k] * (s["grad"][k, :7] if j > b else s["grad"][k, 7:])
+        q = att[b]; g0, gv = acc[3], acc[4:7]
+        ref = np.concatenate([acc[:3], -q[1:] * g0 + q[0] * gv - np.cross(q[1:], gv)])
+        if np.isfinite(ref).all():
+            assert np.abs(w["wrench"][b] - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())

@@ -40,6 +40,8 @@ SYMBOLS = {
     "dcol_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "dcol_scene_wrench": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_se2_constraints": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "dcol_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcol_launch_count": (C.c_int64, [C.c_void_p]),

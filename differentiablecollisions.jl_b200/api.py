@@ -259,6 +259,20 @@ class Context:
                                                 MEM_HOST, _ptr(out.get("alpha")), _ptr(out["wrench"]), _ptr(out.get("status")), _ptr(out.get("iters"))))
         return out
 
+    def se2_constraints(self, xytheta, vehicle_shape, obs_shape, r_obs, p_obs, pdip_tol=1e-6):
+        """`dcol_se2_constraints`: `ineq_con_x` / `ineq_con_x_jac` of examples/trajectory_optimization/piano_mover.jl:39-53 for a
+        batch of planar states (x, y, theta) against K obstacles: c = 1 - alpha (n, K) and dc/d(x, y, theta) (n, K, 3)."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        xyt = np.ascontiguousarray(xytheta, dtype=np.float64).reshape(-1, 3)
+        obs_shape = np.ascontiguousarray(obs_shape, dtype=np.int32).reshape(-1)
+        K = obs_shape.shape[0]; n = xyt.shape[0]
+        r_obs = np.ascontiguousarray(r_obs, dtype=np.float64).reshape(K, 3); p_obs = np.ascontiguousarray(p_obs, dtype=np.float64).reshape(K, 3)
+        c = np.empty((n, K)); Jc = np.empty((n, K, 3)); status = np.empty((n, K), dtype=np.int32)
+        self._check(self._lib.dcol_se2_constraints(self._h, n, _ptr(xyt), int(vehicle_shape), K, _ptr(obs_shape), _ptr(r_obs), _ptr(p_obs),
+                                                   float(pdip_tol), MEM_HOST, _ptr(c), _ptr(Jc), _ptr(status)))
+        return {"c": c, "Jc": Jc, "status": status}
+
     def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
         return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 

@@ -306,6 +306,33 @@ __global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, co
   }
 }
 
+// Planar vehicle against static obstacles (examples/trajectory_optimization/piano_mover.jl:39-53): state (x, y, theta)
+// -> pose r = (x, y, 0), MRP p = (0, 0, tan(theta/4)); pair k = state * n_obs + obstacle.
+__global__ void k_se2_pairs(int64_t n_states, int n_obs, const double* __restrict__ xyt, int32_t vehicle, const int32_t* __restrict__ obs_shape,
+                            double* __restrict__ r1, double* __restrict__ p1,
+                            int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ i1, int32_t* __restrict__ i2) {
+  const int64_t np = n_states * n_obs;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = k / n_obs; const int o = (int)(k - s * n_obs);
+    s1[k] = vehicle; s2[k] = obs_shape[o]; i1[k] = (int32_t)s; i2[k] = o;
+    if (o == 0) {
+      r1[3 * s] = xyt[3 * s]; r1[3 * s + 1] = xyt[3 * s + 1]; r1[3 * s + 2] = 0.0;
+      p1[3 * s] = 0.0; p1[3 * s + 1] = 0.0; p1[3 * s + 2] = tan(0.25 * xyt[3 * s + 2]);
+    }
+  }
+}
+// c = 1 - alpha ; dc/d(x, y, theta) = (-da/dr1_x, -da/dr1_y, -da/dp1_z / (4 cos^2(theta/4)))   (piano_mover.jl:45-52)
+__global__ void k_se2_rows(int64_t np, int n_obs, const double* __restrict__ xyt, const double* __restrict__ alpha,
+                           const double* __restrict__ grad, double* __restrict__ c, double* __restrict__ Jc) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = k / n_obs;
+    const double ct = cos(0.25 * xyt[3 * s + 2]);
+    const double* g = grad + 12 * k;
+    c[k] = 1.0 - alpha[k];
+    Jc[3 * k] = -g[0]; Jc[3 * k + 1] = -g[1]; Jc[3 * k + 2] = -g[5] / (4.0 * ct * ct);
+  }
+}
+
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1029,6 +1056,68 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
     if (alpha) CK(cudaMemcpyAsync(alpha, d_alpha, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
     if (status) CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
     if (iters) CK(cudaMemcpyAsync(iters, d_iters, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+  }
+  CK(cudaStreamSynchronize(S));
+  return 0;
+}
+
+int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta, int32_t vehicle_shape,
+                         int n_obs, const int32_t* obs_shape, const double* r_obs, const double* p_obs,
+                         double pdip_tol, int mem, double* c, double* Jc, int32_t* status) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  if (n_states < 0 || n_obs < 0 || !xytheta || !obs_shape || !r_obs || !p_obs || !c) { ctx->err = "dcol_se2_constraints: bad arguments"; return -1; }
+  if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
+  const int64_t np = n_states * (int64_t)n_obs;
+  if (np == 0) return 0;
+  if (np > 0x7fffffff) { ctx->err = "dcol_se2_constraints: too many pairs for one call"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t S = ctx->stream();
+  const bool host = (mem == DCOL_MEM_HOST);
+  // device scratch: gradient rows | alpha | status | vehicle poses | (host mode) states, c, Jc
+  const size_t w0 = align256(sizeof(double) * 12 * (size_t)np), w1 = align256(sizeof(double) * (size_t)np),
+               w2 = align256(sizeof(int32_t) * (size_t)np), w3 = align256(sizeof(double) * 3 * (size_t)n_states),
+               w4 = align256(sizeof(double) * 3 * (size_t)np);
+  CK(ctx->d_wrench.need(w0 + 2 * w1 + w2 + 3 * w3 + w4));
+  char* wb = (char*)ctx->d_wrench.p;
+  double* d_grad = (double*)wb;
+  double* d_alpha = (double*)(wb + w0);
+  double* d_c = (double*)(wb + w0 + w1);
+  int32_t* d_status = (int32_t*)(wb + w0 + 2 * w1);
+  double* d_r1 = (double*)(wb + w0 + 2 * w1 + w2);
+  double* d_p1 = (double*)(wb + w0 + 2 * w1 + w2 + w3);
+  double* d_xyt = (double*)(wb + w0 + 2 * w1 + w2 + 2 * w3);
+  double* d_J = (double*)(wb + w0 + 2 * w1 + w2 + 3 * w3);
+  const double* x_dev = xytheta; const int32_t* os_dev = obs_shape; const double* ro_dev = r_obs; const double* po_dev = p_obs;
+  if (host) {
+    size_t b0 = align256(sizeof(int32_t) * n_obs), b1 = align256(sizeof(double) * 3 * n_obs);
+    CK(ctx->d_scene.need(b0 + 2 * b1));
+    char* d = (char*)ctx->d_scene.p;
+    CK(cudaMemcpyAsync(d, obs_shape, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0, r_obs, sizeof(double) * 3 * n_obs, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0 + b1, p_obs, sizeof(double) * 3 * n_obs, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d_xyt, xytheta, sizeof(double) * 3 * (size_t)n_states, cudaMemcpyHostToDevice, S));
+    os_dev = (const int32_t*)d; ro_dev = (const double*)(d + b0); po_dev = (const double*)(d + b0 + b1); x_dev = d_xyt;
+  }
+  CK(ctx->d_pairs.need(sizeof(int32_t) * 4 * (size_t)np));
+  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* i1 = s2 + np; int32_t* i2 = i1 + np;
+  const int blocks = (int)std::min<int64_t>((np + 255) / 256, 148 * 16);
+  k_se2_pairs<<<blocks, 256, 0, S>>>(n_states, n_obs, x_dev, vehicle_shape, os_dev, d_r1, d_p1, s1, s2, i1, i2);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  int32_t* q_status = host ? (status ? d_status : nullptr) : status;
+  int rc = run_query(ctx, Q_GRAD, np, s1, s2, d_r1, d_p1, ro_dev, po_dev, DCOL_ATT_MRP, pdip_tol, DCOL_MEM_DEVICE,
+                     d_alpha, nullptr, d_grad, q_status, nullptr, i1, i2, n_states, n_obs, DCOL_MEM_DEVICE);
+  if (rc) return rc;
+  double* o_c = host ? d_c : c;
+  double* o_J = (host || !Jc) ? d_J : Jc;
+  k_se2_rows<<<blocks, 256, 0, S>>>(np, n_obs, x_dev, d_alpha, d_grad, o_c, o_J);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (host) {
+    CK(cudaMemcpyAsync(c, d_c, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
+    if (Jc) CK(cudaMemcpyAsync(Jc, d_J, sizeof(double) * 3 * (size_t)np, cudaMemcpyDeviceToHost, S));
+    if (status) CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
   }
   CK(cudaStreamSynchronize(S));
   return 0;

@@ -140,6 +140,20 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
                       int att_kind, double pdip_tol, int mem,
                       double* alpha, double* wrench, int32_t* status, int32_t* iters);
 
+/* Planar vehicle against static obstacles: the constraint functions of the trajectory-optimisation examples
+ * (examples/trajectory_optimization/piano_mover.jl:39-53, ineq_con_x / ineq_con_x_jac) for a batch of states.  Every state
+ * s = (x, y, theta) puts the vehicle shape at r = (x, y, 0) with MRP p = (0, 0, tan(theta/4)); for every obstacle o
+ * (shape ids obs_shape[n_obs], poses r_obs / p_obs [n_obs*3], MRP):
+ *     c [s*n_obs + o]        = 1 - alpha(vehicle(s), obstacle o)
+ *     Jc[(s*n_obs + o)*3 + m] = d c / d (x, y, theta)_m
+ *                             = (-d alpha/d r1_x, -d alpha/d r1_y, -(d alpha/d p1_z) / (4 cos^2(theta/4)))
+ * i.e. the non-zero columns 1, 2 and 5 of the example's constraint Jacobian rows.  The state -> pose map, the pair list
+ * and the chain rule run on the device around one proximity_gradient query.  xytheta f64[n_states*3]; c f64[n_states*n_obs];
+ * Jc f64[n_states*n_obs*3] (may be NULL); status int32[n_states*n_obs] (may be NULL; failed pairs give NaN in Jc). */
+int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta, int32_t vehicle_shape,
+                         int n_obs, const int32_t* obs_shape, const double* r_obs, const double* p_obs,
+                         double pdip_tol, int mem, double* c, double* Jc, int32_t* status);
+
 /* ---- asynchronous submissions (host buffers) -------------------------------------------------------------
  * dcol_submit enqueues one query (query: 0 proximity, 1 gradient, 2 jacobian; buffers as in the synchronous
  * calls, all HOST memory, pinned for the copies to overlap) and returns a ticket >= 0 without waiting; dcol_wait

@@ -296,6 +296,24 @@ function scene_wrench(shape::Vector{Int32}, r::Matrix{Float64}, att::Matrix{Floa
 end
 
 """
+    se2_constraints(xyθ, vehicle_shape, obs_shape, r_obs, p_obs; pdip_tol) -> (c, Jc, status)
+
+`ineq_con_x` / `ineq_con_x_jac` of the piano-mover example for a batch of planar states: column `s` of `xyθ` (3×n) puts
+the vehicle at `r = (x, y, 0)`, `p = (0, 0, tan(θ/4))`; `c[o, s] = 1 - α` against obstacle `o` and `Jc[:, o, s] = ∂c/∂(x, y, θ)`
+(columns 1, 2 and 5 of the example's Jacobian rows).  Shape ids are 0-based.
+"""
+function se2_constraints(xyθ::Matrix{Float64}, vehicle_shape::Integer, obs_shape::Vector{Int32}, r_obs::Matrix{Float64},
+                         p_obs::Matrix{Float64}; pdip_tol = 1e-6)
+    n = size(xyθ, 2); K = length(obs_shape)
+    c = Matrix{Float64}(undef, K, n); Jc = Array{Float64}(undef, 3, K, n); status = Matrix{Int32}(undef, K, n)
+    _check(ccall((:dcol_se2_constraints, _lib[]), Cint,
+                 (Ptr{Cvoid}, Int64, Ptr{Float64}, Int32, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                  Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                 _ctx[], n, xyθ, vehicle_shape, K, obs_shape, r_obs, p_obs, Float64(pdip_tol), MEM_HOST, c, Jc, status))
+    return c, Jc, status
+end
+
+"""
     query_indexed(kind, shape1, shape2, pose1, pose2, r1, att1, r2, att2; pdip_tol) -> BatchResult
 
 Pose-table query: pair k uses column `pose1[k]+1` of `(r1, att1)` and `pose2[k]+1` of `(r2, att2)` (0-based indices, as in C).

@@ -58,3 +58,6 @@ pose1 = np.repeat(np.arange(B * N, dtype=np.int32), K); pose2 = np.tile(np.arang
 s1 = np.full(B * N * K, sv, np.int32); s2 = np.array(so, np.int32)[pose2]
 w, k, o = timed(lambda: ctx.query_indexed(2, s1, s2, pose1, pose2, r1, p1, r2, p2, dc.ATT_MRP), 3)
 print(f"config 5  piano-mover batch, {B*N*K} box-box MRP jacobians: call {w*1e3:8.3f} ms  kernels {k:7.3f} ms  {B*N*K/w/1e6:8.2f} Mpairs/s  (failed {int((o['status'] != 0).sum())})")
+xyt = np.stack([r1[:, 0], r1[:, 1], theta], axis=1)
+w5, k5, o5 = timed(lambda: ctx.se2_constraints(xyt, sv, np.array(so, np.int32), r2, p2), 3)
+print(f"config 5f same batch through dcol_se2_constraints (c and dc/d(x,y,theta) per pair): call {w5*1e3:8.3f} ms  kernels {k5:7.3f} ms  {B*N*K/w5/1e6:8.2f} Mpairs/s")

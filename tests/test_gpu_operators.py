@@ -196,3 +196,54 @@ def test_scene_wrench_config4_size(ctx):
         ref = np.concatenate([acc[:3], -q[1:] * g0 + q[0] * gv - np.cross(q[1:], gv)])
         if np.isfinite(ref).all():
             assert np.abs(w["wrench"][b] - ref).max() < 1e-11 * max(1.0, np.abs(ref).max())
+
+
+def test_se2_constraints_match_the_example_formulas(ctx, oracle):
+    """dcol_se2_constraints against ineq_con_x / ineq_con_x_jac of piano_mover.jl:39-53 evaluated on the host from per-pair
+    proximity_gradient results (GPU and oracle), and against central finite differences of c in the state."""
+    n, K = 3000, 3
+    veh = dc.create_rect_prism(2.5, 0.15, 0.01)[0]
+    obs = [dc.create_rect_prism(3.0, 3.0, 1.0)[0], dc.create_rect_prism(4.0, 1.0, 1.0)[0], dc.create_rect_prism(1.0, 5.0, 1.1)[0]]   # :70-76
+    t = dc.ShapeTable()
+    sv = t.add(veh); so = np.array([t.add(o) for o in obs], np.int32)
+    ctx.set_shape_arrays(*t.arrays())
+    g = util.rng(23)
+    xyt = np.stack([g.uniform(-1, 6, n), g.uniform(-1, 6, n), g.uniform(-np.pi, np.pi, n)], axis=1)
+    r_obs = np.array([[1.5, 3.5, 0.0], [4.5, 1.5, 0.0], [5.0, 4.0, 0.0]]); p_obs = np.zeros((K, 3))
+    out = ctx.se2_constraints(xyt, sv, so, r_obs, p_obs)
+    assert out["c"].shape == (n, K) and out["Jc"].shape == (n, K, 3)
+
+    def example(query, X):
+        m = X.shape[0]
+        r1 = np.stack([X[:, 0], X[:, 1], np.zeros(m)], axis=1); p1 = np.stack([np.zeros(m), np.zeros(m), np.tan(X[:, 2] / 4)], axis=1)
+        i1 = np.repeat(np.arange(m), K); i2 = np.tile(np.arange(K), m)
+        res = query(np.full(m * K, sv, np.int32), so[i2], r1[i1], p1[i1], r_obs[i2], p_obs[i2])
+        dp = 1.0 / (4 * np.cos(X[i1, 2] / 4) ** 2)                                   # dp_dθ, :46
+        J = np.stack([-res["grad"][:, 0], -res["grad"][:, 1], -res["grad"][:, 5] * dp], axis=1)   # :50
+        return (1 - res["alpha"]).reshape(m, K), J.reshape(m, K, 3), res["status"].reshape(m, K)
+    c_g, J_g, st_g = example(lambda *a: ctx._batch(1, *a, dc.ATT_MRP, 1e-6), xyt)
+    # the device evaluates tan(theta/4) itself (CUDA libm vs numpy: last-bit differences in p), so agreement is to round-off
+    assert np.array_equal(out["status"], st_g)
+    assert np.abs(out["c"] - c_g).max() < 1e-9
+    okg = st_g == 0
+    eg = np.abs(out["Jc"] - J_g).max(axis=2)[okg] / np.maximum(1.0, np.abs(J_g).max(axis=2)[okg])
+    assert np.quantile(eg, 0.99) < 1e-8
+    c_o, J_o, st_o = example(lambda *a: oracle.query(1, t.arrays(), *a, dc.ATT_MRP, 1e-6), xyt)
+    ok = (st_o == 0) & (st_g == 0)
+    assert ok.mean() > 0.99 and (st_o == st_g).all()
+    assert np.abs(out["c"] - c_o)[ok].max() < 1e-6 * max(1.0, np.abs(c_o[ok]).max())
+    err = np.abs(out["Jc"] - J_o).max(axis=2)[ok] / np.maximum(1.0, np.abs(J_o).max(axis=2)[ok])
+    assert (err < 1e-5).mean() > 0.97                       # thin plates: degenerate face-parallel configurations in the tail
+    # finite differences of the constraint itself (tight tolerance so that the difference quotient is meaningful)
+    m = 200; eps = 1e-6
+    fd = np.zeros((m, K, 3))
+    for a in range(3):
+        d = np.zeros(3); d[a] = eps
+        cp = ctx.se2_constraints(xyt[:m] + d, sv, so, r_obs, p_obs, pdip_tol=1e-10)["c"]
+        cm = ctx.se2_constraints(xyt[:m] - d, sv, so, r_obs, p_obs, pdip_tol=1e-10)["c"]
+        fd[:, :, a] = (cp - cm) / (2 * eps)
+    Jt = ctx.se2_constraints(xyt[:m], sv, so, r_obs, p_obs, pdip_tol=1e-10)["Jc"]
+    e = np.abs(fd - Jt).max(axis=2) / np.maximum(1.0, np.abs(Jt).max(axis=2))
+    assert np.median(e) < 1e-5 and (e < 1e-3).mean() > 0.95    # kinks where the active face changes
+    empty = ctx.se2_constraints(np.zeros((0, 3)), sv, so, r_obs, p_obs)
+    assert empty["c"].shape == (0, K)

@@ -168,6 +168,9 @@ def test_scene_wrench_matches_per_pair_accumulation(ctx, oracle, att_kind):
     assert one["wrench"].shape == (1, 6) and (one["wrench"] == 0).all()
     with pytest.raises(ValueError):
         ctx.scene_wrench(shape, r, att, lam[:-1], att_kind)
+    bad = shape.copy(); bad[3] = 12345
+    with pytest.raises(RuntimeError, match="shape index out of range"):
+        ctx.scene_wrench(bad, r, att, lam, att_kind)
 
 
 def test_scene_wrench_config4_size(ctx):
@@ -247,3 +250,7 @@ def test_se2_constraints_match_the_example_formulas(ctx, oracle):
     assert np.median(e) < 1e-5 and (e < 1e-3).mean() > 0.95    # kinks where the active face changes
     empty = ctx.se2_constraints(np.zeros((0, 3)), sv, so, r_obs, p_obs)
     assert empty["c"].shape == (0, K)
+    with pytest.raises(RuntimeError, match="shape index out of range"):
+        ctx.se2_constraints(xyt[:10], 999, so, r_obs, p_obs)
+    again = ctx.se2_constraints(xyt[:10], sv, so, r_obs, p_obs)              # the context stays usable after an API error
+    assert np.array_equal(again["c"], out["c"][:10])

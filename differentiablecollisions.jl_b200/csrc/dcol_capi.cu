@@ -89,10 +89,14 @@ struct dcol_ctx {
 };
 
 // ---------------------------------------------------------------------------
-// binning kernels: counting sort of pair indices by (class1, class2[, shape1, shape2])
+// binning kernels: counting sort of pair indices by the UNORDERED class pair (lo, hi)[, then shape1, shape2]: a pair
+// whose classes arrive as (hi, lo) lands in the bin of (lo, hi) and is marked (bit 31 of its perm entry) so that the
+// solver exchanges its two primitives
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int pair_key(const int32_t* cls, const int32_t* keymap, int n_shapes, int s1, int s2) {
-  return keymap ? keymap[s1 * n_shapes + s2] : cls[s1] * NCLS + cls[s2];
+  if (keymap) return keymap[s1 * n_shapes + s2];
+  const int a = cls[s1], b = cls[s2];
+  return min(a, b) * NCLS + max(a, b);
 }
 
 __global__ void k_hist(const int32_t* __restrict__ shape1, const int32_t* __restrict__ shape2, int64_t n,
@@ -139,6 +143,7 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
     for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0;
     __syncthreads();
     int key[8], rank[8];
+    unsigned swp = 0;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       int64_t i = base + u * blockDim.x + threadIdx.x;
@@ -148,6 +153,7 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
         if ((unsigned)s1 < (unsigned)n_shapes && (unsigned)s2 < (unsigned)n_shapes) {
           key[u] = pair_key(cls, keymap, n_shapes, s1, s2);
           rank[u] = atomicAdd(&sh[key[u]], 1);
+          if (cls[s1] > cls[s2]) swp |= 1u << u;
         }
       }
     }
@@ -157,7 +163,7 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       int64_t i = base + u * blockDim.x + threadIdx.x;
-      if (key[u] >= 0) perm[sh[n_keys + key[u]] + rank[u]] = (int32_t)i;
+      if (key[u] >= 0) perm[sh[n_keys + key[u]] + rank[u]] = (int32_t)((uint32_t)i | (((swp >> u) & 1u) << 31));
     }
     __syncthreads();
   }
@@ -533,19 +539,20 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     ctx->max_rows_cls[c] = std::max(ctx->max_rows_cls[c], S.n_ort);
   }
   if (rows.empty()) rows.push_back(0.0);
-  // dense sort keys ordered by (class1, class2, shape1, shape2) when the table is small enough
+  // dense sort keys ordered by (unordered class pair, shape1, shape2) when the table is small enough
   ctx->use_keymap = (int64_t)n_shapes * n_shapes <= MAX_KEYS;
   std::vector<int32_t> keymap;
   ctx->key_cp.clear();
   if (ctx->use_keymap) {
     std::vector<std::pair<int, int>> order;
     for (int a = 0; a < n_shapes; a++) for (int b = 0; b < n_shapes; b++) order.push_back({a, b});
-    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& u, const std::pair<int, int>& v) {
-      return cls[u.first] * NCLS + cls[u.second] < cls[v.first] * NCLS + cls[v.second]; });
+    auto canon = [&](const std::pair<int, int>& u) {
+      return std::min(cls[u.first], cls[u.second]) * NCLS + std::max(cls[u.first], cls[u.second]); };
+    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int>& u, const std::pair<int, int>& v) { return canon(u) < canon(v); });
     keymap.resize((size_t)n_shapes * n_shapes);
     for (size_t k = 0; k < order.size(); k++) {
       keymap[(size_t)order[k].first * n_shapes + order[k].second] = (int32_t)k;
-      ctx->key_cp.push_back(cls[order[k].first] * NCLS + cls[order[k].second]);
+      ctx->key_cp.push_back(canon(order[k]));
     }
     ctx->n_keys = (int)order.size();
   } else {
@@ -580,7 +587,7 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     for (int tier = 0; tier < NTIER; tier++) {
       dcol_ctx::Tier T;
       std::vector<std::pair<int, int>> members;   // (weight, cp)
-      for (int c1 = 0; c1 < NCLS; c1++) for (int c2 = 0; c2 < NCLS; c2++) {
+      for (int c1 = 0; c1 < NCLS; c1++) for (int c2 = c1; c2 < NCLS; c2++) {      // unordered class pairs
         if (!present[c1] || !present[c2]) continue;
         int need = std::max(1, ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]);
         if (need > tier_cap[NTIER - 1]) { ctx->err = "dcol_set_shapes: too many polytope faces / polygon sides for one pair (shared memory)"; ctx->n_shapes = 0; return -3; }

@@ -1,6 +1,6 @@
 // Persistent proximity kernels (one per query kind): every CTA (2 per SM, 4 warps in lockstep each) pulls CTA-sized
 // tiles from a global queue ordered by class pair and dispatches to the class-pair specialisation of the tile's
-// bin (device-linked entries from dcol_kernels_c*.cu).
+// bin (device-linked entries from dcol_kernels_c*.cu; 21 unordered class pairs per query kind).
 #include "dcol_common.cuh"
 #include <cuda_runtime.h>
 
@@ -12,15 +12,16 @@ namespace dcol {
 template <int C1, int C2, int VAR>
 __device__ void solve_entry(const QueryParams* p, const TileCtx* tc, int idx);   // dcol_kernels_c*.cu
 
+// only class pairs C1 <= C2 exist (dcol_kernels_inst.cuh); the bins are keyed by the unordered class pair
 template <int C1, int VAR>
 __device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, const TileCtx* tc, int idx) {
   switch (c2) {
-    case 0: solve_entry<C1, 0, VAR>(p, tc, idx); break;
-    case 1: solve_entry<C1, 1, VAR>(p, tc, idx); break;
-    case 2: solve_entry<C1, 2, VAR>(p, tc, idx); break;
-    case 3: solve_entry<C1, 3, VAR>(p, tc, idx); break;
-    case 4: solve_entry<C1, 4, VAR>(p, tc, idx); break;
-    case 5: solve_entry<C1, 5, VAR>(p, tc, idx); break;
+    case 0: if constexpr (C1 <= 0) solve_entry<C1, 0, VAR>(p, tc, idx); break;
+    case 1: if constexpr (C1 <= 1) solve_entry<C1, 1, VAR>(p, tc, idx); break;
+    case 2: if constexpr (C1 <= 2) solve_entry<C1, 2, VAR>(p, tc, idx); break;
+    case 3: if constexpr (C1 <= 3) solve_entry<C1, 3, VAR>(p, tc, idx); break;
+    case 4: if constexpr (C1 <= 4) solve_entry<C1, 4, VAR>(p, tc, idx); break;
+    case 5: if constexpr (C1 <= 5) solve_entry<C1, 5, VAR>(p, tc, idx); break;
   }
 }
 

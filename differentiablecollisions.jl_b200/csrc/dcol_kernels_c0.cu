@@ -1,2 +1,2 @@
-#define DCOL_C1 0
+#define DCOL_TU 0
 #include "dcol_kernels_inst.cuh"

@@ -1,2 +1,2 @@
-#define DCOL_C1 1
+#define DCOL_TU 1
 #include "dcol_kernels_inst.cuh"

@@ -1,2 +1,2 @@
-#define DCOL_C1 2
+#define DCOL_TU 2
 #include "dcol_kernels_inst.cuh"

@@ -1,2 +1,2 @@
-#define DCOL_C1 3
+#define DCOL_TU 3
 #include "dcol_kernels_inst.cuh"

@@ -1,2 +1,2 @@
-#define DCOL_C1 4
+#define DCOL_TU 4
 #include "dcol_kernels_inst.cuh"

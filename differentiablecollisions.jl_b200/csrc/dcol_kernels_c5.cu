@@ -1,2 +1,2 @@
-#define DCOL_C1 5
+#define DCOL_TU 5
 #include "dcol_kernels_inst.cuh"

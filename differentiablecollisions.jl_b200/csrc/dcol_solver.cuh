@@ -711,13 +711,21 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
 
   // first pass: idx is a position of the sorted pair list; resume pass: idx is a slot of the bin's overflow list
-  const int pair = (tc.mode == 0) ? p.perm[idx] : (int)tc.in[idx];
-  const DevShape* S1 = p.shapes + p.shape1[pair];
-  const DevShape* S2 = p.shapes + p.shape2[pair];
+  // Only class pairs (C1 <= C2) are instantiated: a pair whose classes arrive in the other order is solved with its two
+  // primitives exchanged (alpha and the world point x do not depend on the order; the derivative blocks are written to
+  // the columns of the primitive they belong to).  The counting sort marks such pairs in bit 31 of the pair index.
+  const int praw = (tc.mode == 0) ? p.perm[idx] : (int)tc.in[idx];
+  const bool swp = praw < 0;
+  const int pair = praw & 0x7fffffff;
+  const DevShape* S1 = p.shapes + (swp ? p.shape2 : p.shape1)[pair];
+  const DevShape* S2 = p.shapes + (swp ? p.shape1 : p.shape2)[pair];
+  const int32_t* const ip1 = swp ? p.pose2 : p.pose1; const int32_t* const ip2 = swp ? p.pose1 : p.pose2;
+  const double* const gr1 = swp ? p.r2 : p.r1; const double* const ga1 = swp ? p.att2 : p.att1;
+  const double* const gr2 = swp ? p.r1 : p.r2; const double* const ga2 = swp ? p.att1 : p.att2;
   const int na = (p.att_kind == 0) ? 4 : 3;
   // pose rows: the pair's own row, or a row of a pose table (indexed queries: scenes, trajectory batches)
-  const int64_t i1 = p.pose1 ? (int64_t)p.pose1[pair] : (int64_t)pair;
-  const int64_t i2 = p.pose2 ? (int64_t)p.pose2[pair] : (int64_t)pair;
+  const int64_t i1 = ip1 ? (int64_t)ip1[pair] : (int64_t)pair;
+  const int64_t i2 = ip2 ? (int64_t)ip2[pair] : (int64_t)pair;
 
   RowStore rs{dcol_dyn_smem + (size_t)threadIdx.x * p.row_pitch};
   // Both poses are fetched up front (14 independent loads in flight at once): all warps of the CTA start a tile
@@ -725,8 +733,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   // for several DRAM round trips per tile (ncu: build_frame held 11 % of the stall samples with 2 % of the instructions).
   double pose[14];
   {
-    const double* g1 = p.r1 + 3 * i1; const double* h1 = p.att1 + na * i1;
-    const double* g2 = p.r2 + 3 * i2; const double* h2 = p.att2 + na * i2;
+    const double* g1 = gr1 + 3 * i1; const double* h1 = ga1 + na * i1;
+    const double* g2 = gr2 + 3 * i2; const double* h2 = ga2 + na * i2;
 #pragma unroll
     for (int a = 0; a < 3; a++) { pose[a] = __ldg(g1 + a); pose[3 + a] = __ldg(h1 + a); pose[7 + a] = __ldg(g2 + a); pose[10 + a] = __ldg(h2 + a); }
     pose[6] = (na == 4) ? __ldg(h1 + 3) : 0.0; pose[13] = (na == 4) ? __ldg(h2 + 3) : 0.0;
@@ -849,7 +857,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
         const int slot = atomicAdd(tc.ov_count, 1);
         const int64_t st = tc.ov_cap;
         double* q = tc.ov + slot;
-        q[0] = (double)pair; q += st;
+        q[0] = (double)praw; q += st;
         q[0] = (double)k; q += st;
         q[0] = sz; q += st;
 #pragma unroll
@@ -934,7 +942,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
 
   // ---------------- outputs ----------------
   Frame F1, F2;
-  build_frame(S1, p.r1 + 3 * i1, p.att1 + na * i1, p.att_kind, F1);
+  build_frame(S1, gr1 + 3 * i1, ga1 + na * i1, p.att_kind, F1);
   p.alpha[pair] = y[3];
   if (p.x) {
 #pragma unroll
@@ -948,13 +956,13 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     {
       double* g = p.deriv + (int64_t)nt * pair;
       if (status == ST_OK) {
-        build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
+        build_frame(S2, gr2 + 3 * i2, ga2 + na * i2, p.att_kind, F2);
         double y1[NV1], y2[NV2];
         PM::to_local(y, R, t, true, y1, y2);
         SideVecs V1, V2;
         A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
-        grad_side(S1, F1, p.att1 + na * i1, p.att_kind, V1, g);
-        grad_side(S2, F2, p.att2 + na * i2, p.att_kind, V2, g + 3 + na);
+        grad_side(S1, F1, ga1 + na * i1, p.att_kind, V1, g + (swp ? 3 + na : 0));
+        grad_side(S2, F2, ga2 + na * i2, p.att_kind, V2, g + (swp ? 0 : 3 + na));
       } else {
         for (int j = 0; j < nt; j++) g[j] = __longlong_as_double(0x7ff8000000000000LL);
       }
@@ -965,7 +973,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     double* Jo = p.deriv + (int64_t)4 * nt * pair;
     bool ok = (status == ST_OK);
     if (ok) {
-      build_frame(S2, p.r2 + 3 * i2, p.att2 + na * i2, p.att_kind, F2);
+      build_frame(S2, gr2 + 3 * i2, ga2 + na * i2, p.att_kind, F2);
       double K1[4][3], K2[4][3], Kb1[4][3], Kb2[4][3], Ye1[4][2], Ye2[4][2], Hw[4][3];
       SideVecs V1, V2;
       {
@@ -1054,8 +1062,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
         }
       }
       if (ok) {
-        jac_side<P1::NE>(S1, F1, p.att1 + na * i1, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo);
-        jac_side<P2::NE>(S2, F2, p.att2 + na * i2, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + 4 * (3 + na));
+        jac_side<P1::NE>(S1, F1, ga1 + na * i1, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo + (swp ? 4 * (3 + na) : 0));
+        jac_side<P2::NE>(S2, F2, ga2 + na * i2, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + (swp ? 0 : 4 * (3 + na)));
       } else {
         status = ST_NUMERICAL;
       }

@@ -87,7 +87,7 @@ struct LaunchTable {
   int tile_prefix[MAX_BINS + 1];   // first tile of bin b
   int begin[MAX_BINS];             // sorted-position range of bin b (resume pass: 0 .. ov_count)
   int end[MAX_BINS];
-  int cp[MAX_BINS];                // class pair c1*NCLS + c2
+  int cp[MAX_BINS];                // class pair c1*NCLS + c2, c1 <= c2
   // straggler hand-over: when at most spill_t pairs of a tile are still iterating, they park their iterate in the
   // bin's overflow list and the tile ends; a second (resume) launch finishes them in dense tiles
   int spill_t;

@@ -1073,8 +1073,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   if (p.status) p.status[pair] = status;
 }
 
-// Out-of-line entry of one specialisation (separate compilation: each class row lives in its own
-// translation unit and is device-linked into the persistent kernels of dcol_dispatch.cu).
+// Out-of-line entry of one specialisation (separate compilation: the 21 class pairs are dealt over six
+// translation units, dcol_kernels_inst.cuh, and device-linked into the persistent kernels of dcol_dispatch.cu).
 template <int C1, int C2, int VAR>
 __device__ __noinline__ void solve_entry(const QueryParams* p, const TileCtx* tc, int idx) {
   solve_pair<C1, C2, VAR>(*p, *tc, idx);

@@ -495,6 +495,7 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     int64_t avail = n_params - param_off[i];
     int c = type_to_cls(type[i]);
     if (c < 0 || param_off[i] < 0 || avail < 13) { ctx->err = "dcol_set_shapes: bad shape type or offset at shape " + std::to_string(i); return -1; }
+    if (rows.size() & 1) rows.push_back(0.0);          // rows of every shape start 16-byte aligned (double2 loads)
     S.cls = c; S.type = type[i]; S.rows_off = (int64_t)rows.size();
     const double* tail = nullptr;
     auto row = [&](std::initializer_list<double> v) { rows.insert(rows.end(), v); };

@@ -229,6 +229,23 @@ struct Prim {
 #endif
   static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE) ? 2 : DCOL_ROW_UNROLL_SMALL;
   __device__ static constexpr bool nz(int a) { return Cls<CLS>::nz(a); }   // structurally non-zero row coefficient
+  // constants of row i (zeros where the class has none).  Every shape's rows start on a 16-byte boundary
+  // (dcol_set_shapes), so polytope rows (4 doubles) and the slack part of polygon rows (6 doubles) are read as double2.
+  __device__ __forceinline__ void load_row(int i, double (&c)[NV]) const {
+    if constexpr (CLS == CLS_POLYTOPE) {
+      const double2* q = reinterpret_cast<const double2*>(rows + i * 4);
+      const double2 u = __ldg(q), v = __ldg(q + 1);
+      c[0] = u.x; c[1] = u.y; c[2] = v.x; c[3] = v.y;
+    } else if constexpr (CLS == CLS_POLYGON) {
+      c[0] = 0.0; c[1] = 0.0; c[2] = 0.0;
+      c[3] = __ldg(rows + i * 6 + 3);
+      const double2 v = __ldg(reinterpret_cast<const double2*>(rows + i * 6 + 4));
+      c[4] = v.x; c[5] = v.y;
+    } else {
+#pragma unroll
+      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
+    }
+  }
   const double* rows; int n; int row0;
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
@@ -268,8 +285,7 @@ struct Prim {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
       double c[NV];
-#pragma unroll
-      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
+      load_row(i, c);
       double u = 0.0;
       if (has_off) {
 #pragma unroll
@@ -295,8 +311,10 @@ struct Prim {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
       double us = 0.0, uz = 0.0;
+      double c[NV];
+      load_row(i, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) { double c = __ldg(rows + i * NV + a); us += c * yh[a]; uz += c * dh[a]; }
+      for (int a = 0; a < NV; a++) if (nz(a)) { us += c[a] * yh[a]; uz += c[a] * dh[a]; }
       rs(F_S, row0 + i) = -us; rs(F_Z, row0 + i) = uz;
       min_s = fmin(min_s, -us); min_z = fmin(min_z, uz);
     }
@@ -340,8 +358,7 @@ struct Prim {
 #pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double c[NV];
-#pragma unroll
-      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
+      load_row(i, c);
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i);
       double u = 0.0;
 #pragma unroll
@@ -422,8 +439,10 @@ struct Prim {
 #pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
+      double c[NV];
+      load_row(i, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) cd += __ldg(rows + i * NV + a) * dyh[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) cd += c[a] * dyh[a];
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i);
       const double t = r - cd;                  // -ds
       const double is = zi * rr;
@@ -469,8 +488,10 @@ struct Prim {
 #pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       const double q = (sigmu - rs(F_P, row0 + i)) * rs(F_Z, row0 + i) * rs(F_R, row0 + i);
+      double c[NV];
+      load_row(i, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) g2[a] += q * __ldg(rows + i * NV + a);
+      for (int a = 0; a < NV; a++) if (nz(a)) g2[a] += q * c[a];
     }
   }
   __device__ __forceinline__ void passC_soc(double sigmu, double (&g2)[NV]) {
@@ -501,8 +522,10 @@ struct Prim {
 #pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
+      double c[NV];
+      load_row(i, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) cd += __ldg(rows + i * NV + a) * dyh[a];
+      for (int a = 0; a < NV; a++) if (nz(a)) cd += c[a] * dyh[a];
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i), pp = rs(F_P, row0 + i);
       const double t = r - cd;
       const double is = zi * rr, iz = si * rr;
@@ -560,8 +583,10 @@ struct Prim {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
       double zi = rs(F_Z, row0 + i);
+      double c[NV];
+      load_row(i, c);
 #pragma unroll
-      for (int a = 0; a < 3; a++) if (nz(a)) w[a] += zi * __ldg(rows + i * NV + a);
+      for (int a = 0; a < 3; a++) if (nz(a)) w[a] += zi * c[a];
     }
     constexpr int SOC = Cls<CLS>::SOC;
     if constexpr (D > 0 && SOC != SOC_BALL) soc_applyT<CLS, NV, D>(sc, z, w);
@@ -585,8 +610,7 @@ struct Prim {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
       double c[NV];
-#pragma unroll
-      for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
+      load_row(i, c);
       double d = rs(F_Z, row0 + i) / rs(F_S, row0 + i);
 #pragma unroll
       for (int a = 0; a < NV; a++) if (nz(a)) { double dc = d * c[a];

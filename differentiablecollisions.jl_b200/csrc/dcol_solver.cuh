@@ -241,12 +241,21 @@ struct Prim {
       c[3] = __ldg(rows + i * 6 + 3);
       const double2 v = __ldg(reinterpret_cast<const double2*>(rows + i * 6 + 4));
       c[4] = v.x; c[5] = v.y;
+    } else if constexpr (CLS == CLS_CAPCYL) {
+      // rows are [0,0,0,L/2,-1], [0,0,0,L/2,+1] (capsule, cylinder) and [+1,0,0,L/2,0], [-1,0,0,L/2,0] (cylinder only):
+      // synthesised from L/2 (kept in a register) and the row index, no loads in the solver loop
+      c[1] = 0.0; c[2] = 0.0; c[3] = rc0;
+      c[4] = (i == 0) ? -1.0 : ((i == 1) ? 1.0 : 0.0);
+      c[0] = (i == 2) ? 1.0 : ((i == 3) ? -1.0 : 0.0);
+    } else if constexpr (CLS == CLS_CONE) {
+      c[0] = -1.0; c[1] = 0.0; c[2] = 0.0; c[3] = rc0;      // the base plane: alpha*H/4 - x~_1
     } else {
 #pragma unroll
       for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
     }
   }
   const double* rows; int n; int row0;
+  double rc0;                          // capsule / cylinder: L/2, cone: H/4 (the only non-trivial row constant)
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
   double wb[DD], bb;                   // NT scaling point wbar and 1/(1+wbar0):  Wbar^-1 = J Wbar J (rank-one form)
@@ -268,6 +277,7 @@ struct Prim {
   __device__ __forceinline__ void load(const DevShape* S, const double* rows_base, int row0_) {
     n = (CLS == CLS_CONE) ? 1 : S->n_ort;      // a cone has exactly one orthant row (its base plane)
     rows = rows_base + S->rows_off; row0 = row0_;
+    if constexpr (CLS == CLS_CAPCYL || CLS == CLS_CONE) rc0 = __ldg(rows + 3);
     constexpr int SOC = Cls<CLS>::SOC;
     if constexpr (SOC == SOC_BALL) sc[0] = S->soc[0];
     if constexpr (SOC == SOC_CONE) { sc[0] = S->soc[0]; sc[1] = S->soc[1]; }

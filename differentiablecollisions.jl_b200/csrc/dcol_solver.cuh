@@ -220,14 +220,15 @@ __device__ __forceinline__ double soc_linesearch_m(const double (&y)[D], const d
 template <int CLS>
 struct Prim {
   static constexpr int NE = Cls<CLS>::NE, NV = 4 + Cls<CLS>::NE, D = Cls<CLS>::D, DD = (Cls<CLS>::D > 0 ? Cls<CLS>::D : 1);
-  // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes); elsewhere code size wins.
+  // orthant-row loops: unrolled twice only where rows are the bulk of the work (polytopes, polygons: -5 % on
+  // polygon pairs, neutral on mixed batches); elsewhere code size wins.
   // The once-per-pair row loops (initial point, hand-over records, derivative epilogue) are never unrolled: the
   // compiler's default (x4) made the code ahead of the main loop 40 KB, which the other CTA of the SM pays for in
   // instruction-cache misses on its loop body.
 #ifndef DCOL_ROW_UNROLL_SMALL
 #define DCOL_ROW_UNROLL_SMALL 1
 #endif
-  static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE) ? 2 : DCOL_ROW_UNROLL_SMALL;
+  static constexpr int ROW_UNROLL = (CLS == CLS_POLYTOPE || CLS == CLS_POLYGON) ? 2 : DCOL_ROW_UNROLL_SMALL;
   __device__ static constexpr bool nz(int a) { return Cls<CLS>::nz(a); }   // structurally non-zero row coefficient
   // constants of row i (zeros where the class has none).  Every shape's rows start on a 16-byte boundary
   // (dcol_set_shapes), so polytope rows (4 doubles) and the slack part of polygon rows (6 doubles) are read as double2.

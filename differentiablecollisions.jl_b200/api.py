@@ -63,6 +63,10 @@ class Context:
 
     # ---- shape table ---------------------------------------------------------------------
     def add_shape(self, prim) -> int:
+        # ids returned here index self.table; after set_shape_arrays (raw mode) the device holds a different
+        # table, so mark it stale: the next query re-uploads self.table instead of silently using the raw one
+        if self._table_version is None:
+            self._table_version = -1
         return self.table.add(prim)
 
     def set_shape_arrays(self, types, offs, params):

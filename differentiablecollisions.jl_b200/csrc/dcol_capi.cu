@@ -16,8 +16,18 @@
 #include <vector>
 
 namespace dcol {
-const void* persistent_kernel_ptr(int var);                                                          // dcol_dispatch.cu
-cudaError_t launch_persistent(int var, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
+// one translation unit per query kind (dcol_kernels_v{0,1,2}.cu, dcol_persistent.cuh)
+const void* persistent_kernel_ptr_v0(); const void* persistent_kernel_ptr_v1(); const void* persistent_kernel_ptr_v2();
+cudaError_t launch_persistent_v0(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
+cudaError_t launch_persistent_v1(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
+cudaError_t launch_persistent_v2(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
+static const void* persistent_kernel_ptr(int var) {
+  return var == 2 ? persistent_kernel_ptr_v2() : (var == 1 ? persistent_kernel_ptr_v1() : persistent_kernel_ptr_v0());
+}
+static cudaError_t launch_persistent(int var, int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter) {
+  return var == 2 ? launch_persistent_v2(grid, block, smem, st, tt, counter)
+       : (var == 1 ? launch_persistent_v1(grid, block, smem, st, tt, counter) : launch_persistent_v0(grid, block, smem, st, tt, counter));
+}
 }
 using namespace dcol;
 
@@ -80,6 +90,10 @@ struct dcol_ctx {
   };
   Slot slots[N_SLOTS];
   int next_ticket = 0;
+  // outcome of submissions whose slot has been reused since (dcol_wait on an older ticket still reports it)
+  static constexpr int N_DONE = 16;
+  int done_ticket[N_DONE]; int done_result[N_DONE]; std::string done_err[N_DONE]; int done_head = 0;
+  dcol_ctx() { for (int i = 0; i < N_DONE; i++) { done_ticket[i] = -1; done_result[i] = 0; } }
   DevBuf d_scene, d_pairs, d_plan, d_wrench;
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   int n_sm = 148;
@@ -87,6 +101,9 @@ struct dcol_ctx {
   double last_ms = -1.0;
   cudaStream_t stream() const { return user ? user : own; }
 };
+
+static int finish_query(dcol_ctx* ctx, int slot);
+static int drain_all(dcol_ctx* ctx);
 
 // ---------------------------------------------------------------------------
 // binning kernels: counting sort of pair indices by the UNORDERED class pair (lo, hi)[, then shape1, shape2]: a pair
@@ -484,6 +501,10 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   ctx->err.clear();
   if (n_shapes <= 0 || !type || !param_off || !params) { ctx->err = "dcol_set_shapes: bad arguments"; return -1; }
   CK(cudaSetDevice(ctx->device));
+  // the table, the row constants and the launch plan are read by kernels of submissions still in flight on the
+  // library's non-blocking streams: join them before anything is overwritten
+  { int rc = drain_all(ctx); if (rc) return rc; }
+  CK(cudaDeviceSynchronize());
   std::vector<DevShape> hs(n_shapes);
   std::vector<double> rows;
   std::vector<int32_t> cls(n_shapes);
@@ -494,7 +515,29 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     const double* p = params + param_off[i];
     int64_t avail = n_params - param_off[i];
     int c = type_to_cls(type[i]);
-    if (c < 0 || param_off[i] < 0 || avail < 13) { ctx->err = "dcol_set_shapes: bad shape type or offset at shape " + std::to_string(i); return -1; }
+    if (c < 0 || param_off[i] < 0 || param_off[i] >= n_params) { ctx->err = "dcol_set_shapes: bad shape type or offset at shape " + std::to_string(i); return -1; }
+    {
+      // packed length per type: geometry + r_offset[3] + Q_offset[9]  (include/dcol_b200.h)
+      int64_t need = 0;
+      const int64_t nn = (type[i] == T_POLYTOPE || type[i] == T_POLYGON) ? (int64_t)p[0] : 0;
+      switch (type[i]) {
+        case T_CAPSULE: case T_CYLINDER: case T_CONE: need = 2 + 12; break;
+        case T_SPHERE: need = 1 + 12; break;
+        case T_ELLIPSOID: need = 9 + 12; break;
+        case T_POLYTOPE: need = 1 + 4 * nn + 12; break;
+        case T_POLYGON: need = 2 + 3 * nn + 12; break;
+      }
+      if (((type[i] == T_POLYTOPE || type[i] == T_POLYGON) && (!(p[0] >= 1.0) || p[0] > 1e6 || p[0] != std::floor(p[0]))) || avail < need) {
+        ctx->err = "dcol_set_shapes: parameter block of shape " + std::to_string(i) + " is truncated or has a bad row count"; return -1; }
+      for (int64_t k = 0; k < need; k++) if (!std::isfinite(p[k])) {
+        ctx->err = "dcol_set_shapes: non-finite parameter at shape " + std::to_string(i); return -1; }
+      bool pos = true;
+      if (type[i] == T_CAPSULE || type[i] == T_CYLINDER || type[i] == T_CONE) pos = p[0] > 0.0 && p[1] > 0.0;
+      if (type[i] == T_CONE) pos = pos && p[1] < 1.5707963267948966;
+      if (type[i] == T_SPHERE) pos = p[0] > 0.0;
+      if (type[i] == T_POLYGON) pos = p[1 + 3 * nn] > 0.0;
+      if (!pos) { ctx->err = "dcol_set_shapes: R, L, H, beta must be positive (beta < pi/2) at shape " + std::to_string(i); return -1; }
+    }
     if (rows.size() & 1) rows.push_back(0.0);          // rows of every shape start 16-byte aligned (double2 loads)
     S.cls = c; S.type = type[i]; S.rows_off = (int64_t)rows.size();
     const double* tail = nullptr;
@@ -643,6 +686,9 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     CK(ctx->d_plan.need(sizeof(LaunchTable) * plan.size()));
     CK(cudaMemcpy(ctx->d_plan.p, plan.data(), sizeof(LaunchTable) * plan.size(), cudaMemcpyHostToDevice));
   }
+  // a cudaMemcpy from pageable memory may return once the data is staged; the solver launches go to non-blocking
+  // streams that are not ordered behind the legacy stream, so make the uploads visible before returning
+  CK(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -677,7 +723,6 @@ double dcol_measure_fp64_tflops(dcol_ctx* ctx) {
 // query driver
 // ---------------------------------------------------------------------------
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
-static int finish_query(dcol_ctx* ctx, int slot);
 
 // pose1/pose2 == NULL: r*/att* have one row per pair.  Otherwise they are tables of np1 / np2 rows and pair k uses
 // rows pose1[k] / pose2[k].  in_mem: where the INPUT arrays live (lets the scene operator feed device-generated
@@ -688,11 +733,13 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
                      double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters,
                      const int32_t* pose1 = nullptr, const int32_t* pose2 = nullptr, int64_t np1 = 0, int64_t np2 = 0,
                      int in_mem = -1, int slot = 0, bool async = false) {
+  if (!ctx) return -1;
   if (in_mem < 0) in_mem = mem;
   dcol_ctx::Slot& L = ctx->slots[slot];
+  // a slot about to be reused: join the submission it still holds; its outcome stays retrievable by ticket (dcol_wait)
   if (L.pending) { int rc = finish_query(ctx, slot); if (rc && !async) return rc; }
+  L.ticket = -1;
   const bool indexed = (pose1 != nullptr);
-  if (!ctx) return -1;
   ctx->err.clear();
   ctx->last_ms = -1.0;
   if (ctx->n_shapes == 0) { ctx->err = "dcol: shape table not set (call dcol_set_shapes first)"; return -1; }
@@ -915,10 +962,22 @@ static int finish_query(dcol_ctx* ctx, int slot) {
     if (cudaEventElapsedTime(&ms, L.ev_t0[c], L.ev_t1[c]) == cudaSuccess) total_ms += ms;
   }
   L.ms = total_ms; ctx->last_ms = total_ms;
-  for (int c = 0; c < L.nchunks; c++)
-    if (L.h_bad[c]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; L.result = -1; return -1; }
   L.result = 0;
-  return 0;
+  for (int c = 0; c < L.nchunks; c++)
+    if (L.h_bad[c]) { ctx->err = "dcol: shape index out of range in shape1/shape2"; L.result = -1; }
+  if (L.ticket >= 0) {
+    const int h = ctx->done_head; ctx->done_head = (h + 1) % dcol_ctx::N_DONE;
+    ctx->done_ticket[h] = L.ticket; ctx->done_result[h] = L.result; ctx->done_err[h] = L.result ? ctx->err : std::string();
+  }
+  return L.result;
+}
+
+// Join every submission still in flight (entry points that rewrite context-level buffers the kernels read)
+static int drain_all(dcol_ctx* ctx) {
+  int rc = 0;
+  for (int k = 0; k < dcol_ctx::N_SLOTS; k++)
+    if (ctx->slots[k].pending) { int r = finish_query(ctx, k); if (r && !rc) rc = r; }
+  return rc;
 }
 
 extern "C" {
@@ -977,6 +1036,7 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
   if (np == 0) return 0;
   if (np > 0x7fffffff) { ctx->err = "dcol_scene_allpairs: too many pairs for one call"; return -1; }
   CK(cudaSetDevice(ctx->device));
+  { int rc = drain_all(ctx); if (rc) return rc; }      // context-level scratch (d_scene, d_pairs) is about to be rewritten
   cudaStream_t S = ctx->stream();
   const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3;
   // body arrays on the device
@@ -1012,6 +1072,7 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
   const int64_t np = dcol_scene_pair_count(n_bodies);
   if (np > 0x7fffffff) { ctx->err = "dcol_scene_wrench: too many pairs for one call"; return -1; }
   CK(cudaSetDevice(ctx->device));
+  { int rc = drain_all(ctx); if (rc) return rc; }
   cudaStream_t S = ctx->stream();
   const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3, nt = 6 + 2 * na;
   if (np == 0) {
@@ -1080,6 +1141,7 @@ int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta,
   if (np == 0) return 0;
   if (np > 0x7fffffff) { ctx->err = "dcol_se2_constraints: too many pairs for one call"; return -1; }
   CK(cudaSetDevice(ctx->device));
+  { int rc = drain_all(ctx); if (rc) return rc; }
   cudaStream_t S = ctx->stream();
   const bool host = (mem == DCOL_MEM_HOST);
   // device scratch: gradient rows | alpha | status | vehicle poses | (host mode) states, c, Jc
@@ -1152,7 +1214,9 @@ int dcol_wait(dcol_ctx* ctx, int ticket) {
   if (!ctx) return -1;
   for (int k = 0; k < dcol_ctx::N_SLOTS; k++)
     if (ctx->slots[k].ticket == ticket) return finish_query(ctx, k);
-  ctx->err = "dcol_wait: unknown ticket (only the last three submissions are kept)";
+  for (int h = 0; h < dcol_ctx::N_DONE; h++)
+    if (ctx->done_ticket[h] == ticket) { if (ctx->done_result[h]) ctx->err = ctx->done_err[h]; return ctx->done_result[h]; }
+  ctx->err = "dcol_wait: unknown ticket (the outcomes of the last 16 submissions are kept)";
   return -1;
 }
 

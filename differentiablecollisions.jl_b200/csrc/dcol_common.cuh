@@ -110,6 +110,7 @@ struct TileCtx {
   int* ov_count;
   const double* in;                // this bin's records to resume from (mode 1)
   int in_cap;
+  int dup;                         // lane past the end of the bin: redoes the bin's last pair for the barriers only
 };
 
 }  // namespace dcol

@@ -94,15 +94,24 @@ __device__ __forceinline__ void soc_jdiv(const double (&lam)[D], const double (&
   for (int i = 1; i < D; i++) out[i] = irho * ((nu * il0 - w[0]) * lam[i] + (rho * il0) * w[i]);
 }
 
-// Gaussian elimination without pivoting, NR right-hand sides, fully unrolled (registers).
-// The reduced KKT matrix G'S^-1 Z G is symmetric positive definite up to the O(distance from the
-// central path) asymmetry of arrow(s)^-1 arrow(z), so elimination in natural order is stable;
-// the reference uses StaticArrays' pivoted LU (src/proximity.jl:100) on the same matrix.
+// Gaussian elimination with partial (row) pivoting, NR right-hand sides, fully unrolled (registers).
+// The reference solves the same reduced KKT system G'S^-1 Z G with StaticArrays' pivoted LU (src/proximity.jl:100);
+// its condition number reaches 1e7 on pairs close to degeneracy, where elimination in natural order loses digits.
+// The pivot search is a chain of predicated row exchanges (no dynamic indexing, so the arrays stay in registers):
+// after comparing row k with every row below it, row k holds the entry of largest magnitude in column k.
 template <int N, int NR>
 __device__ __forceinline__ bool ge_solve(double (&A)[N][N], double (&B)[N][NR]) {
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < N; k++) {
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#pragma unroll
+      for (int j = k; j < N; j++) { const double a = A[k][j], b = A[i][j]; A[k][j] = sw ? b : a; A[i][j] = sw ? a : b; }
+#pragma unroll
+      for (int j = 0; j < NR; j++) { const double a = B[k][j], b = B[i][j]; B[k][j] = sw ? b : a; B[i][j] = sw ? a : b; }
+    }
     double piv = A[k][k];
     ok = ok && (fabs(piv) > 0.0) && (piv == piv);
     double ip = 1.0 / piv;
@@ -140,17 +149,17 @@ __device__ __forceinline__ bool ge_solve(double (&A)[N][N], double (&B)[N][NR]) 
 // block's z (body coords), Be = B~ e (body coords), xt = x~ (body coords).
 struct SideVecs { double wr[3], zb[3], Be[3], xt[3]; };
 
-// build_frame and grad_side are class-independent and are compiled ONCE (dcol_shared.cu, out of line): every
-// specialisation calls the same code, which therefore stays resident in the instruction caches while the
-// persistent kernel moves from one class pair to the next.  jac_side is inlined: its 4x3 operands would
+// build_frame and grad_side are class-independent and are compiled once per query kind (dcol_shared.cuh, out of
+// line): every specialisation calls the same code, which therefore stays resident in the instruction caches while
+// the persistent kernel moves from one class pair to the next.  jac_side is inlined: its 4x3 operands would
 // otherwise travel through local memory (measured: -11 % Jacobian time on mixed batches).
 
 // r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
-__device__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F);
+static __device__ __noinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F);
 
 // gradient columns of one primitive: out[0:3] = d alpha/d r_k, out[3:3+na] = d alpha/d att_k
 // (src/proximity_gradient.jl:1-78: -z' du/dtheta)
-__device__ void grad_side(const DevShape* S, const Frame& F, const double* att, int att_kind, const SideVecs& V, double* out);
+static __device__ __noinline__ void grad_side(const DevShape* S, const Frame& F, const double* att, int att_kind, const SideVecs& V, double* out);
 
 // Jacobian columns of one primitive, written column-major (4 rows) at out[col*4 + row]:
 // columns 0..2 = d/d r_k, 3..3+na = d/d att_k.

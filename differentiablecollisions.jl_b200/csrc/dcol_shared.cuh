@@ -1,10 +1,13 @@
-// Class-independent device routines shared by every specialisation (compiled once, device-linked).
+// Class-independent device routines shared by every specialisation of a query kind: out of line (one copy per
+// translation unit = per query kind), so that they stay resident in the instruction caches while the persistent
+// kernel moves from one class pair to the next.
+#pragma once
 #include "dcol_deriv.cuh"
 
 namespace dcol {
 
 // r~ = r + Qn*r_offset, Q = Qn*Q_offset  (dispatch wrappers, e.g. src/problem_matrices.jl:40-53)
-__device__ __noinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F) {
+static __device__ __noinline__ void build_frame(const DevShape* S, const double* r, const double* att, int att_kind, Frame& F) {
   double Qn[3][3];
   if (att_kind == 0) { double q[4] = {att[0], att[1], att[2], att[3]}; dcm_from_q<double>(q, Qn); }
   else { double p[3] = {att[0], att[1], att[2]}; dcm_from_mrp<double>(p, Qn); }
@@ -25,7 +28,7 @@ __device__ __noinline__ void build_frame(const DevShape* S, const double* r, con
 
 // gradient columns of one primitive: out[0:3] = d alpha/d r_k, out[3:3+na] = d alpha/d att_k
 // (src/proximity_gradient.jl:1-78: -z' du/dtheta)
-__device__ __noinline__ void grad_side(const DevShape* S, const Frame& F, const double* att, int att_kind,
+static __device__ __noinline__ void grad_side(const DevShape* S, const Frame& F, const double* att, int att_kind,
                                           const SideVecs& V, double* out) {
   const bool off = S->has_offset != 0;
   double gwr[3], gzb[3], v[3], a[3], ob[3];

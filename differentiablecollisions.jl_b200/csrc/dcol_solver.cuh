@@ -16,7 +16,7 @@
 //     everything else (y, KKT matrix, SOC blocks) is in registers;
 //   * SOC search directions are accumulated in the NT-scaled space and all reciprocals / rsqrts are
 //     branch-free (hardware seed + one cubic step).
-// The warps of a CTA advance through the interior-point iterations in lockstep (dcol_dispatch.cu pulls CTA-sized
+// The warps of a CTA advance through the interior-point iterations in lockstep (dcol_persistent.cuh pulls CTA-sized
 // tiles from a queue), so that they share instruction-cache lines.
 #pragma once
 #include "dcol_common.cuh"
@@ -873,15 +873,17 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   // the unrolled loop body is far larger than the SM's instruction cache, and warps in lockstep
   // share each fetched instruction line instead of streaming the loop once per warp.
   int it = 0;
-  bool active = (status == ST_OK);
-  bool parked = false;
+  bool active = (status == ST_OK) && !tc.dup;
+  bool parked = tc.dup != 0;                // duplicate lanes write nothing
   if (active) status = ST_PDIP_FAILED;
   for (int k = k0;; k++) {
     const double mu = sz * inv_deg;
     if (active) {
-      if (!(mu == mu)) { status = ST_NUMERICAL; active = false; it = k; }
+      // the reference tests mu only at the START of iterations 1..50 (static_solver2.jl:132,143-146) and raises
+      // "pdip failed" after the 50th step without another test (:188): a pair that would pass on its 50th step fails
+      if (k == MAX_ITERS) { active = false; it = k; }
+      else if (!(mu == mu)) { status = ST_NUMERICAL; active = false; it = k; }
       else if (mu < p.pdip_tol) { status = ST_OK; active = false; it = k; }
-      else if (k == MAX_ITERS) { active = false; it = k; }
     }
     const int n_act = DCOL_COUNT(active);
     if (n_act == 0) break;
@@ -1108,8 +1110,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   if (p.status) p.status[pair] = status;
 }
 
-// Out-of-line entry of one specialisation (separate compilation: the 21 class pairs are dealt over six
-// translation units, dcol_kernels_inst.cuh, and device-linked into the persistent kernels of dcol_dispatch.cu).
+// Out-of-line entry of one specialisation (same translation unit as the persistent kernel that calls it,
+// dcol_persistent.cuh: whole-program compilation, so ptxas allocates registers across the call).
 template <int C1, int C2, int VAR>
 __device__ __noinline__ void solve_entry(const QueryParams* p, const TileCtx* tc, int idx) {
   solve_pair<C1, C2, VAR>(*p, *tc, idx);

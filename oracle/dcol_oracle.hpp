@@ -23,7 +23,7 @@
 
 namespace dcol_oracle {
 
-constexpr int MAXF = 32;            // max faces of a polytope / sides of a polygon
+constexpr int MAXF = 128;           // max faces of a polytope / sides of a polygon
 constexpr int MAXV = 6;             // max per-primitive variables (polygon: x,alpha,y1,y2)
 constexpr int MAXX = 8;             // max pair variables (polygon-polygon)
 constexpr int MAXS = 2 * MAXF + 8;  // max cone rows of a pair

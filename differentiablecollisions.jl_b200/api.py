@@ -154,7 +154,11 @@ class Context:
         return out
 
     # ---- batched host API ----------------------------------------------------------------------
-    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out=None):
+    def set_max_iters(self, k: int = 50):
+        """Testing knob (dcol_set_max_iters): iteration cap of the solver, 50 in the reference and by default."""
+        self._check(self._lib.dcol_set_max_iters(self._h, int(k)))
+
+    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out=None, want_mu=False):
         shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
         shape2 = np.ascontiguousarray(shape2, dtype=np.int32).reshape(-1)
         n = shape1.shape[0]
@@ -178,9 +182,18 @@ class Context:
             deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
             status = np.empty(n, dtype=np.int32)
             iters = np.empty(n, dtype=np.int32)
-        self.query_raw(kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, MEM_HOST,
-                       alpha, x, deriv, status, iters)
+        mu = np.empty(n) if want_mu else None
+        if want_mu:
+            self._check(self._lib.dcol_set_mu_output(self._h, _ptr(mu)))
+        try:
+            self.query_raw(kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, MEM_HOST,
+                           alpha, x, deriv, status, iters)
+        finally:
+            if want_mu:
+                self._lib.dcol_set_mu_output(self._h, None)
         out = {"alpha": alpha, "status": status, "iters": iters}
+        if want_mu:
+            out["mu"] = mu
         if x is not None:
             out["x"] = x
         if kind == 1:

@@ -79,7 +79,7 @@ struct dcol_ctx {
   static constexpr int MAX_CHUNKS = 8;
   static constexpr int N_SLOTS = 3;
   struct Slot {
-    DevBuf d_in, d_out, d_perm, d_hist, d_tables, d_ov;
+    DevBuf d_in, d_out, d_recs, d_inv, d_sorted, d_hist, d_tables, d_ov;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
     cudaEvent_t ev_end = nullptr;       // recorded behind the last operation of the submission (its own join point)
     bool pending = false; int ticket = -1, result = 0;
@@ -99,6 +99,8 @@ struct dcol_ctx {
   int n_sm = 148;
   int64_t launches = 0;
   double last_ms = -1.0;
+  int max_iters = MAX_ITERS;            // testing knob (dcol_set_max_iters); the reference's 50 otherwise
+  double* mu_out = nullptr;             // optional per-pair final duality measure (dcol_set_mu_output), same memory space as the query's outputs
   cudaStream_t stream() const { return user ? user : own; }
 };
 
@@ -131,76 +133,110 @@ __global__ void k_hist(const int32_t* __restrict__ shape1, const int32_t* __rest
   for (int k = threadIdx.x; k < n_keys; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
 }
 
-// single block: exclusive scan of hist[0..n_keys) -> off[0..n_keys], cursor = off
-__global__ void k_scan(const int* __restrict__ hist, int n_keys, int* __restrict__ off, int* __restrict__ cursor) {
-  __shared__ int part[1024];
-  int per = (n_keys + blockDim.x - 1) / blockDim.x;
-  int b = threadIdx.x * per, e = min(b + per, n_keys);
-  int s = 0;
-  for (int k = b; k < e; k++) s += hist[k];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  for (int d = 1; d < blockDim.x; d <<= 1) {
-    int v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
+// Where the pairs of a query come from: per-pair pose rows (pose1 == NULL) or pose tables indexed per pair.
+struct PairSource {
+  const int32_t* shape1; const int32_t* shape2;
+  const int32_t* pose1; const int32_t* pose2;      // optional: row of (r1, att1) / (r2, att2) used by the pair
+  const double* r1; const double* att1; const double* r2; const double* att2;
+  int na;                                          // attitude stride: 4 quaternion, 3 MRP
+};
+
+// Write pair i at sorted position pos as one 128-byte record (eight 16-byte stores = one cache line).  Pairs whose
+// classes arrive as (hi, lo) are stored with their primitives exchanged, so the solver only ever sees (lo, hi).
+__device__ __forceinline__ void pack_pair(const PairSource& src, int64_t i, int s1, int s2, bool swp, PairRec* __restrict__ recs, int pos) {
+  const int64_t i1 = src.pose1 ? (int64_t)src.pose1[i] : i, i2 = src.pose2 ? (int64_t)src.pose2[i] : i;
+  const double* ra = src.r1 + 3 * i1; const double* aa = src.att1 + src.na * i1;
+  const double* rb = src.r2 + 3 * i2; const double* ab = src.att2 + src.na * i2;
+  double v[16];
+  v[0] = __ldg(ra); v[1] = __ldg(ra + 1); v[2] = __ldg(ra + 2);
+  v[3] = __ldg(aa); v[4] = __ldg(aa + 1); v[5] = __ldg(aa + 2); v[6] = (src.na == 4) ? __ldg(aa + 3) : 0.0;
+  v[7] = __ldg(rb); v[8] = __ldg(rb + 1); v[9] = __ldg(rb + 2);
+  v[10] = __ldg(ab); v[11] = __ldg(ab + 1); v[12] = __ldg(ab + 2); v[13] = (src.na == 4) ? __ldg(ab + 3) : 0.0;
+  if (swp) {
+#pragma unroll
+    for (int a = 0; a < 7; a++) { const double t = v[a]; v[a] = v[7 + a]; v[7 + a] = t; }
+    const int t = s1; s1 = s2; s2 = t;
   }
-  int run = part[threadIdx.x] - s;
-  for (int k = b; k < e; k++) { off[k] = run; cursor[k] = run; run += hist[k]; }
-  if (threadIdx.x == blockDim.x - 1) off[n_keys] = part[threadIdx.x];
+  v[14] = __hiloint2double(s2, s1);
+  v[15] = __hiloint2double(swp ? DCOL_REC_SWAPPED : 0, (int)i);
+  double2* q = reinterpret_cast<double2*>(recs + pos);
+#pragma unroll
+  for (int a = 0; a < 8; a++) q[a] = make_double2(v[2 * a], v[2 * a + 1]);
 }
 
-__global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __restrict__ shape2, int64_t n,
-                          const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap, int n_shapes, int n_keys,
-                          int* __restrict__ cursor, int32_t* __restrict__ perm) {
+// counting-sort scatter fused with the packing of the sorted records; also writes inv[i] = sorted position of pair i
+// (coalesced; -1 for pairs with a bad shape index), which k_unpermute uses to bring the results back into caller order
+__global__ void k_scatter_pack(PairSource src, int64_t n, const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap,
+                               int n_shapes, int n_keys, int* __restrict__ cursor, PairRec* __restrict__ recs, int32_t* __restrict__ inv) {
   extern __shared__ int sh[];          // [0,n_keys) local counts, then [n_keys, 2 n_keys) global bases
   int64_t chunk = (int64_t)blockDim.x * 8;
   for (int64_t base = blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
     for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0;
     __syncthreads();
     int key[8], rank[8];
-    unsigned swp = 0;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       int64_t i = base + u * blockDim.x + threadIdx.x;
       key[u] = -1;
       if (i < n) {
-        int s1 = shape1[i], s2 = shape2[i];
+        int s1 = src.shape1[i], s2 = src.shape2[i];
         if ((unsigned)s1 < (unsigned)n_shapes && (unsigned)s2 < (unsigned)n_shapes) {
           key[u] = pair_key(cls, keymap, n_shapes, s1, s2);
           rank[u] = atomicAdd(&sh[key[u]], 1);
-          if (cls[s1] > cls[s2]) swp |= 1u << u;
         }
       }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[n_keys + k] = sh[k] ? atomicAdd(&cursor[k], sh[k]) : 0;
     __syncthreads();
-#pragma unroll
+#pragma unroll 1
     for (int u = 0; u < 8; u++) {
       int64_t i = base + u * blockDim.x + threadIdx.x;
-      if (key[u] >= 0) perm[sh[n_keys + key[u]] + rank[u]] = (int32_t)((uint32_t)i | (((swp >> u) & 1u) << 31));
+      if (i >= n) continue;
+      int pos = -1;
+      if (key[u] >= 0) {
+        pos = sh[n_keys + key[u]] + rank[u];
+        const int s1 = src.shape1[i], s2 = src.shape2[i];
+        pack_pair(src, i, s1, s2, cls[s1] > cls[s2], recs, pos);
+      }
+      if (inv) inv[i] = pos;
     }
     __syncthreads();
   }
 }
 
-// one small block: instantiates the static per-tier launch plan (uploaded once by dcol_set_shapes; key ranges parked in
-// begin[]/end[]) for this call — query parameters arrive as a kernel argument, bin offsets from the counting sort —
-// so that neither a host read of the histogram nor a host-to-device copy sits between the sort and the solver.
-// Also carves the straggler overflow area: bin b gets tiles_b * spill_t records (a tile hands over at most spill_t pairs).
-// The kernel sits on the critical path of every call (sort -> tables -> solver): the plan is copied by all threads,
-// one thread per bin fetches the bin's range, and only the two short prefix sums are serial (in shared memory).
+// results from sorted order (where the solver stored them with coalesced writes) back to the caller's pair order:
+// thread i gathers its pair's results from position inv[i] (L2-resident for batches up to a few million pairs) and
+// writes them coalesced
+__global__ void k_unpermute(int64_t n, const int32_t* __restrict__ inv,
+                            const double* __restrict__ alpha_s, const double* __restrict__ x_s, const int32_t* __restrict__ status_s,
+                            const int32_t* __restrict__ iters_s, const double* __restrict__ mu_s,
+                            double* __restrict__ alpha, double* __restrict__ x, int32_t* __restrict__ status, int32_t* __restrict__ iters,
+                            double* __restrict__ mu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pos = inv[i];
+    if (pos < 0) continue;
+    alpha[i] = alpha_s[pos];
+    if (x) { x[3 * i] = x_s[3 * (int64_t)pos]; x[3 * i + 1] = x_s[3 * (int64_t)pos + 1]; x[3 * i + 2] = x_s[3 * (int64_t)pos + 2]; }
+    if (status) status[i] = status_s[pos];
+    if (iters) iters[i] = iters_s[pos];
+    if (mu) mu[i] = mu_s[pos];
+  }
+}
+
+// Instantiates the static per-tier launch plan (uploaded once by dcol_set_shapes; key ranges parked in begin[]/end[])
+// for this call — query parameters arrive as a kernel argument, bin offsets from the counting sort — so that neither a
+// host read of the histogram nor a host-to-device copy sits between the sort and the solver.  Also carves the
+// straggler overflow area: bin b gets tiles_b * spill_t records (a tile hands over at most spill_t pairs).
+// Called by every thread of a block (block-wide barriers inside); one thread per bin fetches the bin's range, only
+// the two short prefix sums are serial.
 constexpr int TABLE_THREADS = 64;
 static_assert(MAX_BINS <= TABLE_THREADS, "one thread per bin");
-__global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
-                               const int* __restrict__ off, double* ov_base, QueryParams P, int spill_div) {
-  __shared__ int s_nt[MAX_BINS];
-  __shared__ long long s_ovsz[MAX_BINS];
-  __shared__ long long s_ov;
+__device__ void build_tables_dev(const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
+                                 const int* __restrict__ off, double* ov_base, const QueryParams& P, int spill_div,
+                                 int* s_nt, long long* s_ovsz, long long* s_ov) {
   const int tid = threadIdx.x;
-  if (tid == 0) s_ov = 0;
+  if (tid == 0) *s_ov = 0;
   for (int t = 0; t < n_tiers; t++) {
     {
       const int* src = reinterpret_cast<const int*>(plan + t);
@@ -222,13 +258,13 @@ __global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable
     __syncthreads();
     if (tid == 0) {
       int tiles = 0;
-      long long ov = s_ov;
+      long long ov = *s_ov;
       for (int k = 0; k < n_bins; k++) {
         T.tile_prefix[k] = tiles; T.ov_off[k] = ov;
         tiles += s_nt[k]; ov += s_ovsz[k];
       }
       for (int k = n_bins; k <= MAX_BINS; k++) T.tile_prefix[k] = tiles;
-      s_ov = ov;
+      *s_ov = ov;
       const int pitch = T.P.row_pitch;
       T.P = P; T.P.row_pitch = pitch;
       T.spill_t = spill_t;
@@ -238,6 +274,98 @@ __global__ void k_build_tables(const LaunchTable* __restrict__ plan, LaunchTable
     __syncthreads();
   }
 }
+
+// single block: exclusive scan of hist[0..n_keys) -> off[0..n_keys], cursor = off; then the launch tables
+__global__ void k_scan_tables(const int* __restrict__ hist, int n_keys, int* __restrict__ off, int* __restrict__ cursor,
+                              const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
+                              double* ov_base, QueryParams P, int spill_div) {
+  __shared__ int part[1024];
+  __shared__ int s_nt[MAX_BINS];
+  __shared__ long long s_ovsz[MAX_BINS];
+  __shared__ long long s_ov;
+  int per = (n_keys + blockDim.x - 1) / blockDim.x;
+  int b = threadIdx.x * per, e = min(b + per, n_keys);
+  int s = 0;
+  for (int k = b; k < e; k++) s += hist[k];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < blockDim.x; d <<= 1) {
+    int v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int k = b; k < e; k++) { off[k] = run; cursor[k] = run; run += hist[k]; }
+  if (threadIdx.x == blockDim.x - 1) off[n_keys] = part[threadIdx.x];
+  __syncthreads();                       // off[] is read back by other threads of this block below
+  build_tables_dev(plan, tables, n_tiers, off, ov_base, P, spill_div, s_nt, s_ovsz, &s_ov);
+}
+
+// Small batches (n <= SMALL_MAX): histogram, scan, scatter + pack and the launch tables in ONE single-block kernel, so a
+// query is this launch plus one solver launch per shared-memory tier (no hand-over, hence no resume launch, and results
+// are stored at the caller's pair index directly: no un-permute pass).  Latency path of the single-pair drop-in calls
+// (src/proximity.jl:3-14 is what every reference example calls in its inner loop).
+constexpr int SMALL_MAX = 4096;
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_ITEMS = SMALL_MAX / SMALL_THREADS;
+__global__ void __launch_bounds__(SMALL_THREADS) k_small_prep(PairSource src, int n, const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap,
+                             int n_shapes, int n_keys, int* __restrict__ off, int* __restrict__ counters, int n_counters, int* __restrict__ bad,
+                             PairRec* __restrict__ recs, const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
+                             double* ov_base, QueryParams P) {
+  extern __shared__ int sh[];            // [0, n_keys]: counts, then exclusive offsets
+  __shared__ int part[SMALL_THREADS];
+  __shared__ int s_nt[MAX_BINS];
+  __shared__ long long s_ovsz[MAX_BINS];
+  __shared__ long long s_ov;
+  const int tid = threadIdx.x;
+  for (int k = tid; k <= n_keys; k += blockDim.x) sh[k] = 0;
+  for (int k = tid; k < n_counters; k += blockDim.x) counters[k] = 0;
+  if (tid == 0) *bad = 0;
+  __syncthreads();
+  int key[SMALL_ITEMS], rank[SMALL_ITEMS];
+#pragma unroll
+  for (int u = 0; u < SMALL_ITEMS; u++) {
+    const int i = u * blockDim.x + tid;
+    key[u] = -1;
+    if (i < n) {
+      const int s1 = src.shape1[i], s2 = src.shape2[i];
+      if ((unsigned)s1 < (unsigned)n_shapes && (unsigned)s2 < (unsigned)n_shapes) {
+        key[u] = pair_key(cls, keymap, n_shapes, s1, s2);
+        rank[u] = atomicAdd(&sh[key[u]], 1);
+      } else *bad = 1;
+    }
+  }
+  __syncthreads();
+  {  // exclusive scan of the counts, in place
+    const int per = (n_keys + blockDim.x - 1) / blockDim.x;
+    const int b = tid * per, e = min(b + per, n_keys);
+    int s = 0;
+    for (int k = b; k < e; k++) s += sh[k];
+    part[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < blockDim.x; d <<= 1) {
+      int v = (tid >= d) ? part[tid - d] : 0;
+      __syncthreads();
+      part[tid] += v;
+      __syncthreads();
+    }
+    int run = part[tid] - s;
+    for (int k = b; k < e; k++) { const int c = sh[k]; sh[k] = run; off[k] = run; run += c; }
+    if (tid == blockDim.x - 1) { sh[n_keys] = part[tid]; off[n_keys] = part[tid]; }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int u = 0; u < SMALL_ITEMS; u++) {
+    const int i = u * blockDim.x + tid;
+    if (i < n && key[u] >= 0) {
+      const int s1 = src.shape1[i], s2 = src.shape2[i];
+      pack_pair(src, i, s1, s2, cls[s1] > cls[s2], recs, sh[key[u]] + rank[u]);
+    }
+  }
+  build_tables_dev(plan, tables, n_tiers, off, ov_base, P, 0, s_nt, s_ovsz, &s_ov);
+}
+
 // resume-pass table of ONE tier from the overflow counts its previous pass left behind (launched right behind that
 // pass on the tier's stream, so the resume pass of one tier overlaps the first pass of the next); the resume pass may
 // itself hand its stragglers over (spill > 0) into the other overflow buffer, which reuses the previous layout
@@ -446,7 +574,7 @@ void dcol_destroy(dcol_ctx* ctx) {
     }
     if (L.h_bad) cudaFreeHost(L.h_bad);
     if (L.ev_end) cudaEventDestroy(L.ev_end);
-    DevBuf* lb[] = {&L.d_in, &L.d_out, &L.d_perm, &L.d_hist, &L.d_tables, &L.d_ov};
+    DevBuf* lb[] = {&L.d_in, &L.d_out, &L.d_recs, &L.d_inv, &L.d_sorted, &L.d_hist, &L.d_tables, &L.d_ov};
     for (DevBuf* b : lb) b->release();
   }
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
@@ -490,6 +618,23 @@ int dcol_host_unregister(dcol_ctx* ctx, void* ptr) {
     (void)cudaGetLastError();
     ctx->err = std::string("dcol_host_unregister: ") + cudaGetErrorString(e); return -2;
   }
+  return 0;
+}
+
+// Testing knob: iteration cap of the interior-point loop.  The reference hard-codes 50 (static_solver2.jl:132) and so does
+// every production call; a smaller cap lets a test land a pair's convergence exactly on the last allowed step.
+int dcol_set_max_iters(dcol_ctx* ctx, int max_iters) {
+  if (!ctx) return -1;
+  if (max_iters < 1 || max_iters > MAX_ITERS) { ctx->err = "dcol_set_max_iters: 1..50"; return -1; }
+  ctx->max_iters = max_iters;
+  return 0;
+}
+// Optional per-pair output of the duality measure mu = s'z/deg at the iteration that ended the solve (the quantity the
+// reference's verbose mode prints, static_solver2.jl:179-183).  mu lives where the following queries' outputs live (host
+// pointer for DCOL_MEM_HOST calls, device pointer otherwise) and must hold n doubles; NULL switches it off.
+int dcol_set_mu_output(dcol_ctx* ctx, double* mu) {
+  if (!ctx) return -1;
+  ctx->mu_out = mu;
   return 0;
 }
 
@@ -620,7 +765,9 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   // capacity a pair of that class pair can need; inside a tier the heaviest class pairs are queued first
   ctx->tiers.clear();
   {
-    static const int tier_cap[] = {8, 16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 4};
+    // Row capacities of the shared-memory tiers.  Up to 16 rows per pair two 4-warp CTAs fit an SM (the register limit's
+    // 8 warps), so everything up to there is ONE tier = one first-pass and one resume launch (one tail instead of two).
+    static const int tier_cap[] = {16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 8};
     constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
     bool present[NCLS] = {};
     for (int i = 0; i < n_shapes; i++) present[cls[i]] = true;
@@ -649,7 +796,7 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
         T.ov_stride[k] = 3 + 4 + cls_ne(c1) + cls_ne(c2) + 2 * (ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]) + 2 * (cls_d(c1) + cls_d(c2));
         T.max_stride = std::max(T.max_stride, T.ov_stride[k]);
       }
-      T.pitch = (12 + T.rows_cap * NFIELD) | 1; // relative pose (12) + rows; odd pitch: conflict-free 64-bit shared-memory accesses
+      T.pitch = (POSE_SLOTS + T.rows_cap * NFIELD) | 1; // pose slots + rows; odd pitch: conflict-free 64-bit shared-memory accesses
       // 8 warps per SM (255 registers per thread).  Two CTAs of 4 warps when the row stores of both fit: each CTA is
       // its own lockstep group, so one computes while the other sits in the exposed latency of a tile's first gathers
       // and last scatters (measured -3..5 % against one CTA of 8 warps; 4 x 2 and 8 x 1 warps are slower again: fewer
@@ -771,8 +918,15 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   constexpr int MAX_LEVELS = 3;                                     // resume passes after the first pass
   const size_t hist_ints = 3 * (size_t)nk + 16 + (2 + MAX_LEVELS) * NSIDE;   // hist | off | cursor | bad | tile counters per pass and tier
   const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
-  CK(L.d_perm.need(sizeof(int32_t) * n));
   CK(L.d_hist.need(sizeof(int) * hist_stride * nchunks));
+  const bool small = (n <= SMALL_MAX) && nchunks == 1;      // single-block preparation, no hand-over, direct result stores
+  int max_block = 32;
+  for (int t = 0; t < nt_tiers; t++) max_block = std::max(max_block, ctx->tiers[t].block);
+  CK(L.d_recs.need(sizeof(PairRec) * ((size_t)n + max_block)));      // one tile of slack behind the last record
+  if (!small) {
+    CK(L.d_inv.need(sizeof(int32_t) * n));
+    CK(L.d_sorted.need((size_t)n * (8 + 24 + 4 + 4 + 8) + 5 * 256));
+  }
   CK(L.d_tables.need(sizeof(LaunchTable) * (1 + MAX_LEVELS) * std::max(1, nt_tiers) * nchunks));
   // straggler overflow area per chunk (upper bound: every tile hands over spill_t pairs of the widest record)
   int spill_div = 8;
@@ -781,7 +935,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (const char* e = getenv("DCOL_LEVELS")) levels = std::max(1, std::min(MAX_LEVELS, atoi(e)));
   const int64_t chunk_max = (nchunks > 1) ? (n + nchunks - 2) / (nchunks - 1) : n;
   size_t ov_doubles = 0;
-  for (int t = 0; t < nt_tiers; t++) {
+  for (int t = 0; t < nt_tiers && !small; t++) {
     const dcol_ctx::Tier& TR = ctx->tiers[t];
     const int spill_t = spill_div > 0 ? TR.block / spill_div : 0;
     ov_doubles += (size_t)(chunk_max / TR.block + TR.n_bins + 1) * spill_t * TR.max_stride;
@@ -790,7 +944,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   CK(L.d_ov.need(sizeof(double) * std::max<size_t>(ov_doubles, 32) * 2 * nchunks));
 
   size_t o_s1 = 0, o_s2 = 0, o_r1 = 0, o_a1 = 0, o_r2 = 0, o_a2 = 0;
-  size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0;
+  size_t o_alpha = 0, o_x = 0, o_der = 0, o_st = 0, o_it = 0, o_mu = 0;
   char* di = nullptr; char* dout = nullptr;
   size_t o_p1 = 0, o_p2 = 0;
   const int64_t rows1 = indexed ? np1 : n, rows2 = indexed ? np2 : n;
@@ -814,6 +968,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     o_der = b; b += align256(sizeof(double) * dsz * n);
     o_st = b; b += align256(sizeof(int32_t) * n);
     o_it = b; b += align256(sizeof(int32_t) * n);
+    o_mu = b; b += align256(sizeof(double) * (ctx->mu_out ? n : 0));
     CK(L.d_out.need(b));
     dout = (char*)L.d_out.p;
   }
@@ -843,7 +998,10 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     QueryParams P;
     memset(&P, 0, sizeof(P));
     P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
-    P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query;
+    P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query; P.max_iters = ctx->max_iters; P.direct = small ? 1 : 0;
+    PairSource src;
+    memset(&src, 0, sizeof(src));
+    src.na = na;
     if (in_mem == DCOL_MEM_HOST) {
       cudaStream_t SI = piped ? ctx->s_copy : S;
       CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
@@ -858,48 +1016,73 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
         CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
       }
       if (piped) { CK(cudaEventRecord(L.ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, L.ev_in[c], 0)); }
-      P.shape1 = (const int32_t*)(di + o_s1) + c0; P.shape2 = (const int32_t*)(di + o_s2) + c0;
+      src.shape1 = (const int32_t*)(di + o_s1) + c0; src.shape2 = (const int32_t*)(di + o_s2) + c0;
       if (indexed) {
-        P.pose1 = (const int32_t*)(di + o_p1) + c0; P.pose2 = (const int32_t*)(di + o_p2) + c0;
-        P.r1 = (const double*)(di + o_r1); P.att1 = (const double*)(di + o_a1);
-        P.r2 = (const double*)(di + o_r2); P.att2 = (const double*)(di + o_a2);
+        src.pose1 = (const int32_t*)(di + o_p1) + c0; src.pose2 = (const int32_t*)(di + o_p2) + c0;
+        src.r1 = (const double*)(di + o_r1); src.att1 = (const double*)(di + o_a1);
+        src.r2 = (const double*)(di + o_r2); src.att2 = (const double*)(di + o_a2);
       } else {
-        P.r1 = (const double*)(di + o_r1) + 3 * c0; P.att1 = (const double*)(di + o_a1) + na * c0;
-        P.r2 = (const double*)(di + o_r2) + 3 * c0; P.att2 = (const double*)(di + o_a2) + na * c0;
+        src.r1 = (const double*)(di + o_r1) + 3 * c0; src.att1 = (const double*)(di + o_a1) + na * c0;
+        src.r2 = (const double*)(di + o_r2) + 3 * c0; src.att2 = (const double*)(di + o_a2) + na * c0;
       }
     } else {
-      P.shape1 = shape1 + c0; P.shape2 = shape2 + c0;
-      if (indexed) { P.pose1 = pose1 + c0; P.pose2 = pose2 + c0; P.r1 = r1; P.att1 = att1; P.r2 = r2; P.att2 = att2; }
-      else { P.r1 = r1 + 3 * c0; P.att1 = att1 + na * c0; P.r2 = r2 + 3 * c0; P.att2 = att2 + na * c0; }
+      src.shape1 = shape1 + c0; src.shape2 = shape2 + c0;
+      if (indexed) { src.pose1 = pose1 + c0; src.pose2 = pose2 + c0; src.r1 = r1; src.att1 = att1; src.r2 = r2; src.att2 = att2; }
+      else { src.r1 = r1 + 3 * c0; src.att1 = att1 + na * c0; src.r2 = r2 + 3 * c0; src.att2 = att2 + na * c0; }
     }
+    // where the caller's results of this chunk go (caller order): the caller's device arrays or the D2H staging area
+    double* f_alpha; double* f_x; double* f_der; int32_t* f_st; int32_t* f_it; double* f_mu = nullptr;
     if (mem == DCOL_MEM_HOST) {
-      P.alpha = (double*)(dout + o_alpha) + c0; P.x = (double*)(dout + o_x) + 3 * c0;
-      P.deriv = dsz ? (double*)(dout + o_der) + dsz * c0 : nullptr;
-      P.status = (int32_t*)(dout + o_st) + c0; P.iters = (int32_t*)(dout + o_it) + c0;
+      f_alpha = (double*)(dout + o_alpha) + c0; f_x = (double*)(dout + o_x) + 3 * c0;
+      f_der = dsz ? (double*)(dout + o_der) + dsz * c0 : nullptr;
+      f_st = (int32_t*)(dout + o_st) + c0; f_it = (int32_t*)(dout + o_it) + c0;
+      if (ctx->mu_out) f_mu = (double*)(dout + o_mu) + c0;
     } else {
-      P.alpha = alpha + c0; P.x = x ? x + 3 * c0 : nullptr; P.deriv = deriv ? deriv + dsz * c0 : nullptr;
-      P.status = status ? status + c0 : nullptr; P.iters = iters ? iters + c0 : nullptr;
+      f_alpha = alpha + c0; f_x = x ? x + 3 * c0 : nullptr; f_der = deriv ? deriv + dsz * c0 : nullptr;
+      f_st = status ? status + c0 : nullptr; f_it = iters ? iters + c0 : nullptr;
+      if (ctx->mu_out) f_mu = ctx->mu_out + c0;
     }
-    // ---- bin the chunk's pairs by key (device counting sort), build the tile tables on the device
+    // the solver stores the per-pair scalars in SORTED order (coalesced); k_unpermute brings them into caller order.
+    // Derivative rows (120-488 contiguous bytes per pair) go to their final place directly.
+    PairRec* d_recs = (PairRec*)L.d_recs.p + c0;
+    int32_t* d_inv = small ? nullptr : (int32_t*)L.d_inv.p + c0;
+    double* s_alpha = nullptr; double* s_x = nullptr; int32_t* s_st = nullptr; int32_t* s_it = nullptr; double* s_mu = nullptr;
+    if (small) {
+      P.alpha = f_alpha; P.x = f_x; P.status = f_st; P.iters = f_it; P.mu = f_mu;
+    } else {
+      char* sb = (char*)L.d_sorted.p;
+      const size_t nn = (size_t)n;
+      s_alpha = (double*)sb + c0; sb += align256(8 * nn);
+      s_x = (double*)sb + 3 * c0; sb += align256(24 * nn);
+      s_mu = (double*)sb + c0; sb += align256(8 * nn);
+      s_st = (int32_t*)sb + c0; sb += align256(4 * nn);
+      s_it = (int32_t*)sb + c0;
+      P.alpha = s_alpha; P.x = f_x ? s_x : nullptr; P.status = f_st ? s_st : nullptr; P.iters = f_it ? s_it : nullptr; P.mu = f_mu ? s_mu : nullptr;
+    }
+    P.deriv = f_der;
+    P.recs = d_recs;
+    // ---- bin the chunk's pairs by key (device counting sort), pack them in sorted order, build the tile tables on the device
     int* d_hist = (int*)L.d_hist.p + hist_stride * c;
     int* d_off = d_hist + nk;            // nk+1
     int* d_cursor = d_off + nk + 1;      // nk
     int* d_bad = d_cursor + nk;          // 1
-    int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier
-    int32_t* d_perm = (int32_t*)L.d_perm.p + c0;
+    int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier and pass
     LaunchTable* d_tab = (LaunchTable*)L.d_tables.p + (size_t)(1 + MAX_LEVELS) * std::max(1, nt_tiers) * c;
     double* d_ovc = (double*)L.d_ov.p + 2 * ov_doubles * c;
-    P.perm = d_perm;
-    CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
     const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
-    {
+    if (small) {
+      k_small_prep<<<1, SMALL_THREADS, sizeof(int) * (nk + 1), SC>>>(src, (int)nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk,
+                                                                      d_off, d_counter, (2 + MAX_LEVELS) * NSIDE, d_bad, d_recs,
+                                                                      (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P);
+      ctx->launches += 1;
+    } else {
+      CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
       int threads = 256;
       int blocks = (int)std::min<int64_t>((nc + threads * 8 - 1) / (threads * 8), 1184);
-      k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
-      k_scan<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor);
-      k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(P.shape1, P.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_perm);
-      k_build_tables<<<1, TABLE_THREADS, 0, SC>>>((const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_off, d_ovc, P, spill_div);
-      ctx->launches += 4;
+      k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(src.shape1, src.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
+      k_scan_tables<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor, (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P, spill_div);
+      k_scatter_pack<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_recs, d_inv);
+      ctx->launches += 3;
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table
     CK(cudaEventRecord(L.ev_t0[c], SC));
@@ -912,7 +1095,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
       CK(launch_persistent(jac, TR.grid[jac], TR.block, TR.smem, st, d_tab + t, d_counter + t));
       ctx->launches++;
-      for (int lv = 1; lv <= levels && spill_div > 0; lv++) {
+      for (int lv = 1; lv <= levels && spill_div > 0 && !small; lv++) {
         LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers) + t;
         LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers) + t;
         k_build_tables2<<<1, TABLE_THREADS, 0, st>>>(prev, cur, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
@@ -920,6 +1103,11 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
         ctx->launches += 2;
       }
       if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
+    }
+    if (!small) {
+      const int blocks = (int)std::min<int64_t>((nc + 255) / 256, 148 * 16);
+      k_unpermute<<<blocks, 256, 0, SC>>>(nc, d_inv, s_alpha, s_x, s_st, s_it, s_mu, f_alpha, f_x, f_st, f_it, f_mu);
+      ctx->launches += 1;
     }
     CK(cudaEventRecord(L.ev_t1[c], SC));
     // ---- results of this chunk back (host mode), overlapping the next chunk's kernels
@@ -931,6 +1119,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (dsz) CK(cudaMemcpyAsync(deriv + dsz * c0, dout + o_der + sizeof(double) * dsz * c0, sizeof(double) * dsz * nc, cudaMemcpyDeviceToHost, SO));
       if (status) CK(cudaMemcpyAsync(status + c0, dout + o_st + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
       if (iters) CK(cudaMemcpyAsync(iters + c0, dout + o_it + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
+      if (ctx->mu_out) CK(cudaMemcpyAsync(ctx->mu_out + c0, dout + o_mu + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
     }
   }
   // ---- the bad-shape flags come back with the results; the join is finish_query (the only host synchronisation)

@@ -53,23 +53,36 @@ struct DevShape {
 
 constexpr int MAX_ITERS = 50;   // static_solver2.jl:132
 constexpr int NFIELD = 5;       // per-row shared-memory fields
+constexpr int POSE_SLOTS = 24;  // per-thread shared-memory slots ahead of the rows: relative pose R (9) | t (3) | primitive 1's frame Q (9) | r~ (3)
 enum { F_S = 0, F_Z = 1, F_R = 2, F_RZ = 3, F_P = 4 };   // s, z, 1/(s z), rz | ds, p | dz
+
+// One pair, packed by the binning pass at its SORTED position (dcol_capi.cu, k_scatter_pack): 128 bytes = one cache
+// line per pair, so the solver's loads touch every fetched byte and the binning pass writes whole lines.  A pair whose
+// classes arrive as (hi, lo) is stored with its two primitives exchanged (DCOL_REC_SWAPPED): the solver always sees
+// class(prim 1) <= class(prim 2) and only the derivative epilogue looks at the flag (column placement).
+struct alignas(16) PairRec {
+  double r1[3], a1[4];             // pose of the record's first primitive (a1[3] unused for MRPs)
+  double r2[3], a2[4];
+  int32_t s1, s2;                  // shape-table rows
+  int32_t pair;                    // the caller's pair index
+  int32_t flags;
+};
+static_assert(sizeof(PairRec) == 128, "one cache line per pair");
+enum { DCOL_REC_SWAPPED = 1 };
 
 struct QueryParams {
   const DevShape* shapes;
   const double* rows;            // packed row constants
-  const int32_t* perm;           // sorted position -> pair index
-  const int32_t* shape1;
-  const int32_t* shape2;
-  const int32_t* pose1;          // optional: row of (r1, att1) used by the pair; NULL = the pair's own row
-  const int32_t* pose2;
-  const double* r1;  const double* att1;
-  const double* r2;  const double* att2;
+  const PairRec* recs;           // packed pairs in sorted order (first pass: tile position; resume: position kept in the hand-over record)
   int att_kind;                  // 0 quaternion (stride 4), 1 MRP (stride 3)
   int row_pitch;                 // doubles of shared-memory row store per thread (odd)
+  int max_iters;                 // 50 (static_solver2.jl:132); smaller only through the testing knob dcol_set_max_iters
+  int direct;                    // 1: alpha/x/status/iters/mu are indexed by the caller's pair index (small batches: no un-permute pass),
+                                 // 0: by sorted position (coalesced stores; k_unpermute brings them into the caller's order)
   double pdip_tol;
   double* alpha; double* x; int32_t* status; int32_t* iters;
-  double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major
+  double* mu;                    // optional: duality measure s'z/deg at the iteration that ended the solve
+  double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major; always at the caller's pair index
   int query;
 };
 

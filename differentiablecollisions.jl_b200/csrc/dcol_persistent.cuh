@@ -17,6 +17,9 @@
 #ifndef DCOL_MAXTHREADS
 #define DCOL_MAXTHREADS 256
 #endif
+#ifndef DCOL_MINBLOCKS
+#define DCOL_MINBLOCKS 1
+#endif
 #ifndef DCOL_INLINE
 #define DCOL_INLINE 0
 #endif
@@ -45,7 +48,7 @@ __device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, const 
 }
 
 template <int VAR>
-__global__ void __launch_bounds__(DCOL_MAXTHREADS, 1) proximity_persistent(LaunchTable* __restrict__ tt, int* __restrict__ counter) {
+__global__ void __launch_bounds__(DCOL_MAXTHREADS, DCOL_MINBLOCKS) proximity_persistent(LaunchTable* __restrict__ tt, int* __restrict__ counter) {
   __shared__ int s_tile;
   const int n_tiles = tt->n_tiles;
   const int tile_sz = blockDim.x;

@@ -67,7 +67,6 @@ extern __shared__ double dcol_dyn_smem[];
 // Each thread owns a contiguous run of `pitch` doubles (pitch odd, >= rows_cap*NFIELD): field f of row i is at
 // [threadIdx.x*pitch + i*NFIELD + f], so the field offset folds into the LDS/STS immediate and only the row index
 // costs an address instruction; an odd pitch spreads the 16 lanes of a 64-bit wavefront over all banks.
-constexpr int POSE_SLOTS = 12;     // relative pose R (9, row-major) and t (3) of the pair, ahead of the rows
 struct RowStore {
   double* base;
   __device__ __forceinline__ double& operator()(int f, int i) const { return base[POSE_SLOTS + i * NFIELD + f]; }
@@ -76,6 +75,8 @@ struct RowStore {
 // (LDS with immediate offsets) instead of 24 registers that the allocator would otherwise spill to local memory.
 struct RelPoseR { const double* p; __device__ __forceinline__ const double* operator[](int a) const { return p + 3 * a; } };
 struct RelPoseT { const double* p; __device__ __forceinline__ double operator[](int a) const { return p[9 + a]; } };
+// Slots 12..23 keep primitive 1's world frame (Q row-major, r~) for the output / derivative epilogue, which would
+// otherwise rebuild it from the pose in global memory after the loop (a dependent L2 round trip per tile).
 
 // ---------------------------------------------------------------------------
 // small dense helpers (upper-triangular storage in full arrays; fully unrolled)
@@ -735,6 +736,17 @@ struct PairMap {
   }
 };
 
+// primitive 2's world frame from primitive 1's and the relative pose: R = Q2'Q1, t = Q2'(r~1 - r~2)  =>  Q2 = Q1 R', r~2 = r~1 - Q2 t
+template <class RM, class TV>
+__device__ __forceinline__ void frame2_from_relative(const Frame& F1, const RM& R, const TV& t, Frame& F2) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) F2.Q[i][j] = F1.Q[i][0] * R[j][0] + F1.Q[i][1] * R[j][1] + F1.Q[i][2] * R[j][2];
+#pragma unroll
+  for (int i = 0; i < 3; i++) F2.r[i] = F1.r[i] - (F2.Q[i][0] * t[0] + F2.Q[i][1] * t[1] + F2.Q[i][2] * t[2]);
+}
+
 // One pair: relative pose -> initial point -> PDIP loop -> outputs (+ derivative epilogue).
 // VAR (= the query kind: Q_PROX, Q_GRAD, Q_JAC) selects the kernel variant: the proximity variant carries no epilogue,
 // the gradient variant the small envelope-theorem epilogue, the Jacobian variant the implicit-function-theorem one
@@ -745,35 +757,35 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   using PM = PairMap<P1::NE, P2::NE>;
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
 
-  // first pass: idx is a position of the sorted pair list; resume pass: idx is a slot of the bin's overflow list
-  // Only class pairs (C1 <= C2) are instantiated: a pair whose classes arrive in the other order is solved with its two
+  // first pass: idx is a position of the sorted, packed pair list; resume pass: idx is a slot of the bin's overflow
+  // list, whose first field is the pair's sorted position.
+  // Only class pairs (C1 <= C2) are instantiated: a pair whose classes arrive in the other order was packed with its two
   // primitives exchanged (alpha and the world point x do not depend on the order; the derivative blocks are written to
-  // the columns of the primitive they belong to).  The counting sort marks such pairs in bit 31 of the pair index.
-  const int praw = (tc.mode == 0) ? p.perm[idx] : (int)tc.in[idx];
-  const bool swp = praw < 0;
-  const int pair = praw & 0x7fffffff;
-  const DevShape* S1 = p.shapes + (swp ? p.shape2 : p.shape1)[pair];
-  const DevShape* S2 = p.shapes + (swp ? p.shape1 : p.shape2)[pair];
-  const int32_t* const ip1 = swp ? p.pose2 : p.pose1; const int32_t* const ip2 = swp ? p.pose1 : p.pose2;
-  const double* const gr1 = swp ? p.r2 : p.r1; const double* const ga1 = swp ? p.att2 : p.att1;
-  const double* const gr2 = swp ? p.r1 : p.r2; const double* const ga2 = swp ? p.att1 : p.att2;
+  // the columns of the primitive they belong to).
+  const int pos = (tc.mode == 0) ? idx : (int)tc.in[idx];
+  const PairRec* const rec = p.recs + pos;
   const int na = (p.att_kind == 0) ? 4 : 3;
-  // pose rows: the pair's own row, or a row of a pose table (indexed queries: scenes, trajectory batches)
-  const int64_t i1 = ip1 ? (int64_t)ip1[pair] : (int64_t)pair;
-  const int64_t i2 = ip2 ? (int64_t)ip2[pair] : (int64_t)pair;
 
   RowStore rs{dcol_dyn_smem + (size_t)threadIdx.x * p.row_pitch};
-  // Both poses are fetched up front (14 independent loads in flight at once): all warps of the CTA start a tile
-  // together, so a chain of dependent gathers through the out-of-line build_frame calls would leave the SM idle
-  // for several DRAM round trips per tile (ncu: build_frame held 11 % of the stall samples with 2 % of the instructions).
+  // The whole record is fetched up front (eight independent 16-byte loads of one cache line in flight at once): all
+  // warps of the CTA start a tile together, so a chain of dependent loads would leave the SM idle for several DRAM round
+  // trips per tile.
   double pose[14];
+  int s1i, s2i, pair, rflags;
   {
-    const double* g1 = gr1 + 3 * i1; const double* h1 = ga1 + na * i1;
-    const double* g2 = gr2 + 3 * i2; const double* h2 = ga2 + na * i2;
+    const double2* q = reinterpret_cast<const double2*>(rec);
+    double2 v[8];
 #pragma unroll
-    for (int a = 0; a < 3; a++) { pose[a] = __ldg(g1 + a); pose[3 + a] = __ldg(h1 + a); pose[7 + a] = __ldg(g2 + a); pose[10 + a] = __ldg(h2 + a); }
-    pose[6] = (na == 4) ? __ldg(h1 + 3) : 0.0; pose[13] = (na == 4) ? __ldg(h2 + 3) : 0.0;
+    for (int a = 0; a < 8; a++) v[a] = __ldg(q + a);
+#pragma unroll
+    for (int a = 0; a < 7; a++) { pose[2 * a] = v[a].x; pose[2 * a + 1] = v[a].y; }
+    s1i = __double2loint(v[7].x); s2i = __double2hiint(v[7].x);
+    pair = __double2loint(v[7].y); rflags = __double2hiint(v[7].y);
   }
+  const bool swp = (rflags & DCOL_REC_SWAPPED) != 0;
+  const DevShape* S1 = p.shapes + s1i;
+  const DevShape* S2 = p.shapes + s2i;
+  const int64_t oi = p.direct ? (int64_t)pair : (int64_t)pos;      // index of the scalar outputs
   P1 A; P2 B;
   A.load(S1, p.rows, 0);
   B.load(S2, p.rows, A.n);
@@ -791,10 +803,10 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
 #pragma unroll
       for (int b = 0; b < 3; b++) R[a][b] = F2.Q[0][a] * F1.Q[0][b] + F2.Q[1][a] * F1.Q[1][b] + F2.Q[2][a] * F1.Q[2][b];
     }
-  #pragma unroll
-    for (int a = 0; a < 3; a++) { rs.base[9 + a] = t[a];
 #pragma unroll
-      for (int b = 0; b < 3; b++) rs.base[3 * a + b] = R[a][b]; }
+    for (int a = 0; a < 3; a++) { rs.base[9 + a] = t[a]; rs.base[21 + a] = F1.r[a];
+#pragma unroll
+      for (int b = 0; b < 3; b++) { rs.base[3 * a + b] = R[a][b]; rs.base[12 + 3 * a + b] = F1.Q[a][b]; } }
   }
   const RelPoseR R{rs.base};
   const RelPoseT t{rs.base};
@@ -841,7 +853,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     if (!ok) status = ST_NUMERICAL;
   } else {
     // ---------------- resume: reload the iterate parked by the first pass ----------------
-    // record layout (field-major, stride = the bin's record capacity): pair, k, s.z, y[NX], rows s, rows z, SOC s|z of
+    // record layout (field-major, stride = the bin's record capacity): sorted position, k, s.z, y[NX], rows s, rows z, SOC s|z of
     // prim 1, SOC s|z of prim 2; read with one walking pointer (no per-field 64-bit index arithmetic)
     const int64_t st = tc.in_cap;
     const double* q = tc.in + idx + st;
@@ -873,6 +885,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   // the unrolled loop body is far larger than the SM's instruction cache, and warps in lockstep
   // share each fetched instruction line instead of streaming the loop once per warp.
   int it = 0;
+  // loop invariants fetched once (a load behind the block-wide vote of every iteration sat on the critical path)
+  const double tol = p.pdip_tol;
+  const int max_it = p.max_iters, spill_t = tc.spill_t;
   bool active = (status == ST_OK) && !tc.dup;
   bool parked = tc.dup != 0;                // duplicate lanes write nothing
   if (active) status = ST_PDIP_FAILED;
@@ -881,20 +896,20 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     if (active) {
       // the reference tests mu only at the START of iterations 1..50 (static_solver2.jl:132,143-146) and raises
       // "pdip failed" after the 50th step without another test (:188): a pair that would pass on its 50th step fails
-      if (k == MAX_ITERS) { active = false; it = k; }
+      if (k >= max_it) { active = false; it = k; }
       else if (!(mu == mu)) { status = ST_NUMERICAL; active = false; it = k; }
-      else if (mu < p.pdip_tol) { status = ST_OK; active = false; it = k; }
+      else if (mu < tol) { status = ST_OK; active = false; it = k; }
     }
     const int n_act = DCOL_COUNT(active);
     if (n_act == 0) break;
-    if (n_act <= tc.spill_t && k > k0) {
+    if (n_act <= spill_t && k > k0) {
       // few stragglers left in this tile: park their iterates for the resume pass instead of keeping the whole CTA
       // (and its idle lanes) in the loop until the slowest pair converges
       if (active) {
         const int slot = atomicAdd(tc.ov_count, 1);
         const int64_t st = tc.ov_cap;
         double* q = tc.ov + slot;
-        q[0] = (double)praw; q += st;
+        q[0] = (double)pos; q += st;
         q[0] = (double)k; q += st;
         q[0] = sz; q += st;
 #pragma unroll
@@ -979,13 +994,17 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
 
   // ---------------- outputs ----------------
   Frame F1, F2;
-  build_frame(S1, gr1 + 3 * i1, ga1 + na * i1, p.att_kind, F1);
-  p.alpha[pair] = y[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) { F1.r[a] = rs.base[21 + a];
+#pragma unroll
+    for (int b = 0; b < 3; b++) F1.Q[a][b] = rs.base[12 + 3 * a + b]; }
+  p.alpha[oi] = y[3];
   if (p.x) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) p.x[3 * (int64_t)pair + a] = F1.r[a] + F1.Q[a][0] * y[0] + F1.Q[a][1] * y[1] + F1.Q[a][2] * y[2];
+    for (int a = 0; a < 3; a++) p.x[3 * oi + a] = F1.r[a] + F1.Q[a][0] * y[0] + F1.Q[a][1] * y[1] + F1.Q[a][2] * y[2];
   }
-  if (p.iters) p.iters[pair] = it;
+  if (p.iters) p.iters[oi] = it;
+  if (p.mu) p.mu[oi] = sz * inv_deg;
   const int nt = 6 + 2 * na;
 
   if constexpr (VAR == Q_GRAD) {
@@ -993,13 +1012,13 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     {
       double* g = p.deriv + (int64_t)nt * pair;
       if (status == ST_OK) {
-        build_frame(S2, gr2 + 3 * i2, ga2 + na * i2, p.att_kind, F2);
+        frame2_from_relative(F1, R, t, F2);
         double y1[NV1], y2[NV2];
         PM::to_local(y, R, t, true, y1, y2);
         SideVecs V1, V2;
         A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
-        grad_side(S1, F1, ga1 + na * i1, p.att_kind, V1, g + (swp ? 3 + na : 0));
-        grad_side(S2, F2, ga2 + na * i2, p.att_kind, V2, g + (swp ? 0 : 3 + na));
+        grad_side(S1, F1, rec->a1, p.att_kind, V1, g + (swp ? 3 + na : 0));
+        grad_side(S2, F2, rec->a2, p.att_kind, V2, g + (swp ? 0 : 3 + na));
       } else {
         for (int j = 0; j < nt; j++) g[j] = __longlong_as_double(0x7ff8000000000000LL);
       }
@@ -1010,7 +1029,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     double* Jo = p.deriv + (int64_t)4 * nt * pair;
     bool ok = (status == ST_OK);
     if (ok) {
-      build_frame(S2, gr2 + 3 * i2, ga2 + na * i2, p.att_kind, F2);
+      frame2_from_relative(F1, R, t, F2);
       double K1[4][3], K2[4][3], Kb1[4][3], Kb2[4][3], Ye1[4][2], Ye2[4][2], Hw[4][3];
       SideVecs V1, V2;
       {
@@ -1099,15 +1118,15 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
         }
       }
       if (ok) {
-        jac_side<P1::NE>(S1, F1, ga1 + na * i1, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo + (swp ? 4 * (3 + na) : 0));
-        jac_side<P2::NE>(S2, F2, ga2 + na * i2, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + (swp ? 0 : 4 * (3 + na)));
+        jac_side<P1::NE>(S1, F1, rec->a1, p.att_kind, K1, Kb1, Ye1, Hw, V1, Jo + (swp ? 4 * (3 + na) : 0));
+        jac_side<P2::NE>(S2, F2, rec->a2, p.att_kind, K2, Kb2, Ye2, Hw, V2, Jo + (swp ? 0 : 4 * (3 + na)));
       } else {
         status = ST_NUMERICAL;
       }
     }
     if (!ok) for (int j = 0; j < 4 * nt; j++) Jo[j] = __longlong_as_double(0x7ff8000000000000LL);
   }
-  if (p.status) p.status[pair] = status;
+  if (p.status) p.status[oi] = status;
 }
 
 // Out-of-line entry of one specialisation (same translation unit as the persistent kernel that calls it,

@@ -177,6 +177,17 @@ int dcol_wait(dcol_ctx* ctx, int ticket);
 int dcol_host_register(dcol_ctx* ctx, void* ptr, int64_t bytes);
 int dcol_host_unregister(dcol_ctx* ctx, void* ptr);
 
+/* ---- solver diagnostics ------------------------------------------------------------------------------------
+ * dcol_set_mu_output: optional per-pair output of the duality measure mu = s'z/deg at the iteration that ended the
+ * solve (what the reference's verbose mode prints per iteration, src/solvers/coneqp/static_solver2.jl:117-120,
+ * 179-183; verbose printing itself is not reproduced).  `mu` must hold one double per pair of the following queries and
+ * live where their outputs live (host memory for DCOL_MEM_HOST calls, device memory otherwise); NULL switches it off.
+ * dcol_set_max_iters: TESTING knob for the iteration cap, 1..50.  The reference hard-codes 50 (static_solver2.jl:132)
+ * and raises "pdip failed" after the 50th step WITHOUT testing mu again (:188); a smaller cap lets a test land a pair's
+ * convergence exactly on the last allowed step.  Every new context starts at 50. */
+int dcol_set_mu_output(dcol_ctx* ctx, double* mu);
+int dcol_set_max_iters(dcol_ctx* ctx, int max_iters);
+
 /* Instrumentation for bench.py / tests. */
 /* kernels launched by this context since creation (solver + derivative + binning kernels) */
 int64_t dcol_launch_count(const dcol_ctx* ctx);

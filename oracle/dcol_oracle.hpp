@@ -504,7 +504,10 @@ inline bool initialize(const Problem<double>& P, const Cone& K, Solution& S) {  
   return true;
 }
 
-inline void solve_socp(const Problem<double>& P, double pdip_tol, Solution& S, int max_iters = 50) {  // :106-191
+// iteration cap: 50 in the reference (:132).  Tests lower it (together with dcol_set_max_iters on the CUDA side) to land a
+// pair's convergence exactly on the last allowed step: the reference raises "pdip failed" (:188) without testing mu again.
+inline int& max_iters_setting() { static int v = 50; return v; }
+inline void solve_socp(const Problem<double>& P, double pdip_tol, Solution& S, int max_iters = max_iters_setting()) {  // :106-191
   Cone K{P.n_ort, P.d1, P.d2};
   int nx = P.nx, ns = P.ns;
   S.nx = nx; S.ns = ns; S.iters = 0; S.status = ST_OK;

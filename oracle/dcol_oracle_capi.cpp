@@ -45,6 +45,7 @@ extern "C" {
 
 int dcol_oracle_max_threads() { return hw_threads(); }
 int dcol_oracle_max_faces() { return MAXF; }
+void dcol_oracle_set_max_iters(int k) { max_iters_setting() = (k >= 1 && k <= 50) ? k : 50; }
 
 // kind: 0 proximity, 1 gradient, 2 jacobian, 3 jacobian_slow (quaternion only in the reference, src/proximity.jl:154,198)
 int dcol_oracle_query(int kind, int n_shapes, const int32_t* type, const int64_t* param_off, const double* params,

@@ -50,6 +50,11 @@ def max_threads():
     return int(lib().dcol_oracle_max_threads())
 
 
+def set_max_iters(k=50):
+    """Iteration cap of solve_socp (50 in the reference); see dcol_oracle.hpp max_iters_setting."""
+    lib().dcol_oracle_set_max_iters(C.c_int(int(k)))
+
+
 def query(kind, table_arrays, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol=1e-6, nthreads=0):
     """kind: 0 proximity, 1 gradient, 2 jacobian, 3 jacobian_slow.  Returns dict of arrays.
     J is returned as (n, 4, ntheta) (converted from the column-major ABI layout)."""
@@ -101,7 +106,7 @@ def pair_problem(prim1, prim2):
     """(c, G, h, n_ort, d1, d2) for two host primitives at their current poses."""
     p1 = _f64(prim1.packed()); p2 = _f64(prim2.packed())
     dims = np.zeros(5, dtype=np.int32)
-    G = np.zeros(72 * 8); h = np.zeros(72); c = np.zeros(8)
+    G = np.zeros(264 * 8); h = np.zeros(264); c = np.zeros(8)
     rc = lib().dcol_oracle_pair_problem(C.c_int(prim1.shape_type), _p(p1, _dp), C.c_int(prim2.shape_type), _p(p2, _dp),
                                         _p(_f64(prim1.r), _dp), _p(_f64(prim1.att), _dp), _p(_f64(prim2.r), _dp), _p(_f64(prim2.att), _dp),
                                         C.c_int(prim1.att_kind), _p(dims, _ip), _p(G, _dp), _p(h, _dp), _p(c, _dp))
@@ -117,7 +122,7 @@ def combine(Go1, ho1, Gs1, hs1, Go2, ho2, Gs2, hs2):
     L1, v1 = Go1.shape; d1 = Gs1.shape[0]
     L2, v2 = Go2.shape; d2 = Gs2.shape[0]
     dims = np.zeros(5, dtype=np.int32)
-    G = np.zeros(72 * 8); h = np.zeros(72); c = np.zeros(8)
+    G = np.zeros(264 * 8); h = np.zeros(264); c = np.zeros(8)
     rc = lib().dcol_oracle_combine(C.c_int(L1), C.c_int(d1), C.c_int(v1), _p(Go1, _dp), _p(ho1, _dp), _p(Gs1, _dp), _p(hs1, _dp),
                                    C.c_int(L2), C.c_int(d2), C.c_int(v2), _p(Go2, _dp), _p(ho2, _dp), _p(Gs2, _dp), _p(hs2, _dp),
                                    _p(dims, _ip), _p(G, _dp), _p(h, _dp), _p(c, _dp))

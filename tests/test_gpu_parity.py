@@ -29,22 +29,33 @@ def gq(ctx):
     return query
 
 
-def compare(g, o, kind, strict_frac=0.999):
+def compare(g, o, kind, strict_frac=0.999, spread=None):
+    """alpha, classification and status on EVERY pair.  x / grad / J (row max-norm relative error):
+    with `spread` (util.oracle_spread: the oracle's own response to a 1-ulp input perturbation) the tail is bounded pair by
+    pair and as a population — every pair within max(tol, 20 x its spread) up to a handful of exceptions (the spread is a
+    3-sample estimate), no more pairs over tolerance than the perturbed oracle itself produces, and a hard cap of
+    10 x the largest spread; without it (small special-case batches) by pass fraction plus a hard cap."""
     assert (g["status"] == o["status"]).all()
     ok = o["status"] == 0
-    assert (g["iters"] == o["iters"]).mean() > 0.999          # same iterate sequence up to round-off at the mu test
+    n = int(ok.sum())
+    assert (g["iters"] != o["iters"]).sum() <= max(3, 5e-4 * n)      # same iterate sequence up to round-off at the mu test
     ea = util.rel_err(g["alpha"], o["alpha"])[ok]
     assert ea.max() < TOL_AX, ea.max()
     assert ((g["alpha"] <= 1) == (o["alpha"] <= 1))[ok].all()
-    if "x" in g:
-        ex = util.rel_err(g["x"], o["x"])[ok]
-        assert (ex < TOL_AX).mean() >= strict_frac and ex.max() < 1e-3, (ex.max(), (ex < TOL_AX).mean())
-    if kind == 1:
-        eg = util.rel_err(g["grad"], o["grad"])[ok]
-        assert (eg < TOL_J).mean() >= strict_frac and eg.max() < 1e-2, (eg.max(), (eg < TOL_J).mean())
-    if kind == 2:
-        ej = util.rel_err(g["J"], o["J"])[ok]
-        assert (ej < TOL_J).mean() >= strict_frac and np.quantile(ej, 0.9999) < 1e-2, (ej.max(), (ej < TOL_J).mean())
+    for key, tol, cap in (("x", TOL_AX, 1e-2), ("grad", TOL_J, 1e-2), ("J", TOL_J, 1e-2)):
+        if key not in g or (key == "x" and kind == 1):
+            continue
+        e = util.rel_err(g[key], o[key])[ok]
+        frac = (e < tol).mean()
+        if spread is not None:
+            sp = spread[key][ok]
+            viol = int((e > np.maximum(tol, 20.0 * sp)).sum())
+            assert viol <= max(2, 1e-4 * n), (key, viol, e.max())
+            assert (e >= tol).sum() <= 1.5 * (sp >= tol).sum() + 5, (key, int((e >= tol).sum()), int((sp >= tol).sum()))
+            assert e.max() <= 10.0 * max(tol, sp.max()), (key, e.max(), sp.max())
+            assert frac >= 0.995, (key, frac)
+        else:
+            assert frac >= strict_frac and e.max() < cap, (key, e.max(), frac)
 
 
 @pytest.mark.parametrize("att_kind", [dc.ATT_QUAT, dc.ATT_MRP])
@@ -58,8 +69,14 @@ def test_mixed_7x7_vs_oracle(ctx, oracle, att_kind, kind, variant):
     o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6)
     assert (o["status"] == 0).all()
     # 'scene' has the long thin Capsule(0.2, 5.0) of the reference's contact example: near-parallel capsule pairs have a
-    # non-unique witness point, the ill-conditioned tail of SURVEY.md §7 (see test_oracle_x_sensitivity_tail)
-    compare(g, o, kind, strict_frac=0.999 if variant == "cube" else 0.995)
+    # non-unique witness point, the ill-conditioned tail of SURVEY.md §7 (see test_oracle_x_sensitivity_tail); the tail is
+    # bounded against the oracle's own sensitivity, pair by pair.  The 'cube' set has no such pairs: every pair in tolerance.
+    sp = util.oracle_spread(oracle, kind, t.arrays(), s1, s2, r1, a1, r2, a2, att_kind, 1e-6, o)
+    compare(g, o, kind, spread=sp)
+    if variant == "cube":
+        for key, tol in (("x", TOL_AX), ("grad", TOL_J), ("J", TOL_J)):
+            if key in g and key in o:
+                assert util.rel_err(g[key], o[key]).max() < tol, key
 
 
 @pytest.mark.parametrize("tol", [1e-4, 1e-8, 1e-10])
@@ -396,3 +413,78 @@ def test_straggler_handover_is_bit_identical(ctx):
         for a, b in zip(outs[0], o):
             for key in a:
                 assert np.array_equal(a[key], b[key], equal_nan=True), key
+
+
+def test_convergence_on_the_last_allowed_step(ctx, oracle):
+    """static_solver2.jl:132,143-146,188: mu is tested only at the START of iterations 1..cap and "pdip failed" is raised
+    after the last step without another test, so a pair whose mu drops below pdip_tol on exactly the last allowed step
+    FAILS.  The cap is 50 in the reference; the testing knob lowers it on both sides so that thousands of pairs land on
+    that edge robustly (mu falls by orders of magnitude per step there).  Status and iteration counts bit-identical."""
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(20000, 0, seed=31)
+    ta = t.arrays()
+    full = oracle.query(0, ta, s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    try:
+        for cap in (6, 8, 10):
+            oracle.set_max_iters(cap); ctx.set_max_iters(cap)
+            o = oracle.query(0, ta, s1, s2, r1, a1, r2, a2, 0, 1e-6)
+            g = gq(ctx)(0, ta, s1, s2, r1, a1, r2, a2, 0, 1e-6)
+            edge = full["iters"] == cap                       # converge on exactly the cap-th step
+            assert edge.sum() > 100
+            assert (o["status"][edge] == 1).all() and (o["iters"][edge] == cap).all()
+            assert (o["status"][full["iters"] < cap] == 0).all()
+            assert np.array_equal(g["status"], o["status"])
+            assert (g["iters"] == o["iters"]).mean() > 0.999 and np.array_equal(g["iters"][edge], o["iters"][edge])
+    finally:
+        oracle.set_max_iters(50); ctx.set_max_iters(50)
+
+
+def test_many_faces(ctx, oracle):
+    """Polytopes / polygons beyond 32 rows (the oracle's round-1 limit): 48-, 64- and 80-face polytopes, 40-sided polygon
+    (a pair may carry up to 172 orthant rows: one warp per CTA with the whole shared memory as its row store)."""
+    g = util.rng(18)
+    shapes = []
+    for nf in (48, 64, 80):
+        d = g.standard_normal((nf, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        shapes.append(dc.Polytope(d, 0.6 + 0.4 * g.random(nf)))
+    A, b = dc.create_n_sided(40, 0.7)
+    shapes += [dc.Polygon(A, b, 0.1), dc.Capsule(0.3, 1.2), dc.Cone(2.0, np.deg2rad(22))]
+    t = dc.ShapeTable(); ids = np.array([t.add(s) for s in shapes], np.int32)
+    n = 3000
+    s1 = ids[g.integers(0, len(ids), n)]; s2 = ids[g.integers(0, len(ids), n)]
+    r1, a1, r2, a2 = util.random_poses(n, 0, 321)
+    for kind in (0, 2):
+        gg = gq(ctx)(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+        o = oracle.query(kind, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+        assert (o["status"] == 0).all()
+        compare(gg, o, kind, strict_frac=0.995)
+
+
+def test_final_mu_output(ctx):
+    """dcol_set_mu_output: mu = s'z/deg at the iteration that ended the solve (< pdip_tol exactly for converged pairs)."""
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(6000, 1, seed=3)
+    ctx.set_shape_arrays(*t.arrays())
+    g = ctx._batch(1, s1, s2, r1, a1, r2, a2, 1, 1e-6, want_mu=True)
+    assert (g["status"] == 0).all() and (g["mu"] < 1e-6).all() and (g["mu"] > 0).all()
+    try:
+        ctx.set_max_iters(5)
+        h = ctx._batch(0, s1, s2, r1, a1, r2, a2, 1, 1e-6, want_mu=True)
+    finally:
+        ctx.set_max_iters(50)
+    failed = h["status"] == 1
+    assert failed.any() and (h["mu"][~failed] < 1e-6).all() and np.isfinite(h["mu"]).all()
+    small = ctx._batch(0, s1[:100], s2[:100], r1[:100], a1[:100], r2[:100], a2[:100], 1, 1e-6, want_mu=True)   # small-batch path
+    big = ctx._batch(0, s1, s2, r1, a1, r2, a2, 1, 1e-6, want_mu=True)
+    assert np.array_equal(small["mu"], big["mu"][:100])
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_small_batch_path_matches_the_binned_path(ctx, kind):
+    """n <= 4096 runs the single-block preparation without hand-over and un-permute pass; results are bit-identical to the
+    same pairs inside a large batch (sorted, handed over, un-permuted)."""
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(30000, 0, seed=11, variant="scene")
+    ctx.set_shape_arrays(*t.arrays())
+    big = ctx._batch(kind, s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    for n in (1, 2, 33, 4096):
+        sm = ctx._batch(kind, s1[:n], s2[:n], r1[:n], a1[:n], r2[:n], a2[:n], 0, 1e-6)
+        for k in sm:
+            assert np.array_equal(sm[k], big[k][:n], equal_nan=True), (k, n)

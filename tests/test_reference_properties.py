@@ -199,3 +199,20 @@ def test_oracle_x_sensitivity_tail(oracle):
     ex = util.rel_err(o2["x"], o["x"]); ea = util.rel_err(o2["alpha"], o["alpha"])
     assert ea.max() < 1e-6
     assert ex.max() > 1e-6 and (ex > 1e-6).mean() < 5e-3          # a tail exists, and it is small
+
+
+def test_oracle_iteration_cap_semantics():
+    """static_solver2.jl:132,143-146,188: with an iteration cap K, a pair that needs exactly K steps fails ("pdip failed"
+    after the K-th step without another mu test); pairs needing fewer are unaffected."""
+    import util
+    from oracle import oracle as orc
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(3000, 0, seed=31)
+    full = orc.query(0, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    try:
+        orc.set_max_iters(8)
+        o = orc.query(0, t.arrays(), s1, s2, r1, a1, r2, a2, 0, 1e-6)
+    finally:
+        orc.set_max_iters(50)
+    assert (o["status"][full["iters"] >= 8] == 1).all() and (o["iters"][full["iters"] >= 8] == 8).all()
+    lt = full["iters"] < 8
+    assert (o["status"][lt] == 0).all() and np.array_equal(o["alpha"][lt], full["alpha"][lt])

@@ -87,3 +87,20 @@ def rel_err(a, b, floor=1e-12):
         return np.abs(a - b) / np.maximum(np.abs(b), floor)
     ax = tuple(range(1, a.ndim))
     return np.abs(a - b).max(axis=ax) / np.maximum(np.abs(b).max(axis=ax), floor)
+
+
+def oracle_spread(oracle, kind, ta, s1, s2, r1, a1, r2, a2, att_kind, tol, base, trials=3, seed=99):
+    """Intrinsic sensitivity of the oracle's own outputs: row error between the oracle on the given inputs (`base`) and on
+    inputs whose every pose entry is multiplied by 1 + 2.2e-16*U(-1,1) (a 1-ulp perturbation), max over `trials`.
+    The witness point x (and with it J) is ill-conditioned for a small tail of pairs: there the
+    spread exceeds the parity tolerance for ANY implementation, including the oracle compiled with other flags."""
+    g = rng(seed)
+    out = {}
+    for _ in range(trials):
+        pr = [a * (1.0 + 2.2e-16 * (2 * g.random(np.shape(a)) - 1)) for a in (r1, a1, r2, a2)]
+        op = oracle.query(kind, ta, s1, s2, pr[0], pr[1], pr[2], pr[3], att_kind, tol)
+        for k in ("x", "grad", "J"):
+            if k in base:
+                e = rel_err(op[k], base[k])
+                out[k] = np.maximum(out.get(k, 0.0), e)
+    return out

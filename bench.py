@@ -15,7 +15,12 @@ torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of 
                  flops_model with each pair's actual iteration count / kernel time from CUDA events
                  inside the library); peak = DFMA micro-benchmark run in the same process, because
                  MEASURED_PEAKS.json carries no FP64 figure.  "hbm" sub-object: pose-in/result-out bytes.
-  cpu_baseline : the C++ oracle (restatement of the Julia reference) on all host threads, bounded sample
+  cpu_baseline : the C++ oracle (restatement of the Julia reference) on all host threads, bounded sample; rebuilt on the box
+                 it runs on with -O3 -march=native, flags and thread count in `sample`
+  e2e.copy_bound : the same end-to-end loop with the kernels switched off (dcol_set_copy_only): what the host can feed
+  scene        : the same proximity workload on the reference's contact-example shapes (8-face fixture polytope,
+                 Capsule(0.2, 5.0)): kernel time, roofline fraction, mean iterations
+  latency      : wall time of single-pair and config-1 (10k cube-cube) calls through the Python wrapper
 
 `--impl reference` times the reference's CPU implementation of the path; Julia is not in the image, so
 this is the oracle port (kind "port") on all host threads.
@@ -122,13 +127,32 @@ class ClockSampler:
         return out
 
 
+ORACLE_FLAGS = "-O3 -march=native"
+
+
+def native_oracle():
+    """The oracle rebuilt for THIS host (g++ -O3 -march=native) into a temporary directory; falls
+    back to the shipped -march=x86-64-v3 build if the compiler is not there.  Returns (module, flags description)."""
+    from oracle import oracle as orc
+    try:
+        import ctypes
+        out = os.path.join(tempfile.mkdtemp(prefix="dcol_oracle_"), "libdcol_oracle_native.so")
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "-B", "ARCHFLAGS=-march=native", f"OUT={out}"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        orc._LIB = ctypes.CDLL(out)
+        orc._LIB.dcol_oracle_query.restype = ctypes.c_int
+        return orc, "g++ " + ORACLE_FLAGS + " (built on this host)"
+    except Exception:
+        return orc, "g++ -O3 -march=x86-64-v3 (shipped build; native rebuild failed)"
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU path: C++ oracle port on all host threads, bounded sample per step."""
     if rank != 0:
         return
     import dcol_b200 as dc
     import util
-    from oracle import oracle as orc
+    orc, flags = native_oracle()
     threads = orc.max_threads()
     sample = 100_000
     t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sample, dc.ATT_QUAT, seed=1234, variant=args.variant)
@@ -146,7 +170,7 @@ def reference_arm(args, rank, world):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample} pairs of the config-2 workload per step, C++ restatement of the Julia reference "
-                                       f"(Julia is not installed in this image), std::thread x{threads}"},
+                                       f"(Julia is not installed in this image), {flags}, std::thread x{threads} (dynamic chunks of 64 pairs)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -171,6 +195,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = dc.bind_to_gpu_numa_node(local)          # pinned buffers local to the GPU's PCIe root (end-to-end path at N > 1)
+    if not numa.get("bound") and world > 1:
+        numa = dict(numa, fallback=dc.bind_disjoint_cpus(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -191,16 +217,17 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def make(n, att_kind, seed):
-        t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, att_kind, seed=seed + 7919 * rank, variant=args.variant)
+    def make(n, att_kind, seed, variant):
+        t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, att_kind, seed=seed + 7919 * rank, variant=variant)
         host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (s1, s2, r1, a1, r2, a2)]
         devt = [h.to(dev) for h in host]
         return t, host, devt
 
-    def run_config(kind, att_kind, n, steps, warmup, seed):
+    def run_config(kind, att_kind, n, steps, warmup, seed, variant=None, e2e=True):
+        variant = variant or args.variant
         na = 4 if att_kind == 0 else 3
         nt = 6 + 2 * na
-        table, host, devt = make(n, att_kind, seed)
+        table, host, devt = make(n, att_kind, seed, variant)
         ctx.set_shape_arrays(*table.arrays())
         d_alpha = torch.empty(n, dtype=torch.float64, device=dev)
         d_x = torch.empty((n, 3), dtype=torch.float64, device=dev)
@@ -253,32 +280,44 @@ def main():
         clocks = sampler.stop(t_begin, t_end) if sampler else None
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         dev_ms = max_over_ranks(dev_ms)
-        # end to end: host (pinned) buffers through the C ABI, H2D and D2H inside the timed region
-        host_step()
-        barrier()
+        e2e_s = e2e_sync_s = copy_s = None
         e2e_steps = max(4, min(12, steps // 2))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        if e2e:
+            # end to end: host (pinned) buffers through the C ABI, H2D and D2H inside the timed region
             host_step()
-        torch.cuda.synchronize()
-        e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        # pipelined: every step still copies its inputs host->device and its results device->host inside the timed
-        # region; submission k+1 is issued before submission k is waited for
-        for k in range(DEPTH):                 # warm the submission slots (their staging buffers are allocated on first use)
-            ctx.wait(host_submit(k))
-        barrier()
-        t0 = time.perf_counter()
-        tickets = []
-        for k in range(e2e_steps):
-            if len(tickets) >= DEPTH:
-                ctx.wait(tickets[-DEPTH])
-            tickets.append(host_submit(k))
-        for tk in tickets[-DEPTH:]:
-            ctx.wait(tk)
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_step()
+            torch.cuda.synchronize()
+            e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+
+            # pipelined: every step still copies its inputs host->device and its results device->host inside the timed
+            # region; submission k+1 is issued before submission k is waited for
+            def pipelined():
+                for k in range(DEPTH):             # warm the submission slots (their staging buffers are allocated on first use)
+                    ctx.wait(host_submit(k))
+                barrier()
+                t0 = time.perf_counter()
+                tickets = []
+                for k in range(e2e_steps):
+                    if len(tickets) >= DEPTH:
+                        ctx.wait(tickets[-DEPTH])
+                    tickets.append(host_submit(k))
+                for tk in tickets[-DEPTH:]:
+                    ctx.wait(tk)
+                torch.cuda.synchronize()
+                dt = max_over_ranks(time.perf_counter() - t0)
+                barrier()
+                return dt
+            e2e_s = pipelined()
+            # the same loop with the kernels switched off: the copy-only bound of this host / PCIe path at this N
+            ctx.set_copy_only(True)
+            try:
+                copy_s = pipelined()
+            finally:
+                ctx.set_copy_only(False)
         # optional result gather over NVLink: all-gather of the alpha rows, outside the timed step
         gather = None
         if world > 1:
@@ -299,18 +338,55 @@ def main():
         in_b = n * (8 + 8 * (6 + 2 * na))
         out_b = n * (8 + 8 * (1 + 3 + (4 * nt if kind == 2 else 0)))
         return {"n": n, "dev_ms": dev_ms, "steps": steps, "kernel_ms": float(np.mean(kms)), "launches": launches, "clocks": clocks,
-                "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s, "e2e_steps": e2e_steps, "flops": flops, "in_bytes": in_b, "out_bytes": out_b,
+                "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s, "copy_s": copy_s, "e2e_steps": e2e_steps, "variant": variant, "flops": flops, "in_bytes": in_b, "out_bytes": out_b,
                 "mean_iters": float(iters.mean()), "max_iters": int(iters.max()), "failed": int((status != 0).sum()), "gather": gather}
 
-    fp64_peak = ctx.measure_fp64_tflops()
+    # FP64 roofline denominator: 0.6 s of back-to-back DFMA-only launches (median launch), SM clock sampled meanwhile
+    peak_sampler = ClockSampler(local) if rank == 0 else None
+    if peak_sampler:
+        peak_sampler.start()
+        time.sleep(0.1)
+    tp0 = time.time()
+    fp64_peak = ctx.measure_fp64_tflops(0.6)
+    peak_clocks = peak_sampler.stop(tp0, time.time()) if peak_sampler else None
     prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234)
+    other = "scene" if args.variant == "cube" else "cube"
+    prox2 = run_config(0, dc.ATT_QUAT, args.pairs, max(3, args.steps // 4), args.warmup, 1234, variant=other, e2e=False)
     jac = None
     if not args.no_jacobian:
         jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), args.warmup, 4321)
 
+    # latency of the small calls every reference example makes in its inner loop (src/proximity.jl:3-14): wall clock
+    # through the Python wrapper over the C ABI, pageable numpy arrays and device tensors
+    latency = None
+    if rank == 0 and world == 1:
+        def wall(f, reps):
+            for _ in range(10):
+                f()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                f()
+            return 1e6 * (time.perf_counter() - t0) / reps
+        latency = {"unit": "us per call (wall clock, Python wrapper over the C ABI)"}
+        cone = dc.Cone(2.0, np.deg2rad(22)); caps = dc.Capsule(0.3, 1.2)
+        cone.r = np.array([0.3, 0.2, 1.0]); caps.r = np.array([-1.0, 0.4, 0.1])
+        lctx = dc.Context(local)
+        latency["single_pair_proximity"] = wall(lambda: dc.proximity(cone, caps, ctx=lctx), 300)
+        latency["single_pair_jacobian"] = wall(lambda: dc.proximity_jacobian(cone, caps, ctx=lctx), 300)
+        for nn in (1000, 10000):
+            tb, c1, c2, q1, b1, q2, b2 = util.cube_batch(nn, 0, 5)
+            lctx.set_shape_arrays(*tb.arrays())
+            latency[f"config1_cube_cube_{nn}_host"] = wall(lambda: lctx.proximity_batch(c1, c2, q1, b1, q2, b2, att_kind=0, pdip_tol=PDIP_TOL), 100)
+            latency[f"config1_cube_cube_{nn}_kernels"] = 1e3 * lctx.last_kernel_ms()
+            dv = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (c1, c2, q1, b1, q2, b2)]
+            oa = torch.empty(nn, dtype=torch.float64, device=dev); ox = torch.empty((nn, 3), dtype=torch.float64, device=dev)
+            os_ = torch.empty(nn, dtype=torch.int32, device=dev); oi = torch.empty(nn, dtype=torch.int32, device=dev)
+            latency[f"config1_cube_cube_{nn}_device"] = wall(lambda: lctx.query_raw(0, nn, *dv, 0, PDIP_TOL, dc.MEM_DEVICE, oa, ox, None, os_, oi), 100)
+        lctx.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
+        orc, oflags = native_oracle()
         threads = orc.max_threads()
         sample = min(250_000 * threads, 8_000_000)     # ~10-30 s of CPU work in total across the threads, bounded
         t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sample, dc.ATT_QUAT, seed=1234, variant=args.variant)
@@ -318,8 +394,12 @@ def main():
         t0 = time.perf_counter()
         orc.query(0, t.arrays(), s1, s2, r1, a1, r2, a2, 0, PDIP_TOL)
         dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        orc.query(0, t.arrays(), s1[:200000], s2[:200000], r1[:200000], a1[:200000], r2[:200000], a2[:200000], 0, PDIP_TOL, nthreads=1)
+        dt1 = time.perf_counter() - t0
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{sample} pairs of the config-2 workload, C++ restatement of the Julia reference, std::thread x{threads}"}
+               "sample": f"{sample} pairs of the config-2 workload, C++ restatement of the Julia reference, {oflags}, std::thread x{threads}"}
+        cpu["single_thread_us_per_pair"] = 1e6 * dt1 / 200000
         sj = min(100_000 * threads, 3_000_000)
         t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(sj, dc.ATT_MRP, seed=4321, variant=args.variant)
         t0 = time.perf_counter()
@@ -346,13 +426,16 @@ def main():
             ach = r["flops"] / (r["kernel_ms"] * 1e-3) / 1e12
             gbs = (r["in_bytes"] + r["out_bytes"]) / (r["kernel_ms"] * 1e-3) / 1e9
             return {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                    "peak_source": "DFMA micro-benchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                    "peak_source": "DFMA-only kernel launched back to back for 0.6 s in this process, median launch (MEASURED_PEAKS.json has "
+                                   "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)",
+                    "peak_clocks": peak_clocks, "frac_of_nominal_37.2": ach / 37.2,
                     "traffic": traffic.get(key, {}).get("dram_bytes_per_step") if traffic.get(key, {}).get("pairs") == r["n"] else None,
                     "traffic_source": traffic.get(key, {}).get("source"),
                     "kernel_ms_per_step": r["kernel_ms"], "algorithmic_flops_per_pair": r["flops"] / r["n"],
                     "hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                             "peak_source": hbm_src, "algorithmic_bytes_per_pair": (r["in_bytes"] + r["out_bytes"]) / r["n"]}}
 
+        max_over_ranks_done = lambda r: r["dev_ms"]          # dev_ms already is the max over ranks
         value = world * prox["n"] * prox["steps"] / (prox["dev_ms"] * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": prox["steps"], "warmup": args.warmup,
                 "ms_per_step": prox["dev_ms"] / prox["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -360,9 +443,21 @@ def main():
                 "e2e": {"value": world * prox["n"] * prox["e2e_steps"] / prox["e2e_s"], "unit": UNIT,
                         "h2d_bytes_per_step": prox["in_bytes"], "d2h_bytes_per_step": prox["out_bytes"],
                         "api": "dcol_submit/dcol_wait, three submissions in flight, pinned host buffers",
-                        "one_call_at_a_time": world * prox["n"] * prox["e2e_steps"] / prox["e2e_sync_s"]},
+                        "one_call_at_a_time": world * prox["n"] * prox["e2e_steps"] / prox["e2e_sync_s"],
+                        "copy_bound": world * prox["n"] * prox["e2e_steps"] / prox["copy_s"],
+                        "frac_of_copy_bound": prox["copy_s"] / prox["e2e_s"],
+                        "copy_bound_how": "same loop, buffers, streams and submission depth with the kernels switched off (dcol_set_copy_only)"},
                 "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox, "proximity"),
                 "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
+        r2 = roof(prox2, "proximity_" + prox2["variant"])
+        line[prox2["variant"]] = {"what": "same workload on the '%s' shape set" % prox2["variant"],
+                                  "value": world * prox2["n"] * prox2["steps"] / (max_over_ranks_done(prox2) * 1e-3), "unit": UNIT,
+                                  "ms_per_step": prox2["dev_ms"] / prox2["steps"], "kernel_ms_per_step": prox2["kernel_ms"],
+                                  "roofline_frac": r2["frac"], "achieved_tflops": r2["achieved"],
+                                  "algorithmic_flops_per_pair": r2["algorithmic_flops_per_pair"],
+                                  "mean_iters": prox2["mean_iters"], "max_iters": prox2["max_iters"], "failed_pairs": prox2["failed"]}
+        if latency:
+            line["latency"] = latency
         if prox.get("gather"):
             line["gather"] = prox["gather"]
         line["host_affinity"] = numa
@@ -378,7 +473,9 @@ def main():
                 "e2e": {"value": world * jac["n"] * jac["e2e_steps"] / jac["e2e_s"], "unit": UNIT,
                         "h2d_bytes_per_step": jac["in_bytes"], "d2h_bytes_per_step": jac["out_bytes"],
                         "api": "dcol_submit/dcol_wait, three submissions in flight, pinned host buffers",
-                        "one_call_at_a_time": world * jac["n"] * jac["e2e_steps"] / jac["e2e_sync_s"]},
+                        "one_call_at_a_time": world * jac["n"] * jac["e2e_steps"] / jac["e2e_sync_s"],
+                        "copy_bound": world * jac["n"] * jac["e2e_steps"] / jac["copy_s"],
+                        "frac_of_copy_bound": jac["copy_s"] / jac["e2e_s"]},
                 "gpu_launches": jac["launches"], "clocks": jac["clocks"], "roofline": roof(jac, "jacobian"),
                 "solver": {"mean_iters": jac["mean_iters"], "max_iters": jac["max_iters"], "failed_pairs": jac["failed"]}}
         print(json.dumps(line), flush=True)

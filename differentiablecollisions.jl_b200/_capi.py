@@ -35,6 +35,7 @@ SYMBOLS = {
     "dcol_scene_pair_count": (C.c_int64, [C.c_int]),
     "dcol_scene_allpairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_scene_set_cull": (C.c_int, [C.c_void_p, C.c_double]),
     "dcol_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_wait": (C.c_int, [C.c_void_p, C.c_int]),
@@ -49,6 +50,8 @@ SYMBOLS = {
     "dcol_launch_count": (C.c_int64, [C.c_void_p]),
     "dcol_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),
+    "dcol_measure_fp64_tflops_for": (C.c_double, [C.c_void_p, C.c_double]),
+    "dcol_set_copy_only": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib = None

@@ -92,8 +92,12 @@ class Context:
     def last_kernel_ms(self) -> float:
         return float(self._lib.dcol_last_kernel_ms(self._h))
 
-    def measure_fp64_tflops(self) -> float:
-        return float(self._lib.dcol_measure_fp64_tflops(self._h))
+    def measure_fp64_tflops(self, seconds: float = 0.6) -> float:
+        return float(self._lib.dcol_measure_fp64_tflops_for(self._h, float(seconds)))
+
+    def set_copy_only(self, on: bool):
+        """Measurement knob (dcol_set_copy_only): host-pointer calls do their copies but launch no kernels."""
+        self._check(self._lib.dcol_set_copy_only(self._h, int(bool(on))))
 
     # ---- raw call (host numpy arrays or device/pinned torch tensors) --------------------------
     def query_raw(self, kind, n, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, mem,
@@ -239,6 +243,11 @@ class Context:
                                                  int(att_kind), float(pdip_tol), MEM_HOST,
                                                  _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
         return self._finish(out, kind, x, deriv)
+
+    def scene_set_cull(self, alpha_cut: float = 0.0):
+        """Opt-in broad phase of scene_allpairs / scene_wrench (`dcol_scene_set_cull`): pairs whose bounding balls prove
+        alpha* > alpha_cut are answered without the conic solve (alpha = a lower bound > alpha_cut, status 3); 0 = off."""
+        self._check(self._lib.dcol_scene_set_cull(self._h, float(alpha_cut)))
 
     def scene_allpairs(self, kind, shape, r, att, att_kind=ATT_QUAT, pdip_tol=1e-6):
         """All i<j pairs of a scene in `combinations` order (`dcol_scene_allpairs`); pair list generated on the device."""

@@ -3,6 +3,7 @@
 // Entry points are declared in include/dcol_b200.h.
 #include "../../include/dcol_b200.h"
 #include "dcol_common.cuh"
+#include "dcol_deriv.cuh"
 #ifndef DCOL_MAXTHREADS
 #define DCOL_MAXTHREADS 256
 #endif
@@ -84,8 +85,9 @@ struct dcol_ctx {
     cudaEvent_t ev_end = nullptr;       // recorded behind the last operation of the submission (its own join point)
     bool pending = false; int ticket = -1, result = 0;
     int nchunks = 0, nk = 0; size_t hist_stride = 0; bool piped = false;
-    // pinned landing area of the bad-index flags (a pageable destination would make the copy synchronous)
-    int* h_bad = nullptr;
+    // bad-index flags: mapped pinned memory the binning kernels write directly (error path only), so no copy of a
+    // 4-byte flag sits behind every call
+    int* h_bad = nullptr; int* d_bad_map = nullptr;
     double ms = -1.0;
   };
   Slot slots[N_SLOTS];
@@ -94,12 +96,17 @@ struct dcol_ctx {
   static constexpr int N_DONE = 16;
   int done_ticket[N_DONE]; int done_result[N_DONE]; std::string done_err[N_DONE]; int done_head = 0;
   dcol_ctx() { for (int i = 0; i < N_DONE; i++) { done_ticket[i] = -1; done_result[i] = 0; } }
-  DevBuf d_scene, d_pairs, d_plan, d_wrench;
+  DevBuf d_scene, d_pairs, d_plan, d_wrench, d_brad, d_cull;
+  double cull_alpha = 0.0;              // > 0: broad-phase cull of scene operators at this alpha (dcol_scene_set_cull)
+  int* h_count = nullptr;               // pinned landing area of the survivor count
+  // pinned staging of small host-pointer calls: one H2D and one D2H copy per call instead of six and five
+  char* h_stage = nullptr; size_t h_stage_cap = 0;
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   int n_sm = 148;
   int64_t launches = 0;
   double last_ms = -1.0;
   int max_iters = MAX_ITERS;            // testing knob (dcol_set_max_iters); the reference's 50 otherwise
+  bool copy_only = false;               // measurement knob (dcol_set_copy_only): host<->device copies without kernels
   double* mu_out = nullptr;             // optional per-pair final duality measure (dcol_set_mu_output), same memory space as the query's outputs
   cudaStream_t stream() const { return user ? user : own; }
 };
@@ -139,6 +146,7 @@ struct PairSource {
   const int32_t* pose1; const int32_t* pose2;      // optional: row of (r1, att1) / (r2, att2) used by the pair
   const double* r1; const double* att1; const double* r2; const double* att2;
   int na;                                          // attitude stride: 4 quaternion, 3 MRP
+  const int32_t* oidx;                             // optional: where pair i's results go (culled scene lists); NULL = i
 };
 
 // Write pair i at sorted position pos as one 128-byte record (eight 16-byte stores = one cache line).  Pairs whose
@@ -158,16 +166,17 @@ __device__ __forceinline__ void pack_pair(const PairSource& src, int64_t i, int 
     const int t = s1; s1 = s2; s2 = t;
   }
   v[14] = __hiloint2double(s2, s1);
-  v[15] = __hiloint2double(swp ? DCOL_REC_SWAPPED : 0, (int)i);
+  v[15] = __hiloint2double(swp ? DCOL_REC_SWAPPED : 0, src.oidx ? src.oidx[i] : (int)i);
   double2* q = reinterpret_cast<double2*>(recs + pos);
 #pragma unroll
   for (int a = 0; a < 8; a++) q[a] = make_double2(v[2 * a], v[2 * a + 1]);
 }
 
-// counting-sort scatter fused with the packing of the sorted records; also writes inv[i] = sorted position of pair i
-// (coalesced; -1 for pairs with a bad shape index), which k_unpermute uses to bring the results back into caller order
-__global__ void k_scatter_pack(PairSource src, int64_t n, const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap,
-                               int n_shapes, int n_keys, int* __restrict__ cursor, PairRec* __restrict__ recs, int32_t* __restrict__ inv) {
+// counting-sort scatter: inv[i] = sorted position of pair i (coalesced writes; -1 for pairs with a bad shape index).
+// k_pack then writes the records and k_unpermute uses the same array to bring the results back into caller order.
+__global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __restrict__ shape2, int64_t n,
+                          const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap,
+                          int n_shapes, int n_keys, int* __restrict__ cursor, int32_t* __restrict__ inv) {
   extern __shared__ int sh[];          // [0,n_keys) local counts, then [n_keys, 2 n_keys) global bases
   int64_t chunk = (int64_t)blockDim.x * 8;
   for (int64_t base = blockIdx.x * chunk; base < n; base += (int64_t)gridDim.x * chunk) {
@@ -179,7 +188,7 @@ __global__ void k_scatter_pack(PairSource src, int64_t n, const int32_t* __restr
       int64_t i = base + u * blockDim.x + threadIdx.x;
       key[u] = -1;
       if (i < n) {
-        int s1 = src.shape1[i], s2 = src.shape2[i];
+        int s1 = shape1[i], s2 = shape2[i];
         if ((unsigned)s1 < (unsigned)n_shapes && (unsigned)s2 < (unsigned)n_shapes) {
           key[u] = pair_key(cls, keymap, n_shapes, s1, s2);
           rank[u] = atomicAdd(&sh[key[u]], 1);
@@ -189,26 +198,30 @@ __global__ void k_scatter_pack(PairSource src, int64_t n, const int32_t* __restr
     __syncthreads();
     for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[n_keys + k] = sh[k] ? atomicAdd(&cursor[k], sh[k]) : 0;
     __syncthreads();
-#pragma unroll 1
+#pragma unroll
     for (int u = 0; u < 8; u++) {
       int64_t i = base + u * blockDim.x + threadIdx.x;
-      if (i >= n) continue;
-      int pos = -1;
-      if (key[u] >= 0) {
-        pos = sh[n_keys + key[u]] + rank[u];
-        const int s1 = src.shape1[i], s2 = src.shape2[i];
-        pack_pair(src, i, s1, s2, cls[s1] > cls[s2], recs, pos);
-      }
-      if (inv) inv[i] = pos;
+      if (i < n) inv[i] = (key[u] >= 0) ? sh[n_keys + key[u]] + rank[u] : -1;
     }
     __syncthreads();
+  }
+}
+
+// one thread per pair, no barriers: a pure streaming kernel (reads the caller's arrays coalesced in pair order, writes
+// each pair's 128-byte record at its sorted position)
+__global__ void k_pack(PairSource src, int64_t n, const int32_t* __restrict__ cls, const int32_t* __restrict__ inv, PairRec* __restrict__ recs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pos = inv[i];
+    if (pos < 0) continue;
+    const int s1 = src.shape1[i], s2 = src.shape2[i];
+    pack_pair(src, i, s1, s2, cls[s1] > cls[s2], recs, pos);
   }
 }
 
 // results from sorted order (where the solver stored them with coalesced writes) back to the caller's pair order:
 // thread i gathers its pair's results from position inv[i] (L2-resident for batches up to a few million pairs) and
 // writes them coalesced
-__global__ void k_unpermute(int64_t n, const int32_t* __restrict__ inv,
+__global__ void k_unpermute(int64_t n, const int32_t* __restrict__ inv, const int32_t* __restrict__ oidx,
                             const double* __restrict__ alpha_s, const double* __restrict__ x_s, const int32_t* __restrict__ status_s,
                             const int32_t* __restrict__ iters_s, const double* __restrict__ mu_s,
                             double* __restrict__ alpha, double* __restrict__ x, int32_t* __restrict__ status, int32_t* __restrict__ iters,
@@ -216,11 +229,12 @@ __global__ void k_unpermute(int64_t n, const int32_t* __restrict__ inv,
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int pos = inv[i];
     if (pos < 0) continue;
-    alpha[i] = alpha_s[pos];
-    if (x) { x[3 * i] = x_s[3 * (int64_t)pos]; x[3 * i + 1] = x_s[3 * (int64_t)pos + 1]; x[3 * i + 2] = x_s[3 * (int64_t)pos + 2]; }
-    if (status) status[i] = status_s[pos];
-    if (iters) iters[i] = iters_s[pos];
-    if (mu) mu[i] = mu_s[pos];
+    const int64_t o = oidx ? (int64_t)oidx[i] : i;
+    alpha[o] = alpha_s[pos];
+    if (x) { x[3 * o] = x_s[3 * (int64_t)pos]; x[3 * o + 1] = x_s[3 * (int64_t)pos + 1]; x[3 * o + 2] = x_s[3 * (int64_t)pos + 2]; }
+    if (status) status[o] = status_s[pos];
+    if (iters) iters[o] = iters_s[pos];
+    if (mu) mu[o] = mu_s[pos];
   }
 }
 
@@ -302,16 +316,16 @@ __global__ void k_scan_tables(const int* __restrict__ hist, int n_keys, int* __r
   build_tables_dev(plan, tables, n_tiers, off, ov_base, P, spill_div, s_nt, s_ovsz, &s_ov);
 }
 
-// Small batches (n <= SMALL_MAX): histogram, scan, scatter + pack and the launch tables in ONE single-block kernel, so a
-// query is this launch plus one solver launch per shared-memory tier (no hand-over, hence no resume launch, and results
-// are stored at the caller's pair index directly: no un-permute pass).  Latency path of the single-pair drop-in calls
+// Small batches (n <= SMALL_MAX): histogram, scan, sorted positions and the launch tables in ONE single-block kernel, so a
+// query is this launch, the packing launch and one solver launch per shared-memory tier (no hand-over, hence no resume
+// launch, and results are stored at the caller's pair index directly: no un-permute pass).  Latency path of the single-pair drop-in calls
 // (src/proximity.jl:3-14 is what every reference example calls in its inner loop).
-constexpr int SMALL_MAX = 4096;
+constexpr int SMALL_MAX = 16384;
 constexpr int SMALL_THREADS = 1024;
 constexpr int SMALL_ITEMS = SMALL_MAX / SMALL_THREADS;
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_prep(PairSource src, int n, const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap,
                              int n_shapes, int n_keys, int* __restrict__ off, int* __restrict__ counters, int n_counters, int* __restrict__ bad,
-                             PairRec* __restrict__ recs, const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
+                             int32_t* __restrict__ inv, const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
                              double* ov_base, QueryParams P) {
   extern __shared__ int sh[];            // [0, n_keys]: counts, then exclusive offsets
   __shared__ int part[SMALL_THREADS];
@@ -321,7 +335,6 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_prep(PairSource src, in
   const int tid = threadIdx.x;
   for (int k = tid; k <= n_keys; k += blockDim.x) sh[k] = 0;
   for (int k = tid; k < n_counters; k += blockDim.x) counters[k] = 0;
-  if (tid == 0) *bad = 0;
   __syncthreads();
   int key[SMALL_ITEMS], rank[SMALL_ITEMS];
 #pragma unroll
@@ -355,13 +368,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_prep(PairSource src, in
     if (tid == blockDim.x - 1) { sh[n_keys] = part[tid]; off[n_keys] = part[tid]; }
   }
   __syncthreads();
-#pragma unroll 1
+#pragma unroll
   for (int u = 0; u < SMALL_ITEMS; u++) {
     const int i = u * blockDim.x + tid;
-    if (i < n && key[u] >= 0) {
-      const int s1 = src.shape1[i], s2 = src.shape2[i];
-      pack_pair(src, i, s1, s2, cls[s1] > cls[s2], recs, sh[key[u]] + rank[u]);
-    }
+    if (i < n) inv[i] = (key[u] >= 0) ? sh[key[u]] + rank[u] : -1;
   }
   build_tables_dev(plan, tables, n_tiers, off, ov_base, P, 0, s_nt, s_ovsz, &s_ov);
 }
@@ -396,16 +406,84 @@ __global__ void k_build_tables2(const LaunchTable* __restrict__ Tp, LaunchTable*
 
 // (i, j), i < j in combinations(1:N, 2) order (the pair list of examples/contact_physics/ncp_contact_simulation.jl:48),
 // generated on the device: pair k of row i starts at k_i = i(2N - i - 1)/2.
+__device__ __forceinline__ void pair_of_index(int n_bodies, int64_t k, int64_t& i, int64_t& j) {
+  const double N = (double)n_bodies;
+  i = (int64_t)floor(((2.0 * N - 1.0) - sqrt((2.0 * N - 1.0) * (2.0 * N - 1.0) - 8.0 * (double)k)) * 0.5);
+  i = max((int64_t)0, min(i, (int64_t)n_bodies - 2));
+  while (i > 0 && i * (2 * (int64_t)n_bodies - i - 1) / 2 > k) i--;
+  while ((i + 1) * (2 * (int64_t)n_bodies - i - 2) / 2 <= k) i++;
+  j = k - i * (2 * (int64_t)n_bodies - i - 1) / 2 + i + 1;
+}
 __global__ void k_allpairs(int n_bodies, int64_t n_pairs, const int32_t* __restrict__ shape,
                            int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ p1, int32_t* __restrict__ p2) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_pairs; k += (int64_t)gridDim.x * blockDim.x) {
-    const double N = (double)n_bodies;
-    int64_t i = (int64_t)floor(((2.0 * N - 1.0) - sqrt((2.0 * N - 1.0) * (2.0 * N - 1.0) - 8.0 * (double)k)) * 0.5);
-    i = max((int64_t)0, min(i, (int64_t)n_bodies - 2));
-    while (i > 0 && i * (2 * (int64_t)n_bodies - i - 1) / 2 > k) i--;
-    while ((i + 1) * (2 * (int64_t)n_bodies - i - 2) / 2 <= k) i++;
-    const int64_t j = k - i * (2 * (int64_t)n_bodies - i - 1) / 2 + i + 1;
+    int64_t i, j;
+    pair_of_index(n_bodies, k, i, j);
     s1[k] = shape[i]; s2[k] = shape[j]; p1[k] = (int32_t)i; p2[k] = (int32_t)j;
+  }
+}
+
+// Broad phase of the all-pairs scene operators (opt-in, dcol_scene_set_cull): every primitive scales about its body
+// origin r~ = r + Qn r_offset and lies inside the ball of radius rho around it, so alpha* >= |r~_i - r~_j| / (rho_i + rho_j).
+// Pairs whose bound exceeds alpha_cut are answered here (alpha = that lower bound, status DCOL_STATUS_CULLED, zero
+// derivative rows, NaN witness point); the others are appended to a compact pair list for the conic solver, together with
+// the index their results go to.  centre[] holds r~ per body (k_body_centres).
+__global__ void k_body_centres(int n_bodies, const int32_t* __restrict__ shape, const DevShape* __restrict__ shapes, int n_shapes,
+                               const double* __restrict__ r, const double* __restrict__ att, int att_kind, double* __restrict__ centre, int* __restrict__ bad) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bodies) return;
+  const int s = shape[b];
+  double c[3] = {r[3 * b], r[3 * b + 1], r[3 * b + 2]};
+  if ((unsigned)s >= (unsigned)n_shapes) { *bad = 1; }
+  else if (shapes[s].has_offset) {
+    double Q[3][3];
+    if (att_kind == 0) { double q[4] = {att[4 * b], att[4 * b + 1], att[4 * b + 2], att[4 * b + 3]}; dcm_from_q<double>(q, Q); }
+    else { double q[3] = {att[3 * b], att[3 * b + 1], att[3 * b + 2]}; dcm_from_mrp<double>(q, Q); }
+    for (int a = 0; a < 3; a++) c[a] += Q[a][0] * shapes[s].r_off[0] + Q[a][1] * shapes[s].r_off[1] + Q[a][2] * shapes[s].r_off[2];
+  }
+  centre[3 * b] = c[0]; centre[3 * b + 1] = c[1]; centre[3 * b + 2] = c[2];
+}
+__global__ void k_allpairs_cull(int n_bodies, int64_t n_pairs, const int32_t* __restrict__ shape, int n_shapes, const double* __restrict__ brad,
+                                const double* __restrict__ centre, double alpha_cut, int nd,
+                                int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ p1, int32_t* __restrict__ p2,
+                                int32_t* __restrict__ oidx, int* __restrict__ count,
+                                double* __restrict__ alpha, double* __restrict__ x, double* __restrict__ deriv, int32_t* __restrict__ status,
+                                int32_t* __restrict__ iters) {
+  const int64_t span = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (n_pairs + span - 1) / span;
+  for (int64_t rd = 0; rd < rounds; rd++) {
+    const int64_t k = rd * span + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool keep = false;
+    int64_t i = 0, j = 0; int si = 0, sj = 0;
+    if (k < n_pairs) {
+      pair_of_index(n_bodies, k, i, j);
+      si = shape[i]; sj = shape[j];
+      keep = true;
+      if ((unsigned)si < (unsigned)n_shapes && (unsigned)sj < (unsigned)n_shapes) {
+        const double dx = centre[3 * i] - centre[3 * j], dy = centre[3 * i + 1] - centre[3 * j + 1], dz = centre[3 * i + 2] - centre[3 * j + 2];
+        const double lb = sqrt(dx * dx + dy * dy + dz * dz) / (brad[si] + brad[sj]);
+        if (lb > alpha_cut) {
+          keep = false;
+          alpha[k] = lb;
+          if (status) status[k] = DCOL_STATUS_CULLED;
+          if (iters) iters[k] = 0;
+          if (x) { const double qn = __longlong_as_double(0x7ff8000000000000LL); x[3 * k] = qn; x[3 * k + 1] = qn; x[3 * k + 2] = qn; }
+          if (deriv) for (int a = 0; a < nd; a++) deriv[(int64_t)nd * k + a] = 0.0;
+        }
+      }
+    }
+    // warp-aggregated append of the survivors
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(count, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (keep) {
+        const int slot = base + __popc(m & ((1u << lane) - 1));
+        s1[slot] = si; s2[slot] = sj; p1[slot] = (int32_t)i; p2[slot] = (int32_t)j; oidx[slot] = (int32_t)k;
+      }
+    }
   }
 }
 
@@ -415,7 +493,7 @@ __global__ void k_allpairs(int n_bodies, int64_t n_pairs, const int32_t* __restr
 // (variational_utils.jl:24-26), identity for MRPs.  One block per body, no atomics: the pairs (b, j), j > b are the
 // contiguous run starting at k_b = b(2N-b-1)/2 (body b is side 1), the pairs (i, b), i < b sit at k_i + (b-i-1)
 // (body b is side 2).  Fixed summation order, so the result is reproducible.
-__global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, const double* __restrict__ lambda,
+__global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, const double* __restrict__ lambda, const int32_t* __restrict__ culled,
                                const double* __restrict__ att, int att_kind, double* __restrict__ out) {
   const int b = blockIdx.x;
   const int na = (att_kind == 0) ? 4 : 3, nt = 6 + 2 * na, ns = 3 + na;
@@ -426,6 +504,7 @@ __global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, co
     int64_t k; int side;
     if (j > b) { k = (int64_t)b * (2 * N - b - 1) / 2 + (j - b - 1); side = 0; }
     else       { k = (int64_t)j * (2 * N - j - 1) / 2 + (b - j - 1); side = 1; }
+    if (culled && culled[k] == DCOL_STATUS_CULLED) continue;     // far pair: its gradient row was never computed
     const double w = lambda[k];
     const double* g = grad + k * nt + side * ns;
     for (int a = 0; a < ns; a++) acc[a] += w * g[a];
@@ -509,6 +588,70 @@ static int type_to_cls(int type) {
   return -1;
 }
 
+// Radius of the smallest origin-centred ball that contains a primitive in its body frame (the primitive scales about
+// that origin, so alpha times this ball contains the scaled primitive): the broad-phase bound of the scene operators.
+// Polytopes / polygons: largest vertex norm by enumerating the intersections of constraint triples / pairs (done once
+// per shape table; a few thousand candidates for the face counts the reference uses).
+static double bounding_radius(int type, const double* p) {
+  switch (type) {
+    case T_SPHERE: return p[0];
+    case T_CAPSULE: return 0.5 * p[1] + p[0];
+    case T_CYLINDER: return std::sqrt(0.25 * p[1] * p[1] + p[0] * p[0]);
+    case T_CONE: { const double H = p[0], tb = std::tan(p[1]); return std::max(0.75 * H, std::sqrt(H * H / 16 + H * H * tb * tb)); }
+    case T_ELLIPSOID: {          // ||U x|| <= 1  =>  |x| <= 1/sqrt(lambda_min(U'U)); eigenvalues of the symmetric 3x3 in closed form
+      double M[3][3];
+      for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) M[a][c] = p[a] * p[c] + p[3 + a] * p[3 + c] + p[6 + a] * p[6 + c];
+      const double q = (M[0][0] + M[1][1] + M[2][2]) / 3.0;
+      const double p1 = M[0][1] * M[0][1] + M[0][2] * M[0][2] + M[1][2] * M[1][2];
+      const double p2 = (M[0][0] - q) * (M[0][0] - q) + (M[1][1] - q) * (M[1][1] - q) + (M[2][2] - q) * (M[2][2] - q) + 2.0 * p1;
+      double lmin = std::min(M[0][0], std::min(M[1][1], M[2][2]));
+      if (p2 > 0.0) {
+        const double pp = std::sqrt(p2 / 6.0);
+        double B[3][3];
+        for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) B[a][c] = (M[a][c] - (a == c ? q : 0.0)) / pp;
+        const double detB = B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1]) - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0])
+                          + B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0]);
+        const double rr = std::max(-1.0, std::min(1.0, 0.5 * detB));
+        const double phi = std::acos(rr) / 3.0;
+        lmin = q + 2.0 * pp * std::cos(phi + 2.0 * M_PI / 3.0);          // smallest of the three roots
+      }
+      return lmin > 0.0 ? (1.0 + 1e-12) / std::sqrt(lmin) : INFINITY;
+    }
+    case T_POLYTOPE: {
+      const int n = (int)p[0]; const double* A = p + 1; const double* b = p + 1 + 3 * n;
+      double best = 0.0; bool any = false;
+      for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) for (int k = j + 1; k < n; k++) {
+        const double* a1 = A + 3 * i; const double* a2 = A + 3 * j; const double* a3 = A + 3 * k;
+        const double c1[3] = {a2[1] * a3[2] - a2[2] * a3[1], a2[2] * a3[0] - a2[0] * a3[2], a2[0] * a3[1] - a2[1] * a3[0]};
+        const double det = a1[0] * c1[0] + a1[1] * c1[1] + a1[2] * c1[2];
+        if (std::fabs(det) < 1e-12) continue;
+        const double c2[3] = {a3[1] * a1[2] - a3[2] * a1[1], a3[2] * a1[0] - a3[0] * a1[2], a3[0] * a1[1] - a3[1] * a1[0]};
+        const double c3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
+        double v[3];
+        for (int q = 0; q < 3; q++) v[q] = (b[i] * c1[q] + b[j] * c2[q] + b[k] * c3[q]) / det;
+        bool inside = true;
+        for (int m = 0; m < n && inside; m++) inside = A[3 * m] * v[0] + A[3 * m + 1] * v[1] + A[3 * m + 2] * v[2] <= b[m] + 1e-9 * (1.0 + std::fabs(b[m]));
+        if (inside) { best = std::max(best, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])); any = true; }
+      }
+      return any ? best : INFINITY;          // unbounded or degenerate: never culled
+    }
+    case T_POLYGON: {
+      const int n = (int)p[0]; const double* A = p + 1; const double* b = p + 1 + 2 * n; const double R = p[1 + 3 * n];
+      double best = 0.0; bool any = false;
+      for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) {
+        const double det = A[2 * i] * A[2 * j + 1] - A[2 * i + 1] * A[2 * j];
+        if (std::fabs(det) < 1e-12) continue;
+        const double v[2] = {(b[i] * A[2 * j + 1] - A[2 * i + 1] * b[j]) / det, (A[2 * i] * b[j] - b[i] * A[2 * j]) / det};
+        bool inside = true;
+        for (int m = 0; m < n && inside; m++) inside = A[2 * m] * v[0] + A[2 * m + 1] * v[1] <= b[m] + 1e-9 * (1.0 + std::fabs(b[m]));
+        if (inside) { best = std::max(best, std::sqrt(v[0] * v[0] + v[1] * v[1])); any = true; }
+      }
+      return any ? best + R : INFINITY;
+    }
+  }
+  return INFINITY;
+}
+
 extern "C" {
 
 const char* dcol_version(void) { return "dcol_b200 0.1.0 (sm_100a, fp64)"; }
@@ -547,7 +690,8 @@ int dcol_create(dcol_ctx** out, int device_id) {
     }
   for (int k = 0; k < dcol_ctx::N_SLOTS; k++) {
     dcol_ctx::Slot& L = ctx->slots[k];
-    if ((e = cudaHostAlloc((void**)&L.h_bad, sizeof(int) * dcol_ctx::MAX_CHUNKS, cudaHostAllocDefault)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc((void**)&L.h_bad, sizeof(int) * dcol_ctx::MAX_CHUNKS, cudaHostAllocMapped)) != cudaSuccess) return fail("cudaHostAlloc", e);
+    if ((e = cudaHostGetDevicePointer((void**)&L.d_bad_map, L.h_bad, 0)) != cudaSuccess) return fail("cudaHostGetDevicePointer", e);
     if ((e = cudaEventCreateWithFlags(&L.ev_end, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   }
   if ((e = cudaEventCreate(&ctx->ev_k0)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -561,7 +705,8 @@ void dcol_destroy(dcol_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_scene, &ctx->d_pairs, &ctx->d_plan, &ctx->d_wrench};
+  DevBuf* bufs[] = {&ctx->d_shapes, &ctx->d_rows, &ctx->d_cls, &ctx->d_keymap, &ctx->d_scene, &ctx->d_pairs, &ctx->d_plan, &ctx->d_wrench, &ctx->d_brad, &ctx->d_cull};
+  if (ctx->h_count) cudaFreeHost(ctx->h_count);
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < NSIDE; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   for (int k = 0; k < dcol_ctx::N_SLOTS; k++) {
@@ -577,6 +722,7 @@ void dcol_destroy(dcol_ctx* ctx) {
     DevBuf* lb[] = {&L.d_in, &L.d_out, &L.d_recs, &L.d_inv, &L.d_sorted, &L.d_hist, &L.d_tables, &L.d_ov};
     for (DevBuf* b : lb) b->release();
   }
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -635,6 +781,14 @@ int dcol_set_max_iters(dcol_ctx* ctx, int max_iters) {
 int dcol_set_mu_output(dcol_ctx* ctx, double* mu) {
   if (!ctx) return -1;
   ctx->mu_out = mu;
+  return 0;
+}
+
+// Measurement knob: the following host-pointer calls issue their host<->device copies (same staging buffers, streams,
+// chunking and events) but no kernels, which gives the copy-only bound of the end-to-end path (bench.py: e2e.copy_bound).
+int dcol_set_copy_only(dcol_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->copy_only = on != 0;
   return 0;
 }
 
@@ -754,6 +908,12 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   CK(cudaMemcpy(ctx->d_shapes.p, hs.data(), sizeof(DevShape) * n_shapes, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_rows.p, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ctx->d_cls.p, cls.data(), sizeof(int32_t) * n_shapes, cudaMemcpyHostToDevice));
+  {
+    std::vector<double> brad(n_shapes);
+    for (int i = 0; i < n_shapes; i++) brad[i] = bounding_radius(type[i], params + param_off[i]);
+    CK(ctx->d_brad.need(sizeof(double) * n_shapes));
+    CK(cudaMemcpy(ctx->d_brad.p, brad.data(), sizeof(double) * n_shapes, cudaMemcpyHostToDevice));
+  }
   if (ctx->use_keymap) {
     CK(ctx->d_keymap.need(sizeof(int32_t) * keymap.size()));
     CK(cudaMemcpy(ctx->d_keymap.p, keymap.data(), sizeof(int32_t) * keymap.size(), cudaMemcpyHostToDevice));
@@ -766,9 +926,20 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   ctx->tiers.clear();
   {
     // Row capacities of the shared-memory tiers.  Up to 16 rows per pair two 4-warp CTAs fit an SM (the register limit's
-    // 8 warps), so everything up to there is ONE tier = one first-pass and one resume launch (one tail instead of two).
-    static const int tier_cap[] = {16, 32, 64, 128, (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 8};
-    constexpr int NTIER = sizeof(tier_cap) / sizeof(tier_cap[0]);
+    // 8 warps); the <= 8 and <= 16 row tiers stay separate launches all the same: the smaller row store leaves the SM a
+    // larger L1 for the spilled registers (measured -1 % proximity, -2.5 % Jacobian against one merged tier).
+    // Row capacities of the shared-memory tiers.  Up to 16 rows per pair two 4-warp CTAs fit an SM (the register limit's
+    // 8 warps); the <= 8 and <= 16 row tiers stay separate launches all the same: the smaller row store leaves the SM a
+    // larger L1 for the spilled registers (measured -1 % proximity, -2.5 % Jacobian against one merged tier).
+    const int cap_max = (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 8;
+    std::vector<int> tier_cap = {8, 16, 32, 64, 128};
+    if (const char* e = getenv("DCOL_TIERS")) {          // tuning knob: comma-separated row capacities
+      tier_cap.clear();
+      for (const char* q = e; *q;) { int v = atoi(q); if (v > 0 && v < cap_max) tier_cap.push_back(v); while (*q && *q != ',') q++; if (*q == ',') q++; }
+      std::sort(tier_cap.begin(), tier_cap.end());
+    }
+    tier_cap.push_back(cap_max);
+    const int NTIER = (int)tier_cap.size();
     bool present[NCLS] = {};
     for (int i = 0; i < n_shapes; i++) present[cls[i]] = true;
     // first key of every class pair (keys are class-pair major); key_first[cp+1] closes the range
@@ -839,7 +1010,9 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
   return 0;
 }
 
-double dcol_measure_fp64_tflops(dcol_ctx* ctx) {
+// DFMA throughput of the device: `seconds` of back-to-back launches of an FMA-only kernel (8 independent chains per
+// thread, 8 CTAs of 256 threads per SM), median launch.  bench.py samples the SM clock while this runs.
+double dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds) {
   if (!ctx) return -1.0;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
   cudaDeviceProp prop;
@@ -849,20 +1022,25 @@ double dcol_measure_fp64_tflops(dcol_ctx* ctx) {
   if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
   cudaStream_t s = ctx->stream();
   k_dfma<<<blocks, threads, 0, s>>>(d, 2000, 1.0000001, 1e-9);   // warm-up
-  float best = 1e30f;
-  for (int rep = 0; rep < 3; rep++) {
+  cudaStreamSynchronize(s);
+  std::vector<float> ms_all;
+  double total = 0.0;
+  while (total < seconds * 1e3 && ms_all.size() < 4000) {
     cudaEventRecord(ctx->ev_k0, s);
     k_dfma<<<blocks, threads, 0, s>>>(d, iters, 1.0000001, 1e-9);
     cudaEventRecord(ctx->ev_k1, s);
     cudaEventSynchronize(ctx->ev_k1);
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1);
-    best = std::min(best, ms);
+    ms_all.push_back(ms); total += ms; ctx->launches++;
   }
-  ctx->launches += 4;
   cudaFree(d);
+  if (ms_all.empty()) return -1.0;
+  std::sort(ms_all.begin(), ms_all.end());
+  const double med = ms_all[ms_all.size() / 2];
   double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
-  return flops / (best * 1e-3) / 1e12;
+  return flops / (med * 1e-3) / 1e12;
 }
+double dcol_measure_fp64_tflops(dcol_ctx* ctx) { return dcol_measure_fp64_tflops_for(ctx, 0.6); }
 
 }  // extern "C"
 
@@ -879,7 +1057,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
                      int att_kind, double pdip_tol, int mem,
                      double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters,
                      const int32_t* pose1 = nullptr, const int32_t* pose2 = nullptr, int64_t np1 = 0, int64_t np2 = 0,
-                     int in_mem = -1, int slot = 0, bool async = false) {
+                     int in_mem = -1, int slot = 0, bool async = false, const int32_t* oidx = nullptr) {
   if (!ctx) return -1;
   if (in_mem < 0) in_mem = mem;
   dcol_ctx::Slot& L = ctx->slots[slot];
@@ -895,6 +1073,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
   if (n == 0) return 0;
   if (!shape1 || !shape2 || !r1 || !att1 || !r2 || !att2 || !alpha) { ctx->err = "dcol: NULL input/output pointer"; return -1; }
+  if (oidx && (mem != DCOL_MEM_DEVICE || in_mem == DCOL_MEM_HOST)) { ctx->err = "dcol: result indirection needs device-resident pairs and outputs"; return -1; }
   if (indexed && (!pose2 || np1 <= 0 || np2 <= 0)) { ctx->err = "dcol: indexed query needs pose1, pose2 and the pose table sizes"; return -1; }
   if (query == Q_PROX && !x) { ctx->err = "dcol_proximity: x is NULL"; return -1; }
   if (query != Q_PROX && !deriv) { ctx->err = "dcol: derivative output is NULL"; return -1; }
@@ -923,10 +1102,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   int max_block = 32;
   for (int t = 0; t < nt_tiers; t++) max_block = std::max(max_block, ctx->tiers[t].block);
   CK(L.d_recs.need(sizeof(PairRec) * ((size_t)n + max_block)));      // one tile of slack behind the last record
-  if (!small) {
-    CK(L.d_inv.need(sizeof(int32_t) * n));
-    CK(L.d_sorted.need((size_t)n * (8 + 24 + 4 + 4 + 8) + 5 * 256));
-  }
+  CK(L.d_inv.need(sizeof(int32_t) * n));
+  if (!small) CK(L.d_sorted.need((size_t)n * (8 + 24 + 4 + 4 + 8) + 5 * 256));
   CK(L.d_tables.need(sizeof(LaunchTable) * (1 + MAX_LEVELS) * std::max(1, nt_tiers) * nchunks));
   // straggler overflow area per chunk (upper bound: every tile hands over spill_t pairs of the widest record)
   int spill_div = 8;
@@ -972,13 +1149,34 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     CK(L.d_out.need(b));
     dout = (char*)L.d_out.p;
   }
+  // ---- small synchronous host calls: pack the inputs into one pinned staging area (host memcpy), one H2D copy, one D2H
+  // copy of all results, unpack on the host.  Pageable caller memory would otherwise cost one driver-staged copy per array.
+  constexpr size_t STAGE_MAX = 8u << 20;
+  size_t b_in = 0, b_out = 0;
+  if (in_mem == DCOL_MEM_HOST) b_in = o_a2 + align256(sizeof(double) * na * rows2);
+  if (mem == DCOL_MEM_HOST) b_out = o_mu + align256(sizeof(double) * (ctx->mu_out ? n : 0));
+  const bool staged = !async && nchunks == 1 && mem == DCOL_MEM_HOST && in_mem == DCOL_MEM_HOST && b_in + b_out <= STAGE_MAX;
+  if (staged) {
+    if (ctx->h_stage_cap < 2 * STAGE_MAX) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+      CK(cudaHostAlloc((void**)&ctx->h_stage, 2 * STAGE_MAX, cudaHostAllocDefault));
+      ctx->h_stage_cap = 2 * STAGE_MAX;
+    }
+    char* hs = ctx->h_stage;
+    memcpy(hs + o_s1, shape1, sizeof(int32_t) * n); memcpy(hs + o_s2, shape2, sizeof(int32_t) * n);
+    if (indexed) { memcpy(hs + o_p1, pose1, sizeof(int32_t) * n); memcpy(hs + o_p2, pose2, sizeof(int32_t) * n); }
+    memcpy(hs + o_r1, r1, sizeof(double) * 3 * rows1); memcpy(hs + o_a1, att1, sizeof(double) * na * rows1);
+    memcpy(hs + o_r2, r2, sizeof(double) * 3 * rows2); memcpy(hs + o_a2, att2, sizeof(double) * na * rows2);
+  }
   const int jac = query;                       // kernel variant = query kind
   cudaStream_t S = ctx->stream();
   const bool piped = (nchunks > 1) || async;                  // three-stream pipeline (always for asynchronous submissions)
   cudaStream_t SC = piped ? ctx->s_comp : S;                  // compute stream of the pipeline
   if (piped) { CK(cudaEventRecord(ctx->ev_fork, S)); CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_fork, 0)); CK(cudaStreamWaitEvent(SC, ctx->ev_fork, 0)); }
 
-  if (indexed && in_mem == DCOL_MEM_HOST) {       // pose tables go up once, ahead of the first chunk's pair lists
+  if (staged) CK(cudaMemcpyAsync(di, ctx->h_stage, b_in, cudaMemcpyHostToDevice, S));
+  if (indexed && in_mem == DCOL_MEM_HOST && !staged) {       // pose tables go up once, ahead of the first chunk's pair lists
     cudaStream_t SI = piped ? ctx->s_copy : S;
     CK(cudaMemcpyAsync(di + o_r1, r1, sizeof(double) * 3 * np1, cudaMemcpyHostToDevice, SI));
     CK(cudaMemcpyAsync(di + o_a1, att1, sizeof(double) * na * np1, cudaMemcpyHostToDevice, SI));
@@ -986,6 +1184,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     CK(cudaMemcpyAsync(di + o_a2, att2, sizeof(double) * na * np2, cudaMemcpyHostToDevice, SI));
   }
   // chunk boundaries: a short first chunk lets the kernels start early while the bulk is still crossing PCIe
+  for (int c = 0; c < nchunks; c++) L.h_bad[c] = 0;
   std::vector<int64_t> cb(nchunks + 1, 0);
   {
     const int64_t first = (nchunks > 1) ? std::min<int64_t>(n / (2 * nchunks), 120000) : n;
@@ -1002,8 +1201,10 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     PairSource src;
     memset(&src, 0, sizeof(src));
     src.na = na;
+    src.oidx = oidx ? oidx + c0 : nullptr;
     if (in_mem == DCOL_MEM_HOST) {
       cudaStream_t SI = piped ? ctx->s_copy : S;
+      if (!staged) {
       CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       CK(cudaMemcpyAsync(di + o_s2 + sizeof(int32_t) * c0, shape2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       if (indexed) {
@@ -1014,6 +1215,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
         CK(cudaMemcpyAsync(di + o_a1 + sizeof(double) * na * c0, att1 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
         CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
         CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+      }
       }
       if (piped) { CK(cudaEventRecord(L.ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, L.ev_in[c], 0)); }
       src.shape1 = (const int32_t*)(di + o_s1) + c0; src.shape2 = (const int32_t*)(di + o_s2) + c0;
@@ -1045,7 +1247,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     // the solver stores the per-pair scalars in SORTED order (coalesced); k_unpermute brings them into caller order.
     // Derivative rows (120-488 contiguous bytes per pair) go to their final place directly.
     PairRec* d_recs = (PairRec*)L.d_recs.p + c0;
-    int32_t* d_inv = small ? nullptr : (int32_t*)L.d_inv.p + c0;
+    int32_t* d_inv = (int32_t*)L.d_inv.p + c0;
     double* s_alpha = nullptr; double* s_x = nullptr; int32_t* s_st = nullptr; int32_t* s_it = nullptr; double* s_mu = nullptr;
     if (small) {
       P.alpha = f_alpha; P.x = f_x; P.status = f_st; P.iters = f_it; P.mu = f_mu;
@@ -1065,31 +1267,35 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     int* d_hist = (int*)L.d_hist.p + hist_stride * c;
     int* d_off = d_hist + nk;            // nk+1
     int* d_cursor = d_off + nk + 1;      // nk
-    int* d_bad = d_cursor + nk;          // 1
-    int* d_counter = d_bad + 1;          // one tile counter per shared-memory tier and pass
+    int* d_bad = L.d_bad_map + c;        // mapped host flag of this chunk
+    int* d_counter = d_cursor + nk + 1;  // one tile counter per shared-memory tier and pass
     LaunchTable* d_tab = (LaunchTable*)L.d_tables.p + (size_t)(1 + MAX_LEVELS) * std::max(1, nt_tiers) * c;
     double* d_ovc = (double*)L.d_ov.p + 2 * ov_doubles * c;
     const int32_t* d_keymap = ctx->use_keymap ? (const int32_t*)ctx->d_keymap.p : nullptr;
-    if (small) {
+    if (ctx->copy_only) {
+      // measurement mode: the copies of this call with the same buffers, streams and chunking, and no kernels
+    } else if (small) {
       k_small_prep<<<1, SMALL_THREADS, sizeof(int) * (nk + 1), SC>>>(src, (int)nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk,
-                                                                      d_off, d_counter, (2 + MAX_LEVELS) * NSIDE, d_bad, d_recs,
+                                                                      d_off, d_counter, (2 + MAX_LEVELS) * NSIDE, d_bad, d_inv,
                                                                       (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P);
-      ctx->launches += 1;
+      k_pack<<<(int)std::min<int64_t>((nc + 127) / 128, 148 * 16), 128, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
+      ctx->launches += 2;
     } else {
       CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
       int threads = 256;
       int blocks = (int)std::min<int64_t>((nc + threads * 8 - 1) / (threads * 8), 1184);
       k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(src.shape1, src.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
       k_scan_tables<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor, (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P, spill_div);
-      k_scatter_pack<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_recs, d_inv);
-      ctx->launches += 3;
+      k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(src.shape1, src.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_inv);
+      k_pack<<<(int)std::min<int64_t>((nc + 255) / 256, 148 * 32), 256, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
+      ctx->launches += 4;
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table
     CK(cudaEventRecord(L.ev_t0[c], SC));
     // per tier, on the tier's stream: first pass, then (right behind it) the resume passes that finish the handed-over
     // stragglers in dense tiles — the resume pass of one tier overlaps the first pass of the next
     if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
-    for (int t = 0; t < nt_tiers; t++) {
+    for (int t = 0; t < nt_tiers && !ctx->copy_only; t++) {
       const dcol_ctx::Tier& TR = ctx->tiers[t];
       cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
       if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
@@ -1104,14 +1310,16 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       }
       if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
     }
-    if (!small) {
+    if (!small && !ctx->copy_only) {
       const int blocks = (int)std::min<int64_t>((nc + 255) / 256, 148 * 16);
-      k_unpermute<<<blocks, 256, 0, SC>>>(nc, d_inv, s_alpha, s_x, s_st, s_it, s_mu, f_alpha, f_x, f_st, f_it, f_mu);
+      k_unpermute<<<blocks, 256, 0, SC>>>(nc, d_inv, src.oidx, s_alpha, s_x, s_st, s_it, s_mu, f_alpha, f_x, f_st, f_it, f_mu);
       ctx->launches += 1;
     }
     CK(cudaEventRecord(L.ev_t1[c], SC));
     // ---- results of this chunk back (host mode), overlapping the next chunk's kernels
-    if (mem == DCOL_MEM_HOST) {
+    if (staged) {
+      CK(cudaMemcpyAsync(ctx->h_stage + STAGE_MAX, dout, b_out, cudaMemcpyDeviceToHost, S));
+    } else if (mem == DCOL_MEM_HOST) {
       cudaStream_t SO = piped ? ctx->s_out : S;
       if (piped) { CK(cudaEventRecord(L.ev_done[c], SC)); CK(cudaStreamWaitEvent(SO, L.ev_done[c], 0)); }
       CK(cudaMemcpyAsync(alpha + c0, dout + o_alpha + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
@@ -1122,19 +1330,26 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (ctx->mu_out) CK(cudaMemcpyAsync(ctx->mu_out + c0, dout + o_mu + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
     }
   }
-  // ---- the bad-shape flags come back with the results; the join is finish_query (the only host synchronisation)
-  for (int c = 0; c < nchunks; c++) L.h_bad[c] = 0;
+  // ---- the join is finish_query (the only host synchronisation); the bad-shape flags are mapped host memory
   cudaStream_t SL = piped ? ctx->s_out : S;
   if (piped && mem != DCOL_MEM_HOST) { CK(cudaEventRecord(L.ev_done[0], SC)); CK(cudaStreamWaitEvent(SL, L.ev_done[0], 0)); }
-  for (int c = 0; c < nchunks; c++)
-    CK(cudaMemcpyAsync(&L.h_bad[c], (int*)L.d_hist.p + hist_stride * c + 3 * (size_t)nk + 1, sizeof(int), cudaMemcpyDeviceToHost, SL));
   // join point of THIS submission: everything it enqueued precedes ev_end on SL (the compute stream's last work
   // is ordered before it through ev_done), so waiting for it does not wait for later submissions
   if (piped) { CK(cudaEventRecord(L.ev_done[nchunks - 1], SC)); CK(cudaStreamWaitEvent(SL, L.ev_done[nchunks - 1], 0)); }
   CK(cudaEventRecord(L.ev_end, SL));
   L.pending = true; L.nchunks = nchunks; L.piped = piped; L.result = 0;
   if (async) return 0;
-  return finish_query(ctx, slot);
+  const int rc = finish_query(ctx, slot);
+  if (staged && rc == 0) {
+    const char* ho = ctx->h_stage + STAGE_MAX;
+    memcpy(alpha, ho + o_alpha, sizeof(double) * n);
+    if (x) memcpy(x, ho + o_x, sizeof(double) * 3 * n);
+    if (dsz) memcpy(deriv, ho + o_der, sizeof(double) * dsz * n);
+    if (status) memcpy(status, ho + o_st, sizeof(int32_t) * n);
+    if (iters) memcpy(iters, ho + o_it, sizeof(int32_t) * n);
+    if (ctx->mu_out) memcpy(ctx->mu_out, ho + o_mu, sizeof(double) * n);
+  }
+  return rc;
 }
 
 // Join one submission: wait for its streams, collect the kernel time and the bad-index flags.
@@ -1211,6 +1426,38 @@ int dcol_query_indexed(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape
                    pose1, pose2, n_pose1, n_pose2);
 }
 
+// Broad phase of dcol_scene_allpairs / dcol_scene_wrench (opt-in; the reference's contact example solves every pair):
+// alpha_cut > 0 answers every pair whose bounding balls prove alpha* > alpha_cut without running the conic solver
+// (alpha = the lower bound |r~_i - r~_j| / (rho_i + rho_j) > alpha_cut, status DCOL_STATUS_CULLED = 3, iters 0, zero derivative rows,
+// NaN witness point); all other pairs are solved exactly as before, bit for bit.  alpha_cut <= 0 switches it off.
+int dcol_scene_set_cull(dcol_ctx* ctx, double alpha_cut) {
+  if (!ctx) return -1;
+  ctx->cull_alpha = (alpha_cut > 0.0 && alpha_cut == alpha_cut) ? alpha_cut : 0.0;
+  return 0;
+}
+
+// centres, cull kernel, survivor count: fills the compact pair list (s1, s2, p1, p2, oidx) and returns its length in *n_keep
+static int scene_cull(dcol_ctx* ctx, cudaStream_t S, int n_bodies, int64_t np, const int32_t* d_shape, const double* d_r, const double* d_att,
+                      int att_kind, int nd, int32_t* s1, int32_t* s2, int32_t* p1, int32_t* p2, int32_t* oidx,
+                      double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters, int64_t* n_keep) {
+  if (!ctx->h_count) CK(cudaHostAlloc((void**)&ctx->h_count, 2 * sizeof(int), cudaHostAllocDefault));
+  CK(ctx->d_cull.need(sizeof(double) * 3 * (size_t)n_bodies + 256));
+  double* d_centre = (double*)ctx->d_cull.p;
+  int* d_count = (int*)((char*)ctx->d_cull.p + sizeof(double) * 3 * (size_t)n_bodies);      // count, bad flag
+  CK(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), S));
+  k_body_centres<<<(n_bodies + 127) / 128, 128, 0, S>>>(n_bodies, d_shape, (const DevShape*)ctx->d_shapes.p, ctx->n_shapes, d_r, d_att, att_kind,
+                                                        d_centre, d_count + 1);
+  k_allpairs_cull<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, ctx->n_shapes, (const double*)ctx->d_brad.p,
+                                                                                       d_centre, ctx->cull_alpha, nd, s1, s2, p1, p2, oidx, d_count,
+                                                                                       alpha, x, deriv, status, iters);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(ctx->h_count, d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, S));
+  CK(cudaStreamSynchronize(S));
+  *n_keep = ctx->h_count[0];
+  return 0;
+}
+
 int64_t dcol_scene_pair_count(int n_bodies) { return n_bodies < 2 ? 0 : (int64_t)n_bodies * (n_bodies - 1) / 2; }
 
 int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* shape, const double* r, const double* att,
@@ -1240,8 +1487,42 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
     d_shape = (const int32_t*)d; d_r = (const double*)(d + b0); d_att = (const double*)(d + b0 + b1);
   }
   // pair lists generated on the device
-  CK(ctx->d_pairs.need(sizeof(int32_t) * 4 * (size_t)np));
-  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* p1 = s2 + np; int32_t* p2 = p1 + np;
+  CK(ctx->d_pairs.need(sizeof(int32_t) * 5 * (size_t)np));
+  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* p1 = s2 + np; int32_t* p2 = p1 + np; int32_t* oidx = p2 + np;
+  if (ctx->cull_alpha > 0.0) {
+    // broad phase: results of all np pairs live in device arrays (the caller's, or scratch when the caller's are host memory);
+    // far pairs are answered by the cull kernel, the survivors by the solver through the result indirection oidx
+    const int nt = 6 + 2 * na;
+    const int nd = (query == Q_GRAD) ? nt : (query == Q_JAC ? 4 * nt : 0);
+    const bool host = (mem == DCOL_MEM_HOST);
+    double* q_alpha = alpha; double* q_x = x; double* q_der = deriv; int32_t* q_st = status; int32_t* q_it = iters;
+    const size_t w_a = align256(sizeof(double) * (size_t)np), w_x = align256(sizeof(double) * 3 * (size_t)np),
+                 w_d = align256(sizeof(double) * (size_t)nd * (size_t)np), w_i = align256(sizeof(int32_t) * (size_t)np);
+    if (host) {
+      CK(ctx->d_wrench.need(w_a + w_x + w_d + 2 * w_i));
+      char* wb = (char*)ctx->d_wrench.p;
+      q_alpha = (double*)wb; q_x = x ? (double*)(wb + w_a) : nullptr; q_der = nd ? (double*)(wb + w_a + w_x) : nullptr;
+      q_st = (int32_t*)(wb + w_a + w_x + w_d); q_it = (int32_t*)(wb + w_a + w_x + w_d + w_i);
+    }
+    if (!q_alpha || (query != Q_GRAD && !q_x) || (nd && !q_der)) { ctx->err = "dcol_scene_allpairs: NULL output pointer"; return -1; }
+    int64_t n_keep = 0;
+    { int rc = scene_cull(ctx, S, n_bodies, np, d_shape, d_r, d_att, att_kind, nd, s1, s2, p1, p2, oidx, q_alpha, q_x, q_der, q_st, q_it, &n_keep); if (rc) return rc; }
+    if (ctx->h_count[1]) { ctx->err = "dcol: shape index out of range in shape"; return -1; }
+    if (n_keep > 0) {
+      int rc = run_query(ctx, query, n_keep, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE, q_alpha, q_x, q_der, q_st, q_it,
+                         p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE, 0, false, oidx);
+      if (rc) return rc;
+    }
+    if (host) {
+      CK(cudaMemcpyAsync(alpha, q_alpha, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
+      if (x) CK(cudaMemcpyAsync(x, q_x, sizeof(double) * 3 * (size_t)np, cudaMemcpyDeviceToHost, S));
+      if (nd) CK(cudaMemcpyAsync(deriv, q_der, sizeof(double) * (size_t)nd * (size_t)np, cudaMemcpyDeviceToHost, S));
+      if (status) CK(cudaMemcpyAsync(status, q_st, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+      if (iters) CK(cudaMemcpyAsync(iters, q_it, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+      CK(cudaStreamSynchronize(S));
+    }
+    return 0;
+  }
   k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -1293,20 +1574,31 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
     CK(cudaMemcpyAsync(d_lambda, lambda, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, S));
     d_shape = (const int32_t*)d; d_r = (const double*)(d + b0); d_att = (const double*)(d + b0 + b1); d_lam = d_lambda;
   }
-  CK(ctx->d_pairs.need(sizeof(int32_t) * 4 * (size_t)np));
-  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* p1 = s2 + np; int32_t* p2 = p1 + np;
-  k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
-  CK(cudaGetLastError());
-  ctx->launches++;
+  CK(ctx->d_pairs.need(sizeof(int32_t) * 5 * (size_t)np));
+  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* p1 = s2 + np; int32_t* p2 = p1 + np; int32_t* oidx = p2 + np;
   const bool host = (mem == DCOL_MEM_HOST);
+  const bool cull = ctx->cull_alpha > 0.0;
   double* q_alpha = (host || !alpha) ? d_alpha : alpha;
-  int32_t* q_status = host ? (status ? d_status : nullptr) : status;
+  int32_t* q_status = host ? ((status || cull) ? d_status : nullptr) : (status ? status : (cull ? d_status : nullptr));
   int32_t* q_iters = host ? (iters ? d_iters : nullptr) : iters;
-  int rc = run_query(ctx, Q_GRAD, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE,
-                     q_alpha, nullptr, d_grad, q_status, q_iters, p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE);
+  int rc = 0;
+  if (cull) {
+    int64_t n_keep = 0;
+    rc = scene_cull(ctx, S, n_bodies, np, d_shape, d_r, d_att, att_kind, nt, s1, s2, p1, p2, oidx, q_alpha, nullptr, nullptr, q_status, q_iters, &n_keep);
+    if (rc) return rc;
+    if (ctx->h_count[1]) { ctx->err = "dcol: shape index out of range in shape"; return -1; }
+    if (n_keep > 0) rc = run_query(ctx, Q_GRAD, n_keep, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE,
+                                   q_alpha, nullptr, d_grad, q_status, q_iters, p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE, 0, false, oidx);
+  } else {
+    k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    rc = run_query(ctx, Q_GRAD, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE,
+                   q_alpha, nullptr, d_grad, q_status, q_iters, p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE);
+  }
   if (rc) return rc;
   double* o = host ? d_out : wrench;
-  k_scene_wrench<<<n_bodies, 128, 0, S>>>(n_bodies, d_grad, d_lam, d_att, att_kind, o);
+  k_scene_wrench<<<n_bodies, 128, 0, S>>>(n_bodies, d_grad, d_lam, cull ? q_status : nullptr, d_att, att_kind, o);
   CK(cudaGetLastError());
   ctx->launches++;
   if (host) {

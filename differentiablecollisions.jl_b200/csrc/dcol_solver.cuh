@@ -22,14 +22,8 @@
 #include "dcol_common.cuh"
 #include "dcol_deriv.cuh"
 
-#ifndef DCOL_LOCKSTEP
-#define DCOL_LOCKSTEP 1
-#endif
-#if DCOL_LOCKSTEP
+// one block-wide vote per interior-point iteration (the hand-over capacity of a bin assumes CTA-wide votes)
 #define DCOL_COUNT(pred) __syncthreads_count(pred)
-#else
-#define DCOL_COUNT(pred) __popc(__ballot_sync(0xffffffffu, pred))
-#endif
 
 namespace dcol {
 

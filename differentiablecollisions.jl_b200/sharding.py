@@ -71,3 +71,21 @@ def bind_to_gpu_numa_node(device_index: int) -> dict:
     except Exception as e:  # noqa: BLE001
         info["error"] = str(e)
     return info
+
+
+def bind_disjoint_cpus(local_rank: int, local_world: int) -> dict:
+    """Fallback when the box exposes no NUMA topology (numa_node = -1 in a VM): give every rank of the box its own
+    contiguous slice of the allowed CPUs, so that the ranks' host-side work (submission threads, pinned-buffer first
+    touch) does not migrate over each other.  Returns what was done; never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        if local_world > 1 and len(allowed) >= local_world:
+            k = len(allowed) // local_world
+            mine = allowed[local_rank * k:(local_rank + 1) * k]
+            os.sched_setaffinity(0, mine)
+            info.update(bound=True, cpus=len(mine), first_cpu=mine[0], policy="disjoint slice per rank")
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)
+    return info

@@ -59,6 +59,7 @@ extern "C" {
 #define DCOL_STATUS_OK          0
 #define DCOL_STATUS_PDIP_FAILED 1
 #define DCOL_STATUS_NUMERICAL   2
+#define DCOL_STATUS_CULLED      3   /* scene operators with dcol_scene_set_cull only: far pair, alpha is a lower bound */
 
 typedef struct dcol_ctx dcol_ctx;
 
@@ -140,6 +141,15 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
                       int att_kind, double pdip_tol, int mem,
                       double* alpha, double* wrench, int32_t* status, int32_t* iters);
 
+/* Broad phase of the two scene operators above (opt-in: the reference's contact example,
+ * examples/contact_physics/ncp_contact_simulation.jl:86-89,133-139, solves every pair).  Every primitive scales about its
+ * body origin r~ = r + Qn r_offset and lies inside the ball of radius rho around it, so alpha* >= |r~_i - r~_j| / (rho_i + rho_j).
+ * With alpha_cut > 0 the pairs whose bound exceeds alpha_cut are answered without the conic solve: alpha = that lower
+ * bound (> alpha_cut), status = DCOL_STATUS_CULLED, iters = 0, zero derivative rows, NaN witness point; in
+ * dcol_scene_wrench they contribute nothing.  All other pairs are solved exactly as without the cull (bit-identical).
+ * alpha_cut <= 0 switches the cull off (the default). */
+int dcol_scene_set_cull(dcol_ctx* ctx, double alpha_cut);
+
 /* Planar vehicle against static obstacles: the constraint functions of the trajectory-optimisation examples
  * (examples/trajectory_optimization/piano_mover.jl:39-53, ineq_con_x / ineq_con_x_jac) for a batch of states.  Every state
  * s = (x, y, theta) puts the vehicle shape at r = (x, y, 0) with MRP p = (0, 0, tan(theta/4)); for every obstacle o
@@ -194,8 +204,13 @@ int64_t dcol_launch_count(const dcol_ctx* ctx);
 /* device time (ms) of the solver+derivative kernels of the last query call, measured with CUDA
  * events on the launching streams; <0 if unavailable */
 double  dcol_last_kernel_ms(const dcol_ctx* ctx);
-/* measured FP64 FMA throughput of the device in TFLOP/s (DFMA micro-benchmark, ~50 ms) */
+/* measured FP64 FMA throughput of the device in TFLOP/s: DFMA-only kernel launched back to back for `seconds`
+ * (0.6 s for the short form), median launch; the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry) */
 double  dcol_measure_fp64_tflops(dcol_ctx* ctx);
+double  dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds);
+/* measurement knob: host-pointer calls issue their host<->device copies (same staging, streams, chunking) but no kernels;
+ * gives the copy-only bound of the end-to-end path */
+int     dcol_set_copy_only(dcol_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }

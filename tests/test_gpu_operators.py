@@ -254,3 +254,85 @@ def test_se2_constraints_match_the_example_formulas(ctx, oracle):
         ctx.se2_constraints(xyt[:10], 999, so, r_obs, p_obs)
     again = ctx.se2_constraints(xyt[:10], sv, so, r_obs, p_obs)              # the context stays usable after an API error
     assert np.array_equal(again["c"], out["c"][:10])
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_scene_cull_keeps_near_pairs_bit_identical(ctx, att_kind, kind):
+    """dcol_scene_set_cull (SURVEY.md §8f-1 broad phase): pairs that survive the bounding-ball test are bit-identical to
+    the call without the cull; culled pairs truly have alpha > alpha_cut, carry a valid lower bound of it, status 3,
+    zero derivative rows."""
+    nb = 300
+    t, shape, r, att = scene_bodies(nb, att_kind, spread=4.0)
+    ctx.set_shape_arrays(*t.arrays())
+    full = ctx.scene_allpairs(kind, shape, r, att, att_kind)
+    for cut in (1.0, 2.5):
+        try:
+            ctx.scene_set_cull(cut)
+            c = ctx.scene_allpairs(kind, shape, r, att, att_kind)
+        finally:
+            ctx.scene_set_cull(0.0)
+        culled = c["status"] == 3
+        assert culled.any() and (~culled).any()
+        for k in c:
+            assert np.array_equal(c[k][~culled], full[k][~culled], equal_nan=True), (k, cut)
+        ok = culled & (full["status"] == 0)
+        assert (full["alpha"][ok] > cut).all()                       # nothing within the interaction radius is lost
+        assert (c["alpha"][culled] > cut).all() and (c["alpha"][ok] <= full["alpha"][ok] * (1 + 1e-9)).all()   # a lower bound
+        assert (c["iters"][culled] == 0).all()
+        if kind == 1:
+            assert (c["grad"][culled] == 0).all()
+        if kind == 2:
+            assert (c["J"][culled] == 0).all() and np.isnan(c["x"][culled]).all()
+        if cut == 1.0:
+            assert ((full["alpha"] <= 1) & (full["status"] == 0) <= ~culled).all()      # every colliding pair is solved
+
+
+def test_scene_cull_with_offsets_and_wrench(ctx):
+    """the cull respects r_offset (ball centre r + Qn r_offset) and dcol_scene_wrench skips culled pairs consistently"""
+    nb = 200
+    A5, b5 = dc.create_n_sided(5, 0.6)
+    protos = [dc.Capsule(0.3, 1.2), dc.Sphere(0.8), dc.Cone(2.0, np.deg2rad(22)), dc.create_rect_prism(1.0, 1.0, 1.0, attitude="quat")[0],
+              dc.Polygon(A5, b5, 0.2), dc.Ellipsoid(util.ELL_P), dc.Cylinder(0.6, 3.0)]
+    g = util.rng(4)
+    for p in protos:
+        p.r_offset = 1.5 * g.standard_normal(3)
+        p.Q_offset = dc.dcm_from_q(g.standard_normal(4))
+    t = dc.ShapeTable(); ids = np.array([t.add(p) for p in protos], np.int32)
+    shape = ids[np.arange(nb) % len(ids)]
+    r = 4.0 * g.standard_normal((nb, 3)); q = g.standard_normal((nb, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    ctx.set_shape_arrays(*t.arrays())
+    full = ctx.scene_allpairs(1, shape, r, q, 0)
+    lam = g.random(full["alpha"].shape[0])
+    lam_near = np.where(full["alpha"] <= 2.0, lam, 0.0)             # the caller's multipliers vanish outside the interaction radius
+    w_full = ctx.scene_wrench(shape, r, q, lam_near, 0)
+    try:
+        ctx.scene_set_cull(2.0)
+        c = ctx.scene_allpairs(1, shape, r, q, 0)
+        w_cull = ctx.scene_wrench(shape, r, q, lam_near, 0)
+    finally:
+        ctx.scene_set_cull(0.0)
+    culled = c["status"] == 3
+    assert culled.mean() > 0.3 and (full["alpha"][culled & (full["status"] == 0)] > 2.0).all()
+    assert np.array_equal(c["grad"][~culled], full["grad"][~culled], equal_nan=True)
+    np.testing.assert_allclose(w_cull["wrench"], w_full["wrench"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(w_cull["status"] == 3, culled)
+
+
+def test_scene_cull_config4(ctx):
+    """BASELINE config 4 with the contact example's interaction radius (alpha_cut = 1: only colliding pairs matter to the
+    complementarity rows, ncp_contact_simulation.jl:143-149): same colliding set as the full solve."""
+    nb = 4096
+    t, shape, r, att = scene_bodies(nb, 0, spread=5.0)
+    ctx.set_shape_arrays(*t.arrays())
+    full = ctx.scene_allpairs(0, shape, r, att, 0)
+    try:
+        ctx.scene_set_cull(1.0)
+        c = ctx.scene_allpairs(0, shape, r, att, 0)
+    finally:
+        ctx.scene_set_cull(0.0)
+    culled = c["status"] == 3
+    hit = (full["alpha"] <= 1) & (full["status"] == 0)
+    assert not (hit & culled).any()
+    assert np.array_equal(c["alpha"][~culled], full["alpha"][~culled]) and np.array_equal(c["x"][~culled], full["x"][~culled])
+    assert culled.mean() > 0.5

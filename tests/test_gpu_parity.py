@@ -479,12 +479,12 @@ def test_final_mu_output(ctx):
 
 @pytest.mark.parametrize("kind", [0, 1, 2])
 def test_small_batch_path_matches_the_binned_path(ctx, kind):
-    """n <= 4096 runs the single-block preparation without hand-over and un-permute pass; results are bit-identical to the
+    """n <= 16384 runs the single-block preparation without hand-over and un-permute pass; results are bit-identical to the
     same pairs inside a large batch (sorted, handed over, un-permuted)."""
     t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(30000, 0, seed=11, variant="scene")
     ctx.set_shape_arrays(*t.arrays())
     big = ctx._batch(kind, s1, s2, r1, a1, r2, a2, 0, 1e-6)
-    for n in (1, 2, 33, 4096):
+    for n in (1, 2, 33, 4096, 16384):
         sm = ctx._batch(kind, s1[:n], s2[:n], r1[:n], a1[:n], r2[:n], a2[:n], 0, 1e-6)
         for k in sm:
             assert np.array_equal(sm[k], big[k][:n], equal_nan=True), (k, n)

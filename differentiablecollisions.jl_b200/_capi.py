@@ -45,6 +45,10 @@ SYMBOLS = {
                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "dcol_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dcol_solve_socp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_warm_stride": (C.c_int64, [C.c_void_p]),
+    "dcol_set_warm_start": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
     "dcol_set_mu_output": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcol_set_max_iters": (C.c_int, [C.c_void_p, C.c_int]),
     "dcol_launch_count": (C.c_int64, [C.c_void_p]),

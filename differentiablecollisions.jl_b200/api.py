@@ -158,6 +158,35 @@ class Context:
         return out
 
     # ---- batched host API ----------------------------------------------------------------------
+    def solve_socp(self, c, G, h, n_ort, d1, d2, pdip_tol=1e-4):
+        """`dcol_solve_socp`: the reference's solve_socp (static_solver2.jl:106-191; default pdip_tol 1e-4 as there, :112) on
+        one problem (G: ns x nx) or a batch (G: n x ns x nx).  Returns (x, s, z, status, iters)."""
+        G = np.ascontiguousarray(G, dtype=np.float64)
+        single = G.ndim == 2
+        if single:
+            G = G[None]
+        n, ns, nx = G.shape
+        c = np.ascontiguousarray(np.broadcast_to(np.asarray(c, dtype=np.float64).reshape(-1, nx), (n, nx)))
+        h = np.ascontiguousarray(np.broadcast_to(np.asarray(h, dtype=np.float64).reshape(-1, ns), (n, ns)))
+        x = np.empty((n, nx)); s = np.empty((n, ns)); z = np.empty((n, ns))
+        status = np.empty(n, dtype=np.int32); iters = np.empty(n, dtype=np.int32)
+        self._check(self._lib.dcol_solve_socp(self._h, n, nx, int(n_ort), int(d1), int(d2), _ptr(c), _ptr(G), _ptr(h), float(pdip_tol),
+                                              MEM_HOST, _ptr(x), _ptr(s), _ptr(z), _ptr(status), _ptr(iters)))
+        if single:
+            return x[0], s[0], z[0], int(status[0]), int(iters[0])
+        return x, s, z, status, iters
+
+    def warm_stride(self) -> int:
+        if self._table_version is not None:
+            self.sync_shapes()
+        return int(self._lib.dcol_warm_stride(self._h))
+
+    def set_warm_start(self, state=None, capacity_pairs: int = 0, mu_save: float = 1e-2):
+        """Opt-in warm start (`dcol_set_warm_start`; not in the reference, excluded from parity).  `state`: a zero-initialised
+        CUDA tensor of capacity_pairs * warm_stride() doubles that the caller keeps alive; None switches it off."""
+        self._warm_keepalive = state
+        self._check(self._lib.dcol_set_warm_start(self._h, _ptr(state), int(capacity_pairs), float(mu_save)))
+
     def set_max_iters(self, k: int = 50):
         """Testing knob (dcol_set_max_iters): iteration cap of the solver, 50 in the reference and by default."""
         self._check(self._lib.dcol_set_max_iters(self._h, int(k)))

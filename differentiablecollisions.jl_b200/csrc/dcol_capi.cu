@@ -22,6 +22,9 @@ const void* persistent_kernel_ptr_v0(); const void* persistent_kernel_ptr_v1(); 
 cudaError_t launch_persistent_v0(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
 cudaError_t launch_persistent_v1(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
 cudaError_t launch_persistent_v2(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
+cudaError_t launch_solve_socp(int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h, double tol, int max_iters,
+                              double* x, double* s, double* z, int32_t* status, int32_t* iters, cudaStream_t st);        // dcol_socp.cu
+int socp_limit(int which);
 static const void* persistent_kernel_ptr(int var) {
   return var == 2 ? persistent_kernel_ptr_v2() : (var == 1 ? persistent_kernel_ptr_v1() : persistent_kernel_ptr_v0());
 }
@@ -106,6 +109,7 @@ struct dcol_ctx {
   int64_t launches = 0;
   double last_ms = -1.0;
   int max_iters = MAX_ITERS;            // testing knob (dcol_set_max_iters); the reference's 50 otherwise
+  double* warm = nullptr; int64_t warm_cap = 0; double warm_mu = 1e-2;   // opt-in warm start (dcol_set_warm_start)
   bool copy_only = false;               // measurement knob (dcol_set_copy_only): host<->device copies without kernels
   double* mu_out = nullptr;             // optional per-pair final duality measure (dcol_set_mu_output), same memory space as the query's outputs
   cudaStream_t stream() const { return user ? user : own; }
@@ -784,6 +788,25 @@ int dcol_set_mu_output(dcol_ctx* ctx, double* mu) {
   return 0;
 }
 
+// Opt-in warm start (NOT in the reference, which always starts from `initialize`, and excluded from
+// parity: iteration counts change, results agree with a cold solve to the solver tolerance).  `state` is DEVICE memory
+// of capacity_pairs x dcol_warm_stride(ctx) doubles, zero-initialised by the caller, addressed by the pair index of the
+// following queries.  Each solve leaves behind its iterate at the first iteration whose duality measure fell below
+// mu_save (<= 0: 1e-2); a later solve of the same pair index with the same two shapes starts from it instead of the
+// reference's initial point.  state == NULL switches it off.  dcol_set_shapes invalidates the stride: set the table first.
+int64_t dcol_warm_stride(const dcol_ctx* ctx) {
+  if (!ctx) return 0;
+  int stride = 0;
+  for (const dcol_ctx::Tier& TR : ctx->tiers) stride = std::max(stride, TR.max_stride);
+  return stride;
+}
+int dcol_set_warm_start(dcol_ctx* ctx, double* state, int64_t capacity_pairs, double mu_save) {
+  if (!ctx) return -1;
+  if (state && capacity_pairs <= 0) { ctx->err = "dcol_set_warm_start: capacity_pairs must be positive"; return -1; }
+  ctx->warm = state; ctx->warm_cap = state ? capacity_pairs : 0; ctx->warm_mu = mu_save > 0.0 ? mu_save : 1e-2;
+  return 0;
+}
+
 // Measurement knob: the following host-pointer calls issue their host<->device copies (same staging buffers, streams,
 // chunking and events) but no kernels, which gives the copy-only bound of the end-to-end path (bench.py: e2e.copy_bound).
 int dcol_set_copy_only(dcol_ctx* ctx, int on) {
@@ -1198,6 +1221,12 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     memset(&P, 0, sizeof(P));
     P.shapes = (const DevShape*)ctx->d_shapes.p; P.rows = (const double*)ctx->d_rows.p;
     P.att_kind = att_kind; P.pdip_tol = pdip_tol; P.query = query; P.max_iters = ctx->max_iters; P.direct = small ? 1 : 0;
+    if (ctx->warm) {      // records are addressed by the caller's pair index of this call
+      int stride = 0;
+      for (const dcol_ctx::Tier& TR : ctx->tiers) stride = std::max(stride, TR.max_stride);
+      P.warm = ctx->warm + (size_t)c0 * stride; P.warm_stride = stride;
+      P.warm_cap = (int)std::max<int64_t>(0, std::min<int64_t>(ctx->warm_cap - c0, 0x7fffffff)); P.warm_mu = ctx->warm_mu;
+    }
     PairSource src;
     memset(&src, 0, sizeof(src));
     src.na = na;
@@ -1669,6 +1698,46 @@ int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta,
     CK(cudaMemcpyAsync(c, d_c, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
     if (Jc) CK(cudaMemcpyAsync(Jc, d_J, sizeof(double) * 3 * (size_t)np, cudaMemcpyDeviceToHost, S));
     if (status) CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+  }
+  CK(cudaStreamSynchronize(S));
+  return 0;
+}
+
+// Generic batched conic solve (dcol_socp.cu): the reference's solve_socp on n problems of common dimensions.
+int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
+                    double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  const int ns = n_ort + d1 + d2;
+  if (n < 0 || nx < 1 || nx > socp_limit(0) || n_ort < 0 || d1 < 0 || d2 < 0 || ns < 1 || ns > socp_limit(1) || d1 > socp_limit(2) || d2 > socp_limit(2) ||
+      d1 == 1 || d2 == 1) { ctx->err = "dcol_solve_socp: dimensions out of range (nx <= 16, n_ort + d1 + d2 <= 96, d in {0, 2..8})"; return -1; }
+  if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
+  if (n == 0) return 0;
+  if (!c || !G || !h || !x || !s || !z) { ctx->err = "dcol_solve_socp: NULL pointer"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  { int rc = drain_all(ctx); if (rc) return rc; }
+  cudaStream_t S = ctx->stream();
+  const double *dc_ = c, *dG = G, *dh = h; double *dx = x, *ds = s, *dz = z; int32_t *dst = status, *dit = iters;
+  const size_t bc = align256(sizeof(double) * nx * (size_t)n), bG = align256(sizeof(double) * (size_t)ns * nx * (size_t)n), bh = align256(sizeof(double) * ns * (size_t)n),
+               bi = align256(sizeof(int32_t) * (size_t)n);
+  if (mem == DCOL_MEM_HOST) {
+    CK(ctx->d_wrench.need(2 * bc + bG + 3 * bh + 2 * bi));
+    char* w = (char*)ctx->d_wrench.p;
+    CK(cudaMemcpyAsync(w, c, sizeof(double) * nx * (size_t)n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(w + bc, G, sizeof(double) * (size_t)ns * nx * (size_t)n, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(w + bc + bG, h, sizeof(double) * ns * (size_t)n, cudaMemcpyHostToDevice, S));
+    dc_ = (const double*)w; dG = (const double*)(w + bc); dh = (const double*)(w + bc + bG);
+    dx = (double*)(w + bc + bG + bh); ds = (double*)(w + 2 * bc + bG + bh); dz = (double*)(w + 2 * bc + bG + 2 * bh);
+    dst = (int32_t*)(w + 2 * bc + bG + 3 * bh); dit = (int32_t*)(w + 2 * bc + bG + 3 * bh + bi);
+  }
+  CK(launch_solve_socp(n, nx, n_ort, d1, d2, dc_, dG, dh, pdip_tol, ctx->max_iters, dx, ds, dz, dst, dit, S));
+  ctx->launches++;
+  if (mem == DCOL_MEM_HOST) {
+    CK(cudaMemcpyAsync(x, dx, sizeof(double) * nx * (size_t)n, cudaMemcpyDeviceToHost, S));
+    CK(cudaMemcpyAsync(s, ds, sizeof(double) * ns * (size_t)n, cudaMemcpyDeviceToHost, S));
+    CK(cudaMemcpyAsync(z, dz, sizeof(double) * ns * (size_t)n, cudaMemcpyDeviceToHost, S));
+    if (status) CK(cudaMemcpyAsync(status, dst, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, S));
+    if (iters) CK(cudaMemcpyAsync(iters, dit, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, S));
   }
   CK(cudaStreamSynchronize(S));
   return 0;

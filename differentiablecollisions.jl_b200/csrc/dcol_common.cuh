@@ -83,6 +83,9 @@ struct QueryParams {
   double* alpha; double* x; int32_t* status; int32_t* iters;
   double* mu;                    // optional: duality measure s'z/deg at the iteration that ended the solve
   double* deriv;                 // gradient n x ntheta, or J n x (4 x ntheta) column-major; always at the caller's pair index
+  double* warm;                  // optional warm-start records, warm_stride doubles per pair (dcol_set_warm_start); NULL = cold starts
+  int warm_stride, warm_cap;     // record size in doubles; number of pairs the buffer holds
+  double warm_mu;                // an iterate is saved at the first iteration with mu below this
   int query;
 };
 

@@ -812,9 +812,75 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   int cone_degree = A.n + B.n + (P1::D > 0 ? 1 : 0) + (P2::D > 0 ? 1 : 0);   // static_solver2.jl:124-130
   const double inv_deg = 1.0 / (double)cone_degree;
 
+  // The complete iterate of a pair as a record of doubles with stride st: tag, k, s.z, y[NX], rows s, rows z, SOC s|z of
+  // prim 1, SOC s|z of prim 2.  Used by the straggler hand-over (field-major records of a bin, tag = sorted position)
+  // and by the opt-in warm start (one contiguous record per pair, tag = the pair's shape signature).
+  auto store_iterate = [&](double* q, int64_t st, double tag, int k) {
+    q[0] = tag; q += st;
+    q[0] = (double)k; q += st;
+    q[0] = sz; q += st;
+#pragma unroll
+    for (int a = 0; a < NX; a++) { q[0] = y[a]; q += st; }
+    const int nr = A.n + B.n;
+#pragma unroll 1
+    for (int i = 0; i < nr; i++) { q[0] = rs(F_S, i); q += st; }
+#pragma unroll 1
+    for (int i = 0; i < nr; i++) { q[0] = rs(F_Z, i); q += st; }
+    if constexpr (P1::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { q[0] = A.s[i]; q += st; }
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { q[0] = A.z[i]; q += st; }
+    }
+    if constexpr (P2::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { q[0] = B.s[i]; q += st; }
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { q[0] = B.z[i]; q += st; }
+    }
+  };
+  auto load_iterate = [&](const double* q, int64_t st) {      // q points at the k field; returns k
+    const int kk = (int)q[0]; q += st;
+    sz = q[0]; q += st;
+#pragma unroll
+    for (int a = 0; a < NX; a++) { y[a] = q[0]; q += st; }
+    const int nr = A.n + B.n;
+#pragma unroll 1
+    for (int i = 0; i < nr; i++) { rs(F_S, i) = q[0]; q += st; }
+#pragma unroll 1
+    for (int i = 0; i < nr; i++) { rs(F_Z, i) = q[0]; q += st; }
+    if constexpr (P1::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { A.s[i] = q[0]; q += st; }
+#pragma unroll
+      for (int i = 0; i < P1::D; i++) { A.z[i] = q[0]; q += st; }
+    }
+    if constexpr (P2::D > 0) {
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { B.s[i] = q[0]; q += st; }
+#pragma unroll
+      for (int i = 0; i < P2::D; i++) { B.z[i] = q[0]; q += st; }
+    }
+    return kk;
+  };
+  // Opt-in warm start (dcol_set_warm_start; not in the reference, excluded from parity): the pair's record holds the
+  // iterate of its previous solve at the first iteration whose mu fell below warm_mu.  A record whose signature matches
+  // the pair's shapes replaces the initial point; this solve leaves its own iterate behind for the next one.
+  double* const ws = (p.warm && pair < p.warm_cap) ? p.warm + (int64_t)pair * p.warm_stride : nullptr;
+  const double wsig = (double)(s1i * 65536 + s2i + 1);
+  bool warm_saved = false;
+  // A warm-started iterate does not satisfy this pair's linear constraints (the poses moved): its residual shrinks by
+  // (1 - step) per iteration, and since the reference's only exit test is mu < pdip_tol, a warm-started pair must also
+  // have taken steps that shrank it by 1e-5 before it may stop.  0 for cold starts: the default path is unaffected.
+  double warm_res = 0.0;
+
   int k0 = 0;
   // ---------------- initialize (static_solver2.jl:86-103) ----------------
-  if (tc.mode == 0) {
+  if (tc.mode == 0 && ws && ws[0] == wsig) {
+    (void)load_iterate(ws + 1, 1);
+    ws[0] = 0.0;                       // consumed; rewritten below once this solve passes warm_mu
+    warm_res = 1.0;
+  } else if (tc.mode == 0) {
     double N1[NV1][NV1], g1[NV1], N2[NV2][NV2], g2[NV2];
     double y1[NV1], y2[NV2];
 #pragma unroll
@@ -849,29 +915,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     // ---------------- resume: reload the iterate parked by the first pass ----------------
     // record layout (field-major, stride = the bin's record capacity): sorted position, k, s.z, y[NX], rows s, rows z, SOC s|z of
     // prim 1, SOC s|z of prim 2; read with one walking pointer (no per-field 64-bit index arithmetic)
-    const int64_t st = tc.in_cap;
-    const double* q = tc.in + idx + st;
-    k0 = (int)q[0]; q += st;
-    sz = q[0]; q += st;
-#pragma unroll
-    for (int a = 0; a < NX; a++) { y[a] = q[0]; q += st; }
-    const int nr = A.n + B.n;
-#pragma unroll 1
-    for (int i = 0; i < nr; i++) { rs(F_S, i) = q[0]; q += st; }
-#pragma unroll 1
-    for (int i = 0; i < nr; i++) { rs(F_Z, i) = q[0]; q += st; }
-    if constexpr (P1::D > 0) {
-#pragma unroll
-      for (int i = 0; i < P1::D; i++) { A.s[i] = q[0]; q += st; }
-#pragma unroll
-      for (int i = 0; i < P1::D; i++) { A.z[i] = q[0]; q += st; }
-    }
-    if constexpr (P2::D > 0) {
-#pragma unroll
-      for (int i = 0; i < P2::D; i++) { B.s[i] = q[0]; q += st; }
-#pragma unroll
-      for (int i = 0; i < P2::D; i++) { B.z[i] = q[0]; q += st; }
-    }
+    k0 = load_iterate(tc.in + idx + tc.in_cap, tc.in_cap);
+    warm_saved = sz * inv_deg < p.warm_mu;           // the first pass saved it when mu first fell below warm_mu
   }
 
   // ---------------- main loop (static_solver2.jl:132-187) ----------------
@@ -887,12 +932,14 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   if (active) status = ST_PDIP_FAILED;
   for (int k = k0;; k++) {
     const double mu = sz * inv_deg;
+    // (a warm-started pair saves after its first step on the new poses, so that the record follows the trajectory)
+    if (ws && active && !warm_saved && mu < p.warm_mu && (k > 0 || warm_res == 0.0)) { store_iterate(ws, 1, wsig, 0); warm_saved = true; }
     if (active) {
       // the reference tests mu only at the START of iterations 1..50 (static_solver2.jl:132,143-146) and raises
       // "pdip failed" after the 50th step without another test (:188): a pair that would pass on its 50th step fails
       if (k >= max_it) { active = false; it = k; }
       else if (!(mu == mu)) { status = ST_NUMERICAL; active = false; it = k; }
-      else if (mu < tol) { status = ST_OK; active = false; it = k; }
+      else if (mu < tol && warm_res < 1e-5) { status = ST_OK; active = false; it = k; }
     }
     const int n_act = DCOL_COUNT(active);
     if (n_act == 0) break;
@@ -901,30 +948,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
       // (and its idle lanes) in the loop until the slowest pair converges
       if (active) {
         const int slot = atomicAdd(tc.ov_count, 1);
-        const int64_t st = tc.ov_cap;
-        double* q = tc.ov + slot;
-        q[0] = (double)pos; q += st;
-        q[0] = (double)k; q += st;
-        q[0] = sz; q += st;
-#pragma unroll
-        for (int a = 0; a < NX; a++) { q[0] = y[a]; q += st; }
-        const int nr = A.n + B.n;
-#pragma unroll 1
-        for (int i = 0; i < nr; i++) { q[0] = rs(F_S, i); q += st; }
-#pragma unroll 1
-        for (int i = 0; i < nr; i++) { q[0] = rs(F_Z, i); q += st; }
-        if constexpr (P1::D > 0) {
-#pragma unroll
-          for (int i = 0; i < P1::D; i++) { q[0] = A.s[i]; q += st; }
-#pragma unroll
-          for (int i = 0; i < P1::D; i++) { q[0] = A.z[i]; q += st; }
-        }
-        if constexpr (P2::D > 0) {
-#pragma unroll
-          for (int i = 0; i < P2::D; i++) { q[0] = B.s[i]; q += st; }
-#pragma unroll
-          for (int i = 0; i < P2::D; i++) { q[0] = B.z[i]; q += st; }
-        }
+        store_iterate(tc.ov + slot, tc.ov_cap, (double)pos, k);
         parked = true;
       }
       break;
@@ -978,6 +1002,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
         const double al = 0.99 * fast_rcp(fmax(1.0, fmax(m_s, m_z)));   // min(1, 0.99 * step to the boundary)  :172
 #pragma unroll
         for (int a = 0; a < NX; a++) y[a] += al * dy[a];
+        warm_res *= 1.0 - al;
         sz = A.passE_rows(rs, al) + B.passE_rows(rs, al);
         sz += A.passE_soc(al) + B.passE_soc(al);
       }

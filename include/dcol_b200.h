@@ -187,6 +187,30 @@ int dcol_wait(dcol_ctx* ctx, int ticket);
 int dcol_host_register(dcol_ctx* ctx, void* ptr, int64_t bytes);
 int dcol_host_unregister(dcol_ctx* ctx, void* ptr);
 
+/* ---- the conic solver on its own --------------------------------------------------------------------------
+ * Replaces solve_socp(c, G, h, idx_ort, idx_soc1, idx_soc2; pdip_tol) -> (x, s, z) of
+ * src/solvers/coneqp/static_solver2.jl:106-191 for n independent problems of common dimensions:
+ *     min c'x   s.t.   h - G x  in  R+^n_ort x Q^d1 x Q^d2,     rows ordered [orthant; soc1; soc2] (idx_* of the reference).
+ * c: n x nx, G: n x ns x nx (row-major per problem, ns = n_ort + d1 + d2), h: n x ns; outputs x: n x nx, s, z: n x ns.
+ * Limits: nx <= 16, ns <= 96, d1, d2 in {0, 2..8}.  status as for the queries (1 = "pdip failed" after 50 iterations).
+ * One thread per problem, dense arithmetic: a correctness path for driving the solver subsystem directly (the reference's
+ * test/solver_tests.jl fixture runs through it); the proximity entry points above never form G and are the fast path. */
+int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
+                    double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters);
+
+/* ---- warm start -------------------------------------------------------------------
+ * Opt-in, NOT in the reference (every reference solve starts from `initialize`, static_solver2.jl:86-103) and excluded
+ * from parity: iteration counts change; alpha, x and the derivatives agree with a cold solve to the solver tolerance.
+ * `state` is DEVICE memory of capacity_pairs x dcol_warm_stride(ctx) doubles, zero-initialised by the caller and
+ * addressed by the pair index of the queries that follow (for dcol_se2_constraints: state * n_obs + obstacle; for the
+ * scene operators: the `combinations` index).  Every solve leaves behind its iterate (y, s, z) at the first iteration
+ * whose duality measure fell below mu_save (<= 0 selects 1e-2); a later solve of the same pair index with the same two
+ * shapes starts from that iterate.  Meant for callers that re-evaluate the same pairs at slowly changing poses (the
+ * line-search trials and successive iterations of examples/trajectory_optimization/simple_altro.jl:112-163).
+ * state == NULL switches it off.  Call dcol_set_shapes before dcol_warm_stride. */
+int64_t dcol_warm_stride(const dcol_ctx* ctx);
+int     dcol_set_warm_start(dcol_ctx* ctx, double* state, int64_t capacity_pairs, double mu_save);
+
 /* ---- solver diagnostics ------------------------------------------------------------------------------------
  * dcol_set_mu_output: optional per-pair output of the duality measure mu = s'z/deg at the iteration that ended the
  * solve (what the reference's verbose mode prints per iteration, src/solvers/coneqp/static_solver2.jl:117-120,

@@ -43,6 +43,15 @@ w2, k2, o2 = timed(lambda: ctx.scene_wrench(shape, r, att, lam, 0, per_pair=Fals
 print(f"config 4f same scene through dcol_scene_wrench (per-body sums only): call {w2*1e3:8.3f} ms  {npairs/w2/1e6:8.2f} Mpairs/s")
 w3, k3, o3 = timed(lambda: ctx.scene_wrench(shape, r, att, lam, 0, per_pair=True), 2)
 print(f"config 4f same, alpha/status/iters per pair returned as well:        call {w3*1e3:8.3f} ms  {npairs/w3/1e6:8.2f} Mpairs/s")
+# 4c: the same scene with the opt-in broad phase at the example's interaction radius (only colliding pairs matter to the
+# complementarity rows) and at twice that
+for cut in (1.0, 2.0):
+    ctx.scene_set_cull(cut)
+    wc, kc, oc = timed(lambda: ctx.scene_allpairs(1, shape, r, att, 0), 2)
+    wc2, kc2, oc2 = timed(lambda: ctx.scene_wrench(shape, r, att, lam, 0, per_pair=False), 2)
+    ctx.scene_set_cull(0.0)
+    print(f"config 4c same scene, dcol_scene_set_cull({cut}): {int((oc['status'] != 3).sum())} of {npairs} pairs solved: allpairs call {wc*1e3:8.3f} ms  kernels {kc:7.3f} ms"
+          f" | scene_wrench (per-body sums only) call {wc2*1e3:8.3f} ms")
 # 5: piano mover batch: 1024 rollouts x 100 knots x 3 obstacles, jacobian, MRP p = (0,0,tan(theta/4))
 B, N, K = 1024, 100, 3
 veh = dc.create_rect_prism(2.5, 0.15, 0.01)[0]

@@ -278,7 +278,7 @@ def test_scene_cull_keeps_near_pairs_bit_identical(ctx, att_kind, kind):
             assert np.array_equal(c[k][~culled], full[k][~culled], equal_nan=True), (k, cut)
         ok = culled & (full["status"] == 0)
         assert (full["alpha"][ok] > cut).all()                       # nothing within the interaction radius is lost
-        assert (c["alpha"][culled] > cut).all() and (c["alpha"][ok] <= full["alpha"][ok] * (1 + 1e-9)).all()   # a lower bound
+        assert (c["alpha"][culled] > cut).all() and (c["alpha"][ok] <= full["alpha"][ok] * (1 + 1e-6)).all()   # a lower bound (exact for sphere pairs, hence the solver-accuracy slack)
         assert (c["iters"][culled] == 0).all()
         if kind == 1:
             assert (c["grad"][culled] == 0).all()
@@ -336,3 +336,40 @@ def test_scene_cull_config4(ctx):
     assert not (hit & culled).any()
     assert np.array_equal(c["alpha"][~culled], full["alpha"][~culled]) and np.array_equal(c["x"][~culled], full["x"][~culled])
     assert culled.mean() > 0.5
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_warm_start_is_opt_in_and_consistent(ctx, kind):
+    """dcol_set_warm_start (not in the reference, excluded from parity): the default path is untouched
+    (bit-identical with the warm buffer attached but empty), a warm solve of slightly moved poses needs fewer iterations
+    and agrees with the cold solve of the same poses to the solver tolerance."""
+    import torch
+    n = 40000
+    t, s1, s2, r1, a1, r2, a2 = util.mixed_batch(n, 1, seed=23, variant="cube")
+    ctx.set_shape_arrays(*t.arrays())
+    cold = ctx._batch(kind, s1, s2, r1, a1, r2, a2, 1, 1e-6)
+    state = torch.zeros(n * ctx.warm_stride(), dtype=torch.float64, device="cuda:0")
+    g = util.rng(77)
+    r1b = r1 + 0.01 * g.standard_normal(r1.shape); r2b = r2 + 0.01 * g.standard_normal(r2.shape)
+    a1b = a1 + 0.005 * g.standard_normal(a1.shape); a2b = a2 + 0.005 * g.standard_normal(a2.shape)
+    cold_b = ctx._batch(kind, s1, s2, r1b, a1b, r2b, a2b, 1, 1e-6)
+    try:
+        ctx.set_warm_start(state, n, 1e-2)
+        first = ctx._batch(kind, s1, s2, r1, a1, r2, a2, 1, 1e-6)          # empty records: cold starts, iterates saved
+        for k in cold:
+            assert np.array_equal(first[k], cold[k], equal_nan=True), k
+        warm_b = ctx._batch(kind, s1, s2, r1b, a1b, r2b, a2b, 1, 1e-6)       # starts from the saved iterates
+    finally:
+        ctx.set_warm_start(None)
+    assert (warm_b["status"] == 0).all()
+    assert warm_b["iters"].mean() < 0.7 * cold_b["iters"].mean(), (warm_b["iters"].mean(), cold_b["iters"].mean())
+    ea = util.rel_err(warm_b["alpha"], cold_b["alpha"])          # both are O(pdip_tol)-accurate solutions of the same problem
+    assert np.quantile(ea, 0.999) < 1e-5 and ea.max() < 1e-3, (np.quantile(ea, 0.999), ea.max())
+    assert ((warm_b["alpha"] <= 1) == (cold_b["alpha"] <= 1)).mean() > 0.9999
+    if kind == 1:
+        # the duals z (and with them grad = -z' du/dtheta) are only O(sqrt(pdip_tol))-accurate at mu < 1e-6 in either solve:
+        # the reference's own tests compare the gradient with J[4,:] at 1e-3 and with finite differences at 1e-1
+        assert np.quantile(util.rel_err(warm_b["grad"], cold_b["grad"]), 0.99) < 1e-2
+    again = ctx._batch(kind, s1, s2, r1b, a1b, r2b, a2b, 1, 1e-6)            # warm start off again: the cold result, bit for bit
+    for k in cold_b:
+        assert np.array_equal(again[k], cold_b[k], equal_nan=True), k

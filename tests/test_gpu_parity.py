@@ -488,3 +488,38 @@ def test_small_batch_path_matches_the_binned_path(ctx, kind):
         sm = ctx._batch(kind, s1[:n], s2[:n], r1[:n], a1[:n], r2[:n], a2[:n], 0, 1e-6)
         for k in sm:
             assert np.array_equal(sm[k], big[k][:n], equal_nan=True), (k, n)
+
+
+def test_generic_socp_entry_on_the_reference_fixture(ctx, oracle):
+    """dcol_solve_socp (the solver subsystem on its own, static_solver2.jl:106-191) on the reference's stored problem
+    example_socp_2.jld2 with the property its own test asserts (test/solver_tests.jl:63-64: |s'z| < 1e-10 at
+    pdip_tol = 1e-12), against the oracle's iterates, and on dense (c, G, h) of mixed primitive pairs against the
+    proximity entry point that never forms G."""
+    d = json.load(open(os.path.join(util.GOLDEN, "example_socp_2.json")))
+    Gm = np.array(d["G"], float); h = np.array(d["h"], float); c = np.array(d["c"], float)
+    x, s, z, st, it = ctx.solve_socp(c, Gm, h, d["n_ort"], d["n_soc1"], d["n_soc2"], pdip_tol=1e-12)
+    assert st == 0 and abs(s @ z) < 1e-10
+    ox, os_, oz, oit, ost = oracle.solve_socp(c, Gm, h, d["n_ort"], d["n_soc1"], d["n_soc2"], pdip_tol=1e-12)
+    assert it == oit and ost == 0
+    np.testing.assert_allclose(x, ox, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(s, os_, rtol=1e-6, atol=1e-9); np.testing.assert_allclose(z, oz, rtol=1e-6, atol=1e-9)
+    # batched: the dense problems of random pairs of one structure (capsule-cone: nx 5, 3 orthant rows, SOC 4 and 3)
+    g = util.rng(6)
+    caps = dc.Capsule(0.3, 1.2); cone = dc.Cone(2.0, np.deg2rad(22))
+    t = dc.ShapeTable(); i1 = t.add(caps); i2 = t.add(cone)
+    n = 200
+    r1, a1, r2, a2 = util.random_poses(n, 0, 5)
+    Gs, hs = [], []
+    for k in range(n):
+        caps.r, caps.q, cone.r, cone.q = r1[k], a1[k], r2[k], a2[k]
+        cc, Gk, hk, n_ort, d1, d2 = oracle.pair_problem(caps, cone)
+        Gs.append(Gk); hs.append(hk)
+    X, S, Z, stt, its = ctx.solve_socp(cc, np.array(Gs), np.array(hs), n_ort, d1, d2, pdip_tol=1e-6)
+    ctx.set_shape_arrays(*t.arrays())
+    p = ctx._batch(0, np.full(n, i1, np.int32), np.full(n, i2, np.int32), r1, a1, r2, a2, 0, 1e-6)
+    assert (stt == 0).all() and np.array_equal(its, p["iters"])
+    np.testing.assert_allclose(X[:, 3], p["alpha"], rtol=1e-9)
+    np.testing.assert_allclose(X[:, :3], p["x"], rtol=1e-6, atol=1e-8)
+    # dimensions out of range are an API error
+    with pytest.raises(RuntimeError):
+        ctx.solve_socp(np.zeros(20), np.zeros((30, 20)), np.zeros(30), 30, 0, 0)

@@ -153,13 +153,12 @@ struct PairSource {
   const int32_t* oidx;                             // optional: where pair i's results go (culled scene lists); NULL = i
 };
 
-// Write pair i at sorted position pos as one 128-byte record (eight 16-byte stores = one cache line).  Pairs whose
-// classes arrive as (hi, lo) are stored with their primitives exchanged, so the solver only ever sees (lo, hi).
-__device__ __forceinline__ void pack_pair(const PairSource& src, int64_t i, int s1, int s2, bool swp, PairRec* __restrict__ recs, int pos) {
+// The 16 doubles of pair i's 128-byte record.  Pairs whose classes arrive as (hi, lo) are stored with their primitives
+// exchanged, so the solver only ever sees (lo, hi).
+__device__ __forceinline__ void load_pair(const PairSource& src, int64_t i, int s1, int s2, bool swp, double (&v)[16]) {
   const int64_t i1 = src.pose1 ? (int64_t)src.pose1[i] : i, i2 = src.pose2 ? (int64_t)src.pose2[i] : i;
   const double* ra = src.r1 + 3 * i1; const double* aa = src.att1 + src.na * i1;
   const double* rb = src.r2 + 3 * i2; const double* ab = src.att2 + src.na * i2;
-  double v[16];
   v[0] = __ldg(ra); v[1] = __ldg(ra + 1); v[2] = __ldg(ra + 2);
   v[3] = __ldg(aa); v[4] = __ldg(aa + 1); v[5] = __ldg(aa + 2); v[6] = (src.na == 4) ? __ldg(aa + 3) : 0.0;
   v[7] = __ldg(rb); v[8] = __ldg(rb + 1); v[9] = __ldg(rb + 2);
@@ -171,9 +170,6 @@ __device__ __forceinline__ void pack_pair(const PairSource& src, int64_t i, int 
   }
   v[14] = __hiloint2double(s2, s1);
   v[15] = __hiloint2double(swp ? DCOL_REC_SWAPPED : 0, src.oidx ? src.oidx[i] : (int)i);
-  double2* q = reinterpret_cast<double2*>(recs + pos);
-#pragma unroll
-  for (int a = 0; a < 8; a++) q[a] = make_double2(v[2 * a], v[2 * a + 1]);
 }
 
 // counting-sort scatter: inv[i] = sorted position of pair i (coalesced writes; -1 for pairs with a bad shape index).
@@ -211,14 +207,37 @@ __global__ void k_scatter(const int32_t* __restrict__ shape1, const int32_t* __r
   }
 }
 
-// one thread per pair, no barriers: a pure streaming kernel (reads the caller's arrays coalesced in pair order, writes
-// each pair's 128-byte record at its sorted position)
-__global__ void k_pack(PairSource src, int64_t n, const int32_t* __restrict__ cls, const int32_t* __restrict__ inv, PairRec* __restrict__ recs) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int pos = inv[i];
-    if (pos < 0) continue;
-    const int s1 = src.shape1[i], s2 = src.shape2[i];
-    pack_pair(src, i, s1, s2, cls[s1] > cls[s2], recs, pos);
+// Streaming pack: every thread reads its pair in caller order (coalesced), the block transposes through shared memory, and
+// eight consecutive lanes then write one record (8 x 16 bytes = one 128-byte line) at its sorted position, so each warp
+// store instruction writes four whole cache lines instead of 32 half-sectors of 32 different lines.
+constexpr int PACK_THREADS = 256, PACK_PITCH = 18;      // doubles per staged record: 16 + 2 (keeps double2 alignment, spreads banks)
+__global__ void __launch_bounds__(PACK_THREADS) k_pack(PairSource src, int64_t n, const int32_t* __restrict__ cls, const int32_t* __restrict__ inv,
+                                                        PairRec* __restrict__ recs) {
+  __shared__ double tile[PACK_THREADS * PACK_PITCH];
+  __shared__ int spos[PACK_THREADS];
+  const int tid = threadIdx.x;
+  for (int64_t base = blockIdx.x * (int64_t)PACK_THREADS; base < n; base += (int64_t)gridDim.x * PACK_THREADS) {
+    const int64_t i = base + tid;
+    int pos = -1;
+    if (i < n) pos = inv[i];
+    if (pos >= 0) {
+      const int s1 = src.shape1[i], s2 = src.shape2[i];
+      double v[16];
+      load_pair(src, i, s1, s2, cls[s1] > cls[s2], v);
+      double2* q = reinterpret_cast<double2*>(tile + tid * PACK_PITCH);
+#pragma unroll
+      for (int a = 0; a < 8; a++) q[a] = make_double2(v[2 * a], v[2 * a + 1]);
+    }
+    spos[tid] = pos;
+    __syncthreads();
+    const int c = tid & 7;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int r = k * 32 + (tid >> 3);
+      const int p = spos[r];
+      if (p >= 0) reinterpret_cast<double2*>(recs + p)[c] = reinterpret_cast<const double2*>(tile + r * PACK_PITCH)[c];
+    }
+    __syncthreads();
   }
 }
 
@@ -1307,7 +1326,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       k_small_prep<<<1, SMALL_THREADS, sizeof(int) * (nk + 1), SC>>>(src, (int)nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk,
                                                                       d_off, d_counter, (2 + MAX_LEVELS) * NSIDE, d_bad, d_inv,
                                                                       (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P);
-      k_pack<<<(int)std::min<int64_t>((nc + 127) / 128, 148 * 16), 128, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
+      k_pack<<<(int)std::min<int64_t>((nc + PACK_THREADS - 1) / PACK_THREADS, 148 * 8), PACK_THREADS, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
       ctx->launches += 2;
     } else {
       CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
@@ -1316,7 +1335,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       k_hist<<<blocks, threads, sizeof(int) * nk, SC>>>(src.shape1, src.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_hist, d_bad);
       k_scan_tables<<<1, 1024, 0, SC>>>(d_hist, nk, d_off, d_cursor, (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P, spill_div);
       k_scatter<<<blocks, threads, sizeof(int) * 2 * nk, SC>>>(src.shape1, src.shape2, nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk, d_cursor, d_inv);
-      k_pack<<<(int)std::min<int64_t>((nc + 255) / 256, 148 * 32), 256, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
+      k_pack<<<(int)std::min<int64_t>((nc + PACK_THREADS - 1) / PACK_THREADS, 148 * 8), PACK_THREADS, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
       ctx->launches += 4;
     }
     // ---- persistent solver launches, one per shared-memory tier present in the shape table

@@ -46,8 +46,13 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   const double p = fma(e, 0.375, 0.5) * e;     // e/2 + 3 e^2 / 8
   return fma(y, p, y);                         // cubic step
 }
+// max / min as one compare and one select.  fmax / fmin on doubles compile to DSETP.MAX + two selects + a NaN-quieting
+// LOP3 + moves for their operands (5-7 instructions; 10 % of the interior-point loop went there); NaNs need no
+// special care here: a NaN iterate is caught by the mu test of the next iteration.
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 0
-  double r = fast_rsqrt(fmax(x, 1e-300));
+  double r = fast_rsqrt(dmax(x, 0x1p-1000));               // (a power of two: one immediate instead of a 64-bit constant)
   double sq = x * r;
   return fma(fma(-sq, sq, x), 0.5 * r, sq);               // one correction step on the product
 }
@@ -322,7 +327,7 @@ struct Prim {
 #pragma unroll
       for (int a = 0; a < NV; a++) if (nz(a)) { us += c[a] * yh[a]; uz += c[a] * dh[a]; }
       rs(F_S, row0 + i) = -us; rs(F_Z, row0 + i) = uz;
-      min_s = fmin(min_s, -us); min_z = fmin(min_z, uz);
+      min_s = dmin(min_s, -us); min_z = dmin(min_z, uz);
     }
     if constexpr (D > 0) {
       double u[D];
@@ -333,9 +338,9 @@ struct Prim {
       soc_apply<CLS, NV, D>(sc, dh, z);
 #pragma unroll
       for (int i = 1; i < D; i++) { ns += s[i] * s[i]; nz += z[i] * z[i]; }
-      double res_s = s[0] - sqrt(ns), res_z = z[0] - sqrt(nz);
-      if (res_s <= 0.0) a_s = fmax(a_s, -res_s);
-      if (res_z <= 0.0) a_z = fmax(a_z, -res_z);
+      double res_s = s[0] - fast_sqrt(ns), res_z = z[0] - fast_sqrt(nz);
+      if (res_s <= 0.0) a_s = dmax(a_s, -res_s);
+      if (res_z <= 0.0) a_z = dmax(a_z, -res_z);
     }
   }
   __device__ __forceinline__ double init_shift(const RowStore& rs, double sh_s, double sh_z) {   // + (1+a)*e ; returns s.z
@@ -441,7 +446,8 @@ struct Prim {
   }
 
   // ---- pass B: affine direction; step bounds (reciprocal form: m = max -d/y); sums for rho; Mehrotra correction
-  __device__ __forceinline__ void passB_rows(const RowStore& rs, const double (&dyh)[NV], double& m_s, double& m_z, double& dot1, double& dot2) {
+  // (orthant rows: the two ratio tests max q and max (1 - q) are one, 1/2 + max |q - 1/2|; mh carries max |q - 1/2|)
+  __device__ __forceinline__ void passB_rows(const RowStore& rs, const double (&dyh)[NV], double& mh, double& dot1, double& dot2) {
 #pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
@@ -454,13 +460,13 @@ struct Prim {
       const double is = zi * rr;
       const double q = is * t;                  // -ds/s  and  1 + dz/z
       const double dza = zi * q - zi;
-      m_s = fmax(m_s, q); m_z = fmax(m_z, 1.0 - q);
+      mh = dmax(mh, fabs(q - 0.5));
       const double pp = -t * dza;
       rs(F_P, row0 + i) = pp;
       dot1 += si * dza - zi * t; dot2 += pp;
     }
   }
-  __device__ __forceinline__ void passB_soc(const double (&dyh)[NV], double& m_s, double& m_z, double& dot1, double& dot2) {
+  __device__ __forceinline__ void passB_soc(const double (&dyh)[NV], double& m, double& dot1, double& dot2) {
     if constexpr (D > 0) {
       double cd[D], t[D], dsa[D], dza[D], w[D];
       soc_apply<CLS, NV, D>(sc, dyh, cd);
@@ -473,8 +479,8 @@ struct Prim {
       applyV(w, dza);
 #pragma unroll
       for (int i = 0; i < D; i++) dza[i] *= ie;
-      m_s = fmax(m_s, soc_linesearch_m<D>(s, dsa, irs, dens));
-      m_z = fmax(m_z, soc_linesearch_m<D>(z, dza, irz, denz));
+      m = dmax(m, soc_linesearch_m<D>(s, dsa, irs, dens));
+      m = dmax(m, soc_linesearch_m<D>(z, dza, irz, denz));
 #pragma unroll
       for (int i = 0; i < D; i++) { dot1 += s[i] * dza[i] + z[i] * dsa[i]; dot2 += dsa[i] * dza[i]; }
       // -(W^-1 dsa) o (W dza) = v o (v - lambda)   (static_solver2.jl:164)
@@ -524,7 +530,7 @@ struct Prim {
   }
 
   // ---- pass D: final direction and step bounds; directions parked in F_RZ/F_P (rows) and rz/v (SOC)
-  __device__ __forceinline__ void passD_rows(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& m_s, double& m_z) {
+  __device__ __forceinline__ void passD_rows(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& m) {
 #pragma unroll ROW_UNROLL
     for (int i = 0; i < n; i++) {
       double cd = 0.0;
@@ -536,11 +542,11 @@ struct Prim {
       const double t = r - cd;
       const double is = zi * rr, iz = si * rr;
       const double dz = (zi * t + sigmu - pp) * is - zi;
-      m_s = fmax(m_s, t * is); m_z = fmax(m_z, -dz * iz);
+      m = dmax(m, t * is); m = dmax(m, -dz * iz);
       rs(F_RZ, row0 + i) = -t; rs(F_P, row0 + i) = dz;
     }
   }
-  __device__ __forceinline__ void passD_soc(const double (&dyh)[NV], double& m_s, double& m_z) {
+  __device__ __forceinline__ void passD_soc(const double (&dyh)[NV], double& m) {
     if constexpr (D > 0) {
       double cd[D], t[D], ds[D], dz[D], v2[D];
       soc_apply<CLS, NV, D>(sc, dyh, cd);
@@ -553,8 +559,8 @@ struct Prim {
       applyV(v2, dz);
 #pragma unroll
       for (int i = 0; i < D; i++) dz[i] *= ie;
-      m_s = fmax(m_s, soc_linesearch_m<D>(s, ds, irs, dens));
-      m_z = fmax(m_z, soc_linesearch_m<D>(z, dz, irz, denz));
+      m = dmax(m, soc_linesearch_m<D>(s, ds, irs, dens));
+      m = dmax(m, soc_linesearch_m<D>(z, dz, irz, denz));
 #pragma unroll
       for (int i = 0; i < D; i++) { rz[i] = ds[i]; v[i] = dz[i]; }
     }
@@ -905,8 +911,8 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     B.init_rows(rs, y2, d2, ms, mz, a_s, a_z);
     min_s = ms; min_z = mz;
     if (A.n + B.n > 0) {   // bring2cone :62-64 — orthant part first, then max with the SOC residuals
-      if (min_s <= 0.0) a_s = fmax(a_s, -min_s);
-      if (min_z <= 0.0) a_z = fmax(a_z, -min_z);
+      if (min_s <= 0.0) a_s = dmax(a_s, -min_s);
+      if (min_z <= 0.0) a_z = dmax(a_z, -min_z);
     }
     double sh_s = (a_s < 0.0) ? 0.0 : 1.0 + a_s, sh_z = (a_z < 0.0) ? 0.0 : 1.0 + a_z;
     sz = A.init_shift(rs, sh_s, sh_z) + B.init_shift(rs, sh_s, sh_z);
@@ -972,15 +978,15 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
       if (!ok) { status = ST_NUMERICAL; active = false; it = k; }
       else {
         chol_solve<NX>(M, idg, rhs, dy);            // affine direction
-        double m_s = 0.0, m_z = 0.0, dot1 = 0.0, dot2 = 0.0;
+        double mh = 0.0, m = 0.0, dot1 = 0.0, dot2 = 0.0;
         PM::to_local(dy, R, t, false, y1, y2);
-        A.passB_rows(rs, y1, m_s, m_z, dot1, dot2);
-        B.passB_rows(rs, y2, m_s, m_z, dot1, dot2);
-        A.passB_soc(y1, m_s, m_z, dot1, dot2);
-        B.passB_soc(y2, m_s, m_z, dot1, dot2);
-        const double aa = fast_rcp(fmax(1.0, fmax(m_s, m_z)));   // min(1, step to the boundary)  :159
+        A.passB_rows(rs, y1, mh, dot1, dot2);
+        B.passB_rows(rs, y2, mh, dot1, dot2);
+        A.passB_soc(y1, m, dot1, dot2);
+        B.passB_soc(y2, m, dot1, dot2);
+        const double aa = fast_rcp(dmax(1.0, dmax(mh + 0.5, m)));   // min(1, step to the boundary)  :159
         const double rho = (sz + aa * (dot1 + aa * dot2)) * fast_rcp(sz);
-        double sig = fmax(0.0, fmin(1.0, rho)); sig = sig * sig * sig;   // :161
+        double sig = dmax(0.0, dmin(1.0, rho)); sig = sig * sig * sig;   // :161
         const double sigmu = sig * mu;
         {
           double g1[NV1], g2[NV2], rc[NX];
@@ -993,13 +999,13 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
           for (int a = 0; a < NX; a++) rhs[a] += rc[a];
         }
         chol_solve<NX>(M, idg, rhs, dy);            // combined direction
-        m_s = 0.0; m_z = 0.0;
+        m = 0.0;
         PM::to_local(dy, R, t, false, y1, y2);
-        A.passD_rows(rs, y1, sigmu, m_s, m_z);
-        B.passD_rows(rs, y2, sigmu, m_s, m_z);
-        A.passD_soc(y1, m_s, m_z);
-        B.passD_soc(y2, m_s, m_z);
-        const double al = 0.99 * fast_rcp(fmax(1.0, fmax(m_s, m_z)));   // min(1, 0.99 * step to the boundary)  :172
+        A.passD_rows(rs, y1, sigmu, m);
+        B.passD_rows(rs, y2, sigmu, m);
+        A.passD_soc(y1, m);
+        B.passD_soc(y2, m);
+        const double al = 0.99 * fast_rcp(dmax(1.0, m));   // min(1, 0.99 * step to the boundary)  :172
 #pragma unroll
         for (int a = 0; a < NX; a++) y[a] += al * dy[a];
         warm_res *= 1.0 - al;

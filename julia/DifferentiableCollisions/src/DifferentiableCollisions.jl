@@ -365,6 +365,43 @@ end
 unpin!(a::Array) = (_check(ccall((:dcol_host_unregister, _lib[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), _ctx[], a)); nothing)
 
 # ---------------------------------------------------------------------------------------------
+# round-2 additions to the C ABI (include/dcol_b200.h): the solver on its own, opt-in cull / warm start, diagnostics
+# ---------------------------------------------------------------------------------------------
+"""
+    solve_socp(c, G, h, idx_ort, idx_soc1, idx_soc2; pdip_tol = 1e-4) -> (x, s, z)
+
+Same call as the reference's `solve_socp` (`src/solvers/coneqp/static_solver2.jl:106-191`); rows of `G`, `h` must be
+ordered `[idx_ort; idx_soc1; idx_soc2]` as `combine_problem_matrices` produces them.  Runs `dcol_solve_socp` on one problem.
+"""
+function solve_socp(c::AbstractVector, G::AbstractMatrix, h::AbstractVector, idx_ort, idx_soc1, idx_soc2; pdip_tol = 1e-4, verbose = false)
+    ns, nx = size(G)
+    Gr = Matrix{Float64}(transpose(G))                               # row-major ns x nx for the C side
+    x = Vector{Float64}(undef, nx); s = Vector{Float64}(undef, ns); z = Vector{Float64}(undef, ns)
+    status = Int32[0]; iters = Int32[0]
+    _check(ccall((:dcol_solve_socp, _lib[]), Cint,
+                 (Ptr{Cvoid}, Int64, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                  Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                 _ctx[], 1, nx, length(idx_ort), length(idx_soc1), length(idx_soc2), collect(Float64, c), Gr, collect(Float64, h),
+                 Float64(pdip_tol), MEM_HOST, x, s, z, status, iters))
+    status[1] == 1 && error("pdip failed")                           # static_solver2.jl:188
+    status[1] == 0 || throw(DomainError(status[1], "numerical breakdown in the conic solver"))
+    return x, s, z
+end
+
+"`scene_set_cull!(α_cut)`: opt-in broad phase of `scene_allpairs` / `scene_wrench` (`dcol_scene_set_cull`); pairs proven to have α > α_cut come back with status 3 and a lower bound of α.  0 switches it off."
+scene_set_cull!(α_cut::Real) = (_check(ccall((:dcol_scene_set_cull, _lib[]), Cint, (Ptr{Cvoid}, Float64), _ctx[], Float64(α_cut))); nothing)
+
+"`set_mu_output!(μ)`: the following host-pointer queries also return the final duality measure per pair in `μ` (a `Vector{Float64}` the caller keeps alive); `nothing` switches it off."
+set_mu_output!(μ::Union{Vector{Float64},Nothing}) =
+    (_check(ccall((:dcol_set_mu_output, _lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}), _ctx[], μ === nothing ? C_NULL : μ)); nothing)
+
+"`warm_stride()`: doubles per pair of a warm-start record for the current shape table (`dcol_warm_stride`).  The records live in DEVICE memory; allocate them with your CUDA binding of choice and pass the device pointer to `set_warm_start!`."
+warm_stride() = Int(ccall((:dcol_warm_stride, _lib[]), Int64, (Ptr{Cvoid},), _ctx[]))
+set_warm_start!(state::Ptr{Float64}, capacity_pairs::Integer; mu_save = 1e-2) =
+    (_check(ccall((:dcol_set_warm_start, _lib[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64), _ctx[], state, capacity_pairs, Float64(mu_save))); nothing)
+
+
+# ---------------------------------------------------------------------------------------------
 # single-pair drop-in calls: a batch of one through the same entry points
 # ---------------------------------------------------------------------------------------------
 function _single(sym, P1, P2, pdip_tol)

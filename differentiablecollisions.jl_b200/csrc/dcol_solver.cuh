@@ -21,6 +21,7 @@
 #pragma once
 #include "dcol_common.cuh"
 #include "dcol_deriv.cuh"
+#include <type_traits>
 
 // one block-wide vote per interior-point iteration (the hand-over capacity of a bin assumes CTA-wide votes)
 #define DCOL_COUNT(pred) __syncthreads_count(pred)
@@ -49,10 +50,15 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // max / min as one compare and one select.  fmax / fmin on doubles compile to DSETP.MAX + two selects + a NaN-quieting
 // LOP3 + moves for their operands (5-7 instructions; 10 % of the interior-point loop went there); NaNs need no
 // special care here: a NaN iterate is caught by the mu test of the next iteration.
-__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+// (written in PTX: with a constant operand the compiler turns the C++ ternary back into the fmax sequence)
+__device__ __forceinline__ double dmax(double a, double b) {
+  double r; asm("{ .reg .pred p; setp.gt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b)); return r;
+}
+__device__ __forceinline__ double dmin(double a, double b) {
+  double r; asm("{ .reg .pred p; setp.lt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b)); return r;
+}
 __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 0
-  double r = fast_rsqrt(dmax(x, 0x1p-1000));               // (a power of two: one immediate instead of a 64-bit constant)
+  double r = fast_rsqrt(x + 0x1p-1000);                    // keeps rsqrt(0) finite; x + 2^-1000 == x for every x >= 2^-947
   double sq = x * r;
   return fma(fma(-sq, sq, x), 0.5 * r, sq);               // one correction step on the product
 }
@@ -255,6 +261,41 @@ struct Prim {
       for (int a = 0; a < NV; a++) c[a] = nz(a) ? __ldg(rows + i * NV + a) : 0.0;
     }
   }
+  // Row iteration of the per-iteration passes.  Capsules and cylinders have 2 or 4 rows of fixed structure
+  // ([0,0,0,L/2,-1], [0,0,0,L/2,+1], and for cylinders [+1,0,0,L/2,0], [-1,0,0,L/2,0]): their passes run straight-line, one
+  // compile-time row index each, so the row constants fold into the arithmetic (no row synthesis, no loop control, shared-
+  // memory offsets as immediates; rows took a third of the instructions of a capsule pair's iteration before).  All
+  // other classes run the run-time loop.  `f` receives the row index as std::integral_constant or as int.
+  template <int I> using RowC = std::integral_constant<int, I>;
+  template <class F>
+  __device__ __forceinline__ void for_rows(F&& f) const {
+    if constexpr (CLS == CLS_CAPCYL) {
+      f(RowC<0>{}); f(RowC<1>{});
+      if (n == 4) { f(RowC<2>{}); f(RowC<3>{}); }
+    } else {
+#pragma unroll ROW_UNROLL
+      for (int i = 0; i < n; i++) f(i);
+    }
+  }
+  template <class IT>
+  __device__ __forceinline__ void row_coef(IT I, double (&c)[NV]) const {
+    if constexpr (std::is_same<IT, int>::value) load_row(I, c);
+    else {
+      constexpr int i = IT::value;
+#pragma unroll
+      for (int a = 0; a < NV; a++) c[a] = 0.0;
+      c[3] = rc0;
+      if constexpr (i == 0) c[4] = -1.0;
+      if constexpr (i == 1) c[4] = 1.0;
+      if constexpr (i == 2) c[0] = 1.0;
+      if constexpr (i == 3) c[0] = -1.0;
+    }
+  }
+  template <class IT>
+  __device__ static constexpr bool row_nz(IT, int a) {          // structurally non-zero coefficient a of this row
+    if constexpr (std::is_same<IT, int>::value) return Cls<CLS>::nz(a);
+    else return a == 3 || (IT::value < 2 ? a == 4 : a == 0);
+  }
   const double* rows; int n; int row0;
   double rc0;                          // capsule / cylinder: L/2, cone: H/4 (the only non-trivial row constant)
   double sc[9];
@@ -366,27 +407,27 @@ struct Prim {
     for (int a = 0; a < NV; a++) { g[a] = 0.0;
 #pragma unroll
       for (int b = a; b < NV; b++) N[a][b] = 0.0; }
-#pragma unroll ROW_UNROLL
-    for (int i = 0; i < n; i++) {
+    for_rows([&](auto I) {
+      const int i = I;
       double c[NV];
-      load_row(i, c);
+      row_coef(I, c);
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i);
       double u = 0.0;
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) u += c[a] * yh[a];
+      for (int a = 0; a < NV; a++) if (row_nz(I, a)) u += c[a] * yh[a];
       const double r = si - u;
       const double rr = fast_rcp(si * zi);     // 1/(s z): 1/s = z*rr, 1/z = s*rr
       const double d = zi * zi * rr;           // z/s
       const double dr = d * r;
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) {
+      for (int a = 0; a < NV; a++) if (row_nz(I, a)) {
         const double dc = d * c[a];
         g[a] += dr * c[a];
 #pragma unroll
-        for (int b = a; b < NV; b++) if (nz(b)) N[a][b] += dc * c[b];
+        for (int b = a; b < NV; b++) if (row_nz(I, b)) N[a][b] += dc * c[b];
       }
       rs(F_R, row0 + i) = rr; rs(F_RZ, row0 + i) = r;
-    }
+    });
   }
   __device__ __forceinline__ bool passA_soc(const double (&yh)[NV], double (&N)[NV][NV], double (&g)[NV]) {
     if constexpr (D > 0) {
@@ -448,13 +489,13 @@ struct Prim {
   // ---- pass B: affine direction; step bounds (reciprocal form: m = max -d/y); sums for rho; Mehrotra correction
   // (orthant rows: the two ratio tests max q and max (1 - q) are one, 1/2 + max |q - 1/2|; mh carries max |q - 1/2|)
   __device__ __forceinline__ void passB_rows(const RowStore& rs, const double (&dyh)[NV], double& mh, double& dot1, double& dot2) {
-#pragma unroll ROW_UNROLL
-    for (int i = 0; i < n; i++) {
+    for_rows([&](auto I) {
+      const int i = I;
       double cd = 0.0;
       double c[NV];
-      load_row(i, c);
+      row_coef(I, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) cd += c[a] * dyh[a];
+      for (int a = 0; a < NV; a++) if (row_nz(I, a)) cd += c[a] * dyh[a];
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i);
       const double t = r - cd;                  // -ds
       const double is = zi * rr;
@@ -464,7 +505,7 @@ struct Prim {
       const double pp = -t * dza;
       rs(F_P, row0 + i) = pp;
       dot1 += si * dza - zi * t; dot2 += pp;
-    }
+    });
   }
   __device__ __forceinline__ void passB_soc(const double (&dyh)[NV], double& m, double& dot1, double& dot2) {
     if constexpr (D > 0) {
@@ -497,14 +538,14 @@ struct Prim {
   __device__ __forceinline__ void passC_rows(const RowStore& rs, double sigmu, double (&g2)[NV]) {
 #pragma unroll
     for (int a = 0; a < NV; a++) g2[a] = 0.0;
-#pragma unroll ROW_UNROLL
-    for (int i = 0; i < n; i++) {
+    for_rows([&](auto I) {
+      const int i = I;
       const double q = (sigmu - rs(F_P, row0 + i)) * rs(F_Z, row0 + i) * rs(F_R, row0 + i);
       double c[NV];
-      load_row(i, c);
+      row_coef(I, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) g2[a] += q * c[a];
-    }
+      for (int a = 0; a < NV; a++) if (row_nz(I, a)) g2[a] += q * c[a];
+    });
   }
   __device__ __forceinline__ void passC_soc(double sigmu, double (&g2)[NV]) {
     if constexpr (D > 0) {
@@ -531,20 +572,20 @@ struct Prim {
 
   // ---- pass D: final direction and step bounds; directions parked in F_RZ/F_P (rows) and rz/v (SOC)
   __device__ __forceinline__ void passD_rows(const RowStore& rs, const double (&dyh)[NV], double sigmu, double& m) {
-#pragma unroll ROW_UNROLL
-    for (int i = 0; i < n; i++) {
+    for_rows([&](auto I) {
+      const int i = I;
       double cd = 0.0;
       double c[NV];
-      load_row(i, c);
+      row_coef(I, c);
 #pragma unroll
-      for (int a = 0; a < NV; a++) if (nz(a)) cd += c[a] * dyh[a];
+      for (int a = 0; a < NV; a++) if (row_nz(I, a)) cd += c[a] * dyh[a];
       const double si = rs(F_S, row0 + i), zi = rs(F_Z, row0 + i), rr = rs(F_R, row0 + i), r = rs(F_RZ, row0 + i), pp = rs(F_P, row0 + i);
       const double t = r - cd;
       const double is = zi * rr, iz = si * rr;
       const double dz = (zi * t + sigmu - pp) * is - zi;
       m = dmax(m, t * is); m = dmax(m, -dz * iz);
       rs(F_RZ, row0 + i) = -t; rs(F_P, row0 + i) = dz;
-    }
+    });
   }
   __device__ __forceinline__ void passD_soc(const double (&dyh)[NV], double& m) {
     if constexpr (D > 0) {
@@ -569,11 +610,11 @@ struct Prim {
   // ---- pass E: take the step; returns the new s.z
   __device__ __forceinline__ double passE_rows(const RowStore& rs, double al) {
     double sz = 0.0;
-#pragma unroll ROW_UNROLL
-    for (int i = 0; i < n; i++) {
+    for_rows([&](auto I) {
+      const int i = I;
       double a = rs(F_S, row0 + i) + al * rs(F_RZ, row0 + i), b = rs(F_Z, row0 + i) + al * rs(F_P, row0 + i);
       rs(F_S, row0 + i) = a; rs(F_Z, row0 + i) = b; sz += a * b;
-    }
+    });
     return sz;
   }
   __device__ __forceinline__ double passE_soc(double al) {

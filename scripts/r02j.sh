@@ -3,6 +3,6 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02j_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02j_tests.log
 run() { echo "=== $1 [$2]"; env $2 DCOL_B200_LIB=build_variants/libdcol_$1.so timeout 300 python scripts/gpu_mini.py 2>&1 | tail -1; }
-{ run pre ""; run dmax ""; run pre ""; run dmax ""; } > gpurun_out/r02j_variants.log 2>&1
-timeout 600 bash scripts/gpu_ab.sh build_variants/libdcol_pre.so build_variants/libdcol_dmax.so > gpurun_out/r02j_ab.log 2>&1
+{ run dmax ""; run rows ""; run dmax ""; run rows ""; } > gpurun_out/r02j_variants.log 2>&1
+timeout 600 bash scripts/gpu_ab.sh build_variants/libdcol_dmax.so build_variants/libdcol_rows.so > gpurun_out/r02j_ab.log 2>&1
 tail -3 gpurun_out/r02j_tests.log; cat gpurun_out/r02j_variants.log; cat gpurun_out/r02j_ab.log | fold -w 200

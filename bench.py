@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-jacobian", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="cube", choices=["cube", "scene"])
+    ap.add_argument("--profile", action="store_true",
+                    help="for runs under ncu: the same device-resident timed region, without the end-to-end, scene, latency and CPU legs")
     return ap.parse_args()
 
 
@@ -347,19 +349,19 @@ def main():
         peak_sampler.start()
         time.sleep(0.1)
     tp0 = time.time()
-    fp64_peak = ctx.measure_fp64_tflops(0.6)
+    fp64_peak = ctx.measure_fp64_tflops(0.02 if args.profile else 0.6)
     peak_clocks = peak_sampler.stop(tp0, time.time()) if peak_sampler else None
-    prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234)
+    prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234, e2e=not args.profile)
     other = "scene" if args.variant == "cube" else "cube"
-    prox2 = run_config(0, dc.ATT_QUAT, args.pairs, max(3, args.steps // 4), args.warmup, 1234, variant=other, e2e=False)
+    prox2 = None if args.profile else run_config(0, dc.ATT_QUAT, args.pairs, max(3, args.steps // 4), args.warmup, 1234, variant=other, e2e=False)
     jac = None
     if not args.no_jacobian:
-        jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), args.warmup, 4321)
+        jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), args.warmup, 4321, e2e=not args.profile)
 
     # latency of the small calls every reference example makes in its inner loop (src/proximity.jl:3-14): wall clock
     # through the Python wrapper over the C ABI, pageable numpy arrays and device tensors
     latency = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.profile:
         def wall(f, reps):
             for _ in range(10):
                 f()
@@ -385,7 +387,7 @@ def main():
         lctx.close()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
         orc, oflags = native_oracle()
         threads = orc.max_threads()
         sample = min(250_000 * threads, 8_000_000)     # ~10-30 s of CPU work in total across the threads, bounded
@@ -440,7 +442,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": prox["steps"], "warmup": args.warmup,
                 "ms_per_step": prox["dev_ms"] / prox["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-                "e2e": {"value": world * prox["n"] * prox["e2e_steps"] / prox["e2e_s"], "unit": UNIT,
+                "e2e": None if args.profile else {"value": world * prox["n"] * prox["e2e_steps"] / prox["e2e_s"], "unit": UNIT,
                         "h2d_bytes_per_step": prox["in_bytes"], "d2h_bytes_per_step": prox["out_bytes"],
                         "api": "dcol_submit/dcol_wait, three submissions in flight, pinned host buffers",
                         "one_call_at_a_time": world * prox["n"] * prox["e2e_steps"] / prox["e2e_sync_s"],
@@ -449,13 +451,14 @@ def main():
                         "copy_bound_how": "same loop, buffers, streams and submission depth with the kernels switched off (dcol_set_copy_only)"},
                 "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox, "proximity"),
                 "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
-        r2 = roof(prox2, "proximity_" + prox2["variant"])
-        line[prox2["variant"]] = {"what": "same workload on the '%s' shape set" % prox2["variant"],
-                                  "value": world * prox2["n"] * prox2["steps"] / (max_over_ranks_done(prox2) * 1e-3), "unit": UNIT,
-                                  "ms_per_step": prox2["dev_ms"] / prox2["steps"], "kernel_ms_per_step": prox2["kernel_ms"],
-                                  "roofline_frac": r2["frac"], "achieved_tflops": r2["achieved"],
-                                  "algorithmic_flops_per_pair": r2["algorithmic_flops_per_pair"],
-                                  "mean_iters": prox2["mean_iters"], "max_iters": prox2["max_iters"], "failed_pairs": prox2["failed"]}
+        r2 = roof(prox2, "proximity_" + prox2["variant"]) if prox2 else None
+        if prox2:
+            line[prox2["variant"]] = {"what": "same workload on the '%s' shape set" % prox2["variant"],
+                                      "value": world * prox2["n"] * prox2["steps"] / (max_over_ranks_done(prox2) * 1e-3), "unit": UNIT,
+                                      "ms_per_step": prox2["dev_ms"] / prox2["steps"], "kernel_ms_per_step": prox2["kernel_ms"],
+                                      "roofline_frac": r2["frac"], "achieved_tflops": r2["achieved"],
+                                      "algorithmic_flops_per_pair": r2["algorithmic_flops_per_pair"],
+                                      "mean_iters": prox2["mean_iters"], "max_iters": prox2["max_iters"], "failed_pairs": prox2["failed"]}
         if latency:
             line["latency"] = latency
         if prox.get("gather"):
@@ -470,7 +473,7 @@ def main():
                 "ms_per_step": jac["dev_ms"] / jac["steps"],
                 "config": {"workload": "BASELINE config 3: proximity_jacobian, mixed 7x7 primitive types, MRP attitude",
                            "pairs_per_gpu": jac["n"], "global_pairs": jac["n"] * world},
-                "e2e": {"value": world * jac["n"] * jac["e2e_steps"] / jac["e2e_s"], "unit": UNIT,
+                "e2e": None if args.profile else {"value": world * jac["n"] * jac["e2e_steps"] / jac["e2e_s"], "unit": UNIT,
                         "h2d_bytes_per_step": jac["in_bytes"], "d2h_bytes_per_step": jac["out_bytes"],
                         "api": "dcol_submit/dcol_wait, three submissions in flight, pinned host buffers",
                         "one_call_at_a_time": world * jac["n"] * jac["e2e_steps"] / jac["e2e_sync_s"],

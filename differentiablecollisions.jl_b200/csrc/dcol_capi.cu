@@ -1358,12 +1358,12 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       }
       if (st != SC) { CK(cudaEventRecord(ctx->ev_join[t % (NSIDE - 1)], st)); CK(cudaStreamWaitEvent(SC, ctx->ev_join[t % (NSIDE - 1)], 0)); }
     }
+    CK(cudaEventRecord(L.ev_t1[c], SC));             // dcol_last_kernel_ms brackets the solver launches only (first pass + resume, all tiers)
     if (!small && !ctx->copy_only) {
       const int blocks = (int)std::min<int64_t>((nc + 255) / 256, 148 * 16);
       k_unpermute<<<blocks, 256, 0, SC>>>(nc, d_inv, src.oidx, s_alpha, s_x, s_st, s_it, s_mu, f_alpha, f_x, f_st, f_it, f_mu);
       ctx->launches += 1;
     }
-    CK(cudaEventRecord(L.ev_t1[c], SC));
     // ---- results of this chunk back (host mode), overlapping the next chunk's kernels
     if (staged) {
       CK(cudaMemcpyAsync(ctx->h_stage + STAGE_MAX, dout, b_out, cudaMemcpyDeviceToHost, S));

@@ -106,7 +106,11 @@ __device__ __forceinline__ bool ge_solve(double (&A)[N][N], double (&B)[N][NR]) 
   for (int k = 0; k < N; k++) {
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
+#ifdef DCOL_NO_PIVOT
+      const bool sw = false;                       // measurement build: elimination in natural order (round 1)
+#else
       const bool sw = fabs(A[i][k]) > fabs(A[k][k]);
+#endif
 #pragma unroll
       for (int j = k; j < N; j++) { const double a = A[k][j], b = A[i][j]; A[k][j] = sw ? b : a; A[i][j] = sw ? a : b; }
 #pragma unroll

@@ -120,8 +120,8 @@ static int drain_all(dcol_ctx* ctx);
 
 // ---------------------------------------------------------------------------
 // binning kernels: counting sort of pair indices by the UNORDERED class pair (lo, hi)[, then shape1, shape2]: a pair
-// whose classes arrive as (hi, lo) lands in the bin of (lo, hi) and is marked (bit 31 of its perm entry) so that the
-// solver exchanges its two primitives
+// whose classes arrive as (hi, lo) lands in the bin of (lo, hi) and is packed with its primitives exchanged (k_pack), so
+// the solver only ever sees class(prim 1) <= class(prim 2)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int pair_key(const int32_t* cls, const int32_t* keymap, int n_shapes, int s1, int s2) {
   if (keymap) return keymap[s1 * n_shapes + s2];
@@ -586,12 +586,19 @@ __global__ void k_se2_rows(int64_t np, int n_obs, const double* __restrict__ xyt
   }
 }
 
-// FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
+// FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure): 8 independent
+// chains per thread, 16 rounds per loop trip (128 DFMA against 3 loop instructions).  Under ncu the pipe reads 98 %
+// active; the round-1 probe (8 DFMA per trip as written, 32 after the compiler's unrolling) read 91 % and understated the
+// peak by as much (33.8 instead of 36.5 TFLOP/s; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2).
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; i++) {
-    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll 1
+  for (int i = 0; i < iters; i += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
@@ -1063,7 +1070,7 @@ double dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds) {
   double* d = nullptr;
   if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
   cudaStream_t s = ctx->stream();
-  k_dfma<<<blocks, threads, 0, s>>>(d, 2000, 1.0000001, 1e-9);   // warm-up
+  k_dfma<<<blocks, threads, 0, s>>>(d, 2000, 1.0000001, 1e-9);   // warm-up (iteration counts are multiples of 16)
   cudaStreamSynchronize(s);
   std::vector<float> ms_all;
   double total = 0.0;

@@ -23,27 +23,51 @@
 
 namespace dcol {
 
+// ---------------------------------------------------------------------------
+// branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H,
+// ~20 good bits) + one cubically convergent step.  No slow-path calls: operands here are positive, normal
+// numbers (failures are flagged by explicit `ok` tests before the result is used), and the
+// straight-line form keeps the solver passes in large basic blocks the scheduler can interleave.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);            // seed error e ~ 2^-20
+  return fma(y, fma(e, e, e), y);              // y (1 + e + e^2): cubic step, error e^3 ~ 2^-60
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);        // 1 - x y^2
+  const double p = fma(e, 0.375, 0.5) * e;     // e/2 + 3 e^2 / 8
+  return fma(y, p, y);                         // cubic step
+}
 // ---- one-partial forward-mode dual number -------------------------------------------------
 struct Dual1 { double v, d; };
 __device__ __forceinline__ Dual1 operator+(const Dual1& a, const Dual1& b) { return {a.v + b.v, a.d + b.d}; }
 __device__ __forceinline__ Dual1 operator-(const Dual1& a, const Dual1& b) { return {a.v - b.v, a.d - b.d}; }
 __device__ __forceinline__ Dual1 operator*(const Dual1& a, const Dual1& b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
-__device__ __forceinline__ Dual1 operator/(const Dual1& a, const Dual1& b) { double inv = 1.0 / b.v; double q = a.v * inv; return {q, (a.d - q * b.d) * inv}; }
+__device__ __forceinline__ Dual1 operator/(const Dual1& a, const Dual1& b) { double inv = fast_rcp(b.v); double q = a.v * inv; return {q, (a.d - q * b.d) * inv}; }
 __device__ __forceinline__ Dual1 operator+(const Dual1& a, double b) { return {a.v + b, a.d}; }
 __device__ __forceinline__ Dual1 operator-(const Dual1& a, double b) { return {a.v - b, a.d}; }
 __device__ __forceinline__ Dual1 operator-(double b, const Dual1& a) { return {b - a.v, -a.d}; }
 __device__ __forceinline__ Dual1 operator*(double b, const Dual1& a) { return {a.v * b, a.d * b}; }
 __device__ __forceinline__ Dual1 operator*(const Dual1& a, double b) { return {a.v * b, a.d * b}; }
-__device__ __forceinline__ Dual1 operator/(double b, const Dual1& a) { double inv = 1.0 / a.v; double q = b * inv; return {q, -q * a.d * inv}; }
-template <class T> __device__ __forceinline__ T t_sqrt(const T& a);
-template <> __device__ __forceinline__ double t_sqrt<double>(const double& a) { return sqrt(a); }
-template <> __device__ __forceinline__ Dual1 t_sqrt<Dual1>(const Dual1& a) { double r = sqrt(a.v); return {r, a.d * (0.5 / r)}; }
+__device__ __forceinline__ Dual1 operator/(double b, const Dual1& a) { double inv = fast_rcp(a.v); double q = b * inv; return {q, -q * a.d * inv}; }
+// 1/sqrt(a): the attitude maps only ever divide by the norm, so they take the reciprocal square root (hardware seed + one
+// cubic step, ~2^-60 relative) and multiply; the IEEE sqrt + four divisions were ~150 instructions per frame
+template <class T> __device__ __forceinline__ T t_rsqrt(const T& a);
+template <> __device__ __forceinline__ double t_rsqrt<double>(const double& a) { return fast_rsqrt(a); }
+template <> __device__ __forceinline__ Dual1 t_rsqrt<Dual1>(const Dual1& a) { double r = fast_rsqrt(a.v); return {r, -0.5 * a.d * r * r * r}; }
+template <class T> __device__ __forceinline__ T t_rcp(const T& a);
+template <> __device__ __forceinline__ double t_rcp<double>(const double& a) { return fast_rcp(a); }
+template <> __device__ __forceinline__ Dual1 t_rcp<Dual1>(const Dual1& a) { double r = fast_rcp(a.v); return {r, -a.d * r * r}; }
 
 // ---- attitude maps (src/problem_matrices.jl:9-27), templated on the scalar ------------------
 template <class T>
 __device__ __forceinline__ void dcm_from_q(const T q[4], T Q[3][3]) {
-  T nrm = t_sqrt<T>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  T q4 = q[0] / nrm, q1 = q[1] / nrm, q2 = q[2] / nrm, q3 = q[3] / nrm;
+  T inrm = t_rsqrt<T>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  T q4 = q[0] * inrm, q1 = q[1] * inrm, q2 = q[2] * inrm, q3 = q[3] * inrm;
   Q[0][0] = 2.0 * q1 * q1 + 2.0 * q4 * q4 - 1.0; Q[0][1] = 2.0 * (q1 * q2 - q3 * q4);         Q[0][2] = 2.0 * (q1 * q3 + q2 * q4);
   Q[1][0] = 2.0 * (q1 * q2 + q3 * q4);         Q[1][1] = 2.0 * q2 * q2 + 2.0 * q4 * q4 - 1.0; Q[1][2] = 2.0 * (q2 * q3 - q1 * q4);
   Q[2][0] = 2.0 * (q1 * q3 - q2 * q4);         Q[2][1] = 2.0 * (q2 * q3 + q1 * q4);         Q[2][2] = 2.0 * q3 * q3 + 2.0 * q4 * q4 - 1.0;
@@ -54,7 +78,7 @@ __device__ __forceinline__ void dcm_from_mrp(const T p[3], T Q[3][3]) {
   T den1 = p1 * p1 + p2 * p2 + p3 * p3 + 1.0;
   T den = den1 * den1;
   T a = 4.0 * p1 * p1 + 4.0 * p2 * p2 + 4.0 * p3 * p3 - 4.0;
-  T id = 1.0 / den;
+  T id = t_rcp<T>(den);
   Q[0][0] = 1.0 - (8.0 * p2 * p2 + 8.0 * p3 * p3) * id; Q[0][1] = (8.0 * p1 * p2 + p3 * a) * id; Q[0][2] = (8.0 * p1 * p3 - p2 * a) * id;
   Q[1][0] = (8.0 * p1 * p2 - p3 * a) * id; Q[1][1] = 1.0 - (8.0 * p1 * p1 + 8.0 * p3 * p3) * id; Q[1][2] = (8.0 * p2 * p3 + p1 * a) * id;
   Q[2][0] = (8.0 * p1 * p3 + p2 * a) * id; Q[2][1] = (8.0 * p2 * p3 - p1 * a) * id; Q[2][2] = 1.0 - (8.0 * p1 * p1 + 8.0 * p2 * p2) * id;
@@ -88,7 +112,7 @@ __device__ __forceinline__ void soc_jdiv(const double (&lam)[D], const double (&
   double rho = lam[0] * lam[0], nu = 0.0;
 #pragma unroll
   for (int i = 1; i < D; i++) { rho -= lam[i] * lam[i]; nu += lam[i] * w[i]; }
-  double irho = 1.0 / rho, il0 = 1.0 / lam[0];
+  double irho = fast_rcp(rho), il0 = fast_rcp(lam[0]);
   out[0] = irho * (lam[0] * w[0] - nu);
 #pragma unroll
   for (int i = 1; i < D; i++) out[i] = irho * ((nu * il0 - w[0]) * lam[i] + (rho * il0) * w[i]);
@@ -118,7 +142,7 @@ __device__ __forceinline__ bool ge_solve(double (&A)[N][N], double (&B)[N][NR]) 
     }
     double piv = A[k][k];
     ok = ok && (fabs(piv) > 0.0) && (piv == piv);
-    double ip = 1.0 / piv;
+    double ip = fast_rcp(piv);
 #pragma unroll
     for (int i = k + 1; i < N; i++) {
       double f = A[i][k] * ip;

@@ -28,25 +28,6 @@
 
 namespace dcol {
 
-// ---------------------------------------------------------------------------
-// branch-free FP64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H,
-// ~20 good bits) + one cubically convergent step.  No slow-path calls: operands here are positive, normal
-// numbers (failures are flagged by explicit `ok` tests before the result is used), and the
-// straight-line form keeps the solver passes in large basic blocks the scheduler can interleave.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double fast_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x, y, 1.0);            // seed error e ~ 2^-20
-  return fma(y, fma(e, e, e), y);              // y (1 + e + e^2): cubic step, error e^3 ~ 2^-60
-}
-__device__ __forceinline__ double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x * y, y, 1.0);        // 1 - x y^2
-  const double p = fma(e, 0.375, 0.5) * e;     // e/2 + 3 e^2 / 8
-  return fma(y, p, y);                         // cubic step
-}
 // max / min as one compare and one select.  fmax / fmin on doubles compile to DSETP.MAX + two selects + a NaN-quieting
 // LOP3 + moves for their operands (5-7 instructions; 10 % of the interior-point loop went there); NaNs need no
 // special care here: a NaN iterate is caught by the mu test of the next iteration.
@@ -664,7 +645,7 @@ struct Prim {
     for (int i = 0; i < n; i++) {
       double c[NV];
       load_row(i, c);
-      double d = rs(F_Z, row0 + i) / rs(F_S, row0 + i);
+      double d = rs(F_Z, row0 + i) * fast_rcp(rs(F_S, row0 + i));
 #pragma unroll
       for (int a = 0; a < NV; a++) if (nz(a)) { double dc = d * c[a];
 #pragma unroll
@@ -857,7 +838,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   double sz;
   int status = ST_OK;
   int cone_degree = A.n + B.n + (P1::D > 0 ? 1 : 0) + (P2::D > 0 ? 1 : 0);   // static_solver2.jl:124-130
-  const double inv_deg = 1.0 / (double)cone_degree;
+  const double inv_deg = fast_rcp((double)cone_degree);
 
   // The complete iterate of a pair as a record of doubles with stride st: tag, k, s.z, y[NX], rows s, rows z, SOC s|z of
   // prim 1, SOC s|z of prim 2.  Used by the straggler hand-over (field-major records of a bin, tag = sorted position)

@@ -13,7 +13,13 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace dcol {
@@ -59,6 +65,75 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Host-side copy engine for calls on PAGEABLE caller memory (plain numpy / Julia arrays).  The driver moves pageable
+// memory through its own bounce buffers on one thread (5-10 GB/s, and synchronously); the library instead copies
+// between the caller's arrays and its own pinned staging area with a few threads, chunk by chunk, while the GPU works
+// on the neighbouring chunks (run_query).  Slices of 1 MiB are handed out through one atomic counter; the calling
+// thread takes part.
+struct CopyJob { char* dst; const char* src; size_t bytes; };
+struct HostCopier {
+  // one batch of slices; late-waking workers that still hold an old batch find its counter exhausted and do nothing
+  struct Batch { std::vector<CopyJob> jobs; std::atomic<size_t> next{0}, done{0}; };
+  std::vector<std::thread> th;
+  std::mutex m; std::condition_variable cv;
+  std::shared_ptr<Batch> cur;
+  std::atomic<uint64_t> gen{0};
+  std::atomic<bool> stop{false};
+  static void add(std::vector<CopyJob>& J, void* dst, const void* src, size_t bytes) {
+    constexpr size_t SL = 512u << 10;
+    for (size_t o = 0; o < bytes; o += SL) J.push_back({(char*)dst + o, (const char*)src + o, std::min(SL, bytes - o)});
+  }
+  static void drain(Batch& B) {
+    for (;;) {
+      const size_t i = B.next.fetch_add(1, std::memory_order_relaxed);
+      if (i >= B.jobs.size()) break;
+      memcpy(B.jobs[i].dst, B.jobs[i].src, B.jobs[i].bytes);
+      B.done.fetch_add(1, std::memory_order_release);
+    }
+  }
+  static void relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  // Workers spin for a short while after their last batch before they block: the copy phases of one call (and of calls
+  // issued back to back) are fractions of a millisecond apart, and a futex wake-up costs as much as copying a megabyte.
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      const auto t0 = std::chrono::steady_clock::now();
+      while (gen.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(1500)) {
+          std::unique_lock<std::mutex> lk(m);
+          cv.wait(lk, [&] { return stop.load() || gen.load() != seen; });
+          break;
+        }
+        relax();
+      }
+      if (stop.load()) return;
+      std::shared_ptr<Batch> B;
+      { std::lock_guard<std::mutex> lk(m); B = cur; seen = gen.load(); }
+      if (B) drain(*B);
+    }
+  }
+  void start(int n) { for (int i = 0; i < n; i++) th.emplace_back([this] { loop(); }); }
+  void run(std::vector<CopyJob>& J) {      // consumes J
+    if (J.empty()) return;
+    if (th.empty() || J.size() < 4) { for (const CopyJob& j : J) memcpy(j.dst, j.src, j.bytes); J.clear(); return; }
+    std::shared_ptr<Batch> B = std::make_shared<Batch>();
+    B->jobs.swap(J);
+    { std::lock_guard<std::mutex> lk(m); cur = B; gen.fetch_add(1, std::memory_order_release); }
+    cv.notify_all();
+    drain(*B);
+    while (B->done.load(std::memory_order_acquire) < B->jobs.size()) relax();
+  }
+  ~HostCopier() {
+    { std::lock_guard<std::mutex> lk(m); stop.store(true); }
+    cv.notify_all();
+    for (std::thread& t : th) t.join();
+  }
+};
+
 }  // namespace
 
 struct dcol_ctx {
@@ -78,6 +153,10 @@ struct dcol_ctx {
   struct Tier { int n_bins = 0, rows_cap = 0, block = 0, pitch = 1; size_t smem = 0; int grid[3] = {0, 0, 0};
                 int cp[MAX_BINS]; int key_begin[MAX_BINS]; int key_end[MAX_BINS]; int ov_stride[MAX_BINS]; int max_stride = 0; };
   std::vector<Tier> tiers;
+  // Small batches (<= SMALL_MAX pairs) run every class pair in ONE launch with the row store of the largest tier: at
+  // that size the second launch, its side stream and the events between them cost more than the smaller L1 (only when
+  // the table has more than one tier and four warps of the merged row store fit an SM)
+  Tier small_tier; bool has_small = false;
   // per-call scratch.  Three slots, so that asynchronous submissions (dcol_submit) overlap: one staging its inputs,
   // one computing, one returning results; the synchronous entry points use slot 0.
   static constexpr int MAX_CHUNKS = 8;
@@ -85,6 +164,7 @@ struct dcol_ctx {
   struct Slot {
     DevBuf d_in, d_out, d_recs, d_inv, d_sorted, d_hist, d_tables, d_ov;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {}, ev_t0[MAX_CHUNKS] = {}, ev_t1[MAX_CHUNKS] = {};
+    cudaEvent_t ev_out[MAX_CHUNKS] = {};  // results of a chunk have landed in the pinned staging area (pageable-memory pipeline)
     cudaEvent_t ev_end = nullptr;       // recorded behind the last operation of the submission (its own join point)
     bool pending = false; int ticket = -1, result = 0;
     int nchunks = 0, nk = 0; size_t hist_stride = 0; bool piped = false;
@@ -104,6 +184,10 @@ struct dcol_ctx {
   int* h_count = nullptr;               // pinned landing area of the survivor count
   // pinned staging of small host-pointer calls: one H2D and one D2H copy per call instead of six and five
   char* h_stage = nullptr; size_t h_stage_cap = 0;
+  // pinned staging + copy threads of large calls on pageable caller memory (created on first use)
+  char* h_pin = nullptr; size_t h_pin_cap = 0;
+  HostCopier* copier = nullptr;
+  int host_pipe = -1;                   // -1: not probed yet (DCOL_HOST_PIPE=0 disables, DCOL_HOST_THREADS sets the thread count)
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   int n_sm = 148;
   int64_t launches = 0;
@@ -346,10 +430,11 @@ __global__ void k_scan_tables(const int* __restrict__ hist, int n_keys, int* __r
 constexpr int SMALL_MAX = 16384;
 constexpr int SMALL_THREADS = 1024;
 constexpr int SMALL_ITEMS = SMALL_MAX / SMALL_THREADS;
+constexpr int SMALL_FUSED = 4096;       // up to this many pairs the preparation kernel writes the packed records itself
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_prep(PairSource src, int n, const int32_t* __restrict__ cls, const int32_t* __restrict__ keymap,
                              int n_shapes, int n_keys, int* __restrict__ off, int* __restrict__ counters, int n_counters, int* __restrict__ bad,
                              int32_t* __restrict__ inv, const LaunchTable* __restrict__ plan, LaunchTable* __restrict__ tables, int n_tiers,
-                             double* ov_base, QueryParams P) {
+                             double* ov_base, QueryParams P, PairRec* __restrict__ recs) {
   extern __shared__ int sh[];            // [0, n_keys]: counts, then exclusive offsets
   __shared__ int part[SMALL_THREADS];
   __shared__ int s_nt[MAX_BINS];
@@ -394,7 +479,18 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_prep(PairSource src, in
 #pragma unroll
   for (int u = 0; u < SMALL_ITEMS; u++) {
     const int i = u * blockDim.x + tid;
-    if (i < n) inv[i] = (key[u] >= 0) ? sh[key[u]] + rank[u] : -1;
+    if (i < n) {
+      const int pos = (key[u] >= 0) ? sh[key[u]] + rank[u] : -1;
+      inv[i] = pos;
+      if (recs && pos >= 0) {            // a few thousand pairs at most: pack them here and save the k_pack launch
+        const int s1 = src.shape1[i], s2 = src.shape2[i];
+        double v[16];
+        load_pair(src, i, s1, s2, cls[s1] > cls[s2], v);
+        double2* q = reinterpret_cast<double2*>(recs + pos);
+#pragma unroll
+        for (int a = 0; a < 8; a++) q[a] = make_double2(v[2 * a], v[2 * a + 1]);
+      }
+    }
   }
   build_tables_dev(plan, tables, n_tiers, off, ov_base, P, 0, s_nt, s_ovsz, &s_ov);
 }
@@ -715,6 +811,7 @@ int dcol_create(dcol_ctx** out, int device_id) {
       dcol_ctx::Slot& L = ctx->slots[k];
       if ((e = cudaEventCreateWithFlags(&L.ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
       if ((e = cudaEventCreateWithFlags(&L.ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+      if ((e = cudaEventCreateWithFlags(&L.ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
       if ((e = cudaEventCreate(&L.ev_t0[i])) != cudaSuccess) return fail("cudaEventCreate", e);
       if ((e = cudaEventCreate(&L.ev_t1[i])) != cudaSuccess) return fail("cudaEventCreate", e);
     }
@@ -744,6 +841,7 @@ void dcol_destroy(dcol_ctx* ctx) {
     for (int i = 0; i < dcol_ctx::MAX_CHUNKS; i++) {
       if (L.ev_in[i]) cudaEventDestroy(L.ev_in[i]);
       if (L.ev_done[i]) cudaEventDestroy(L.ev_done[i]);
+      if (L.ev_out[i]) cudaEventDestroy(L.ev_out[i]);
       if (L.ev_t0[i]) cudaEventDestroy(L.ev_t0[i]);
       if (L.ev_t1[i]) cudaEventDestroy(L.ev_t1[i]);
     }
@@ -753,6 +851,8 @@ void dcol_destroy(dcol_ctx* ctx) {
     for (DevBuf* b : lb) b->release();
   }
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  delete ctx->copier;
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
@@ -995,14 +1095,18 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     std::vector<int> key_first(NCLS * NCLS + 1, ctx->n_keys);
     for (int k = ctx->n_keys - 1; k >= 0; k--) key_first[ctx->key_cp[k]] = k;
     for (int cp = NCLS * NCLS - 1; cp >= 0; cp--) if (key_first[cp] == ctx->n_keys || key_first[cp] > key_first[cp + 1]) key_first[cp] = key_first[cp + 1];
-    for (int tier = 0; tier < NTIER; tier++) {
+    ctx->has_small = false;
+    for (int tier = 0; tier <= NTIER; tier++) {
+      // tier == NTIER: the merged tier of small batches (every class pair present, row store of the largest)
+      const bool merged = (tier == NTIER);
+      if (merged && ctx->tiers.size() < 2) break;
       dcol_ctx::Tier T;
       std::vector<std::pair<int, int>> members;   // (weight, cp)
       for (int c1 = 0; c1 < NCLS; c1++) for (int c2 = c1; c2 < NCLS; c2++) {      // unordered class pairs
         if (!present[c1] || !present[c2]) continue;
         int need = std::max(1, ctx->max_rows_cls[c1] + ctx->max_rows_cls[c2]);
         if (need > tier_cap[NTIER - 1]) { ctx->err = "dcol_set_shapes: too many polytope faces / polygon sides for one pair (shared memory)"; ctx->n_shapes = 0; return -3; }
-        if (!(need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1]))) continue;
+        if (!merged && !(need <= tier_cap[tier] && (tier == 0 || need > tier_cap[tier - 1]))) continue;
         int weight = need + 6 * (cls_d(c1) + cls_d(c2)) + 8 * (cls_ne(c1) + cls_ne(c2));
         members.push_back({-weight, c1 * NCLS + c2});
         T.rows_cap = std::max(T.rows_cap, need);
@@ -1039,12 +1143,26 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
         }
         if (min_occ >= need_occ[a]) break;      // 4-warp CTAs only if two of them are resident per SM
       }
-      ctx->tiers.push_back(T);
+      if (merged) {
+        if (fit >= 4) {                          // four warps of the merged row store fit: 128-pair tiles as in the regular tiers
+          T.block = 128; T.smem = (size_t)T.pitch * sizeof(double) * T.block;
+          for (int jac = 0; jac < 3; jac++) {
+            const void* kfn = persistent_kernel_ptr(jac);
+            if (T.smem > 48 * 1024) CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_SMEM - 1024)));
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, T.block, T.smem));
+            T.grid[jac] = std::max(1, occ) * ctx->n_sm;
+          }
+          ctx->small_tier = T; ctx->has_small = true;
+        }
+      } else ctx->tiers.push_back(T);
     }
-    // device copy of the plan: one LaunchTable template per tier (key ranges in begin/end, CTA size in n_tiles, row pitch in P)
-    std::vector<LaunchTable> plan(std::max<size_t>(1, ctx->tiers.size()));
-    for (size_t t = 0; t < ctx->tiers.size(); t++) {
-      const dcol_ctx::Tier& TR = ctx->tiers[t];
+    if (const char* e = getenv("DCOL_SMALL_MERGED")) if (atoi(e) == 0) ctx->has_small = false;   // tuning knob
+    // device copy of the plan: one LaunchTable template per tier (key ranges in begin/end, CTA size in n_tiles, row pitch in P);
+    // the merged small-batch tier, if any, sits behind the regular ones
+    std::vector<LaunchTable> plan(std::max<size_t>(1, ctx->tiers.size()) + 1);
+    for (size_t t = 0; t < ctx->tiers.size() + (ctx->has_small ? 1 : 0); t++) {
+      const dcol_ctx::Tier& TR = (t < ctx->tiers.size()) ? ctx->tiers[t] : ctx->small_tier;
       LaunchTable& T = plan[t];
       memset(&T, 0, sizeof(T));
       T.P.row_pitch = TR.pitch; T.n_bins = TR.n_bins; T.rows_cap = TR.rows_cap; T.n_tiles = TR.block;
@@ -1135,9 +1253,28 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
 
   // ---- chunking: device-pointer calls run as one chunk; host-pointer calls are split so that the H2D copy of
   // chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (three streams)
+  // Large synchronous calls on PAGEABLE caller memory run the library's own staging pipeline (HostCopier): per chunk,
+  // copy threads move the caller's inputs into pinned memory ahead of the H2D copy and the results out of pinned memory
+  // behind the D2H copy, overlapping the GPU work of the neighbouring chunks.  Page-locked arrays (cudaHostAlloc,
+  // dcol_host_register) keep the direct path.
+  constexpr size_t STAGE_MAX = 8u << 20;      // below this, one packed staging copy per direction (the small-call path further down)
+  bool pageable = false;
+  {
+    const size_t approx = (size_t)n * (8 + 8 * (6 + 2 * (size_t)na) + 8 + 24 + 8 * dsz + 8 + (ctx->mu_out ? 8 : 0));
+    if (ctx->host_pipe < 0) { const char* e = getenv("DCOL_HOST_PIPE"); ctx->host_pipe = (e && atoi(e) == 0) ? 0 : 1; }
+    if (ctx->host_pipe && !async && mem == DCOL_MEM_HOST && !ctx->copy_only && approx > STAGE_MAX) {
+      auto unpinned = [](const void* q) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, q) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+        return pa.type == cudaMemoryTypeUnregistered;
+      };
+      pageable = unpinned(alpha) || (deriv && unpinned(deriv)) || (x && unpinned(x));
+      if (in_mem == DCOL_MEM_HOST) pageable = pageable || unpinned(r1) || unpinned(att2);   // (device-generated pair lists: results only)
+    }
+  }
   int nchunks = 1;
   if ((mem == DCOL_MEM_HOST || in_mem == DCOL_MEM_HOST) && !async) {      // asynchronous submissions overlap with each other instead
-    int64_t target = 350000;
+    int64_t target = pageable ? 200000 : 350000;
     if (const char* e = getenv("DCOL_CHUNK")) target = std::max<int64_t>(1024, atoll(e));
     nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(dcol_ctx::MAX_CHUNKS, (n + target / 2) / target));
   }
@@ -1148,7 +1285,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   const size_t hist_stride = (hist_ints + 63) & ~(size_t)63;
   CK(L.d_hist.need(sizeof(int) * hist_stride * nchunks));
   const bool small = (n <= SMALL_MAX) && nchunks == 1;      // single-block preparation, no hand-over, direct result stores
-  int max_block = 32;
+  int max_block = 128;
   for (int t = 0; t < nt_tiers; t++) max_block = std::max(max_block, ctx->tiers[t].block);
   CK(L.d_recs.need(sizeof(PairRec) * ((size_t)n + max_block)));      // one tile of slack behind the last record
   CK(L.d_inv.need(sizeof(int32_t) * n));
@@ -1200,7 +1337,6 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   }
   // ---- small synchronous host calls: pack the inputs into one pinned staging area (host memcpy), one H2D copy, one D2H
   // copy of all results, unpack on the host.  Pageable caller memory would otherwise cost one driver-staged copy per array.
-  constexpr size_t STAGE_MAX = 8u << 20;
   size_t b_in = 0, b_out = 0;
   if (in_mem == DCOL_MEM_HOST) b_in = o_a2 + align256(sizeof(double) * na * rows2);
   if (mem == DCOL_MEM_HOST) b_out = o_mu + align256(sizeof(double) * (ctx->mu_out ? n : 0));
@@ -1218,6 +1354,57 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     memcpy(hs + o_r1, r1, sizeof(double) * 3 * rows1); memcpy(hs + o_a1, att1, sizeof(double) * na * rows1);
     memcpy(hs + o_r2, r2, sizeof(double) * 3 * rows2); memcpy(hs + o_a2, att2, sizeof(double) * na * rows2);
   }
+  // ---- pageable-memory pipeline: pinned staging for the whole call (inputs | results), copy threads on first use
+  char* hp_in = nullptr; char* hp_out = nullptr;
+  if (pageable) {
+    size_t lim_mb = 8192;
+    if (const char* e = getenv("DCOL_PIN_MAX_MB")) lim_mb = (size_t)std::max(0, atoi(e));
+    const size_t want = align256(b_in) + align256(b_out);
+    if (want > (lim_mb << 20)) pageable = false;
+    else if (ctx->h_pin_cap < want) {
+      if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+      ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+      const size_t cap = want + want / 8;
+      if (cudaHostAlloc((void**)&ctx->h_pin, cap, cudaHostAllocDefault) == cudaSuccess) ctx->h_pin_cap = cap;
+      else { (void)cudaGetLastError(); ctx->h_pin = nullptr; pageable = false; }      // no pinned memory to spare: the driver's pageable path
+    }
+    if (pageable && !ctx->copier) {
+      int nth = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+      if (const char* e = getenv("DCOL_HOST_THREADS")) nth = std::max(1, std::min(64, atoi(e)));
+      ctx->copier = new HostCopier();
+      ctx->copier->start(nth - 1);                // the calling thread copies too
+    }
+    if (pageable) { hp_in = ctx->h_pin; hp_out = ctx->h_pin + align256(b_in); }
+  }
+  // host-side source / destination of the copies: the caller's arrays, or their image in the pinned staging area
+  const int32_t* hs1 = pageable ? (const int32_t*)(hp_in + o_s1) : shape1;
+  const int32_t* hs2 = pageable ? (const int32_t*)(hp_in + o_s2) : shape2;
+  const int32_t* hq1 = pageable ? (const int32_t*)(hp_in + o_p1) : pose1;
+  const int32_t* hq2 = pageable ? (const int32_t*)(hp_in + o_p2) : pose2;
+  const double* hr1 = pageable ? (const double*)(hp_in + o_r1) : r1;
+  const double* ha1 = pageable ? (const double*)(hp_in + o_a1) : att1;
+  const double* hr2 = pageable ? (const double*)(hp_in + o_r2) : r2;
+  const double* ha2 = pageable ? (const double*)(hp_in + o_a2) : att2;
+  double* ho_alpha = pageable ? (double*)(hp_out + o_alpha) : alpha;
+  double* ho_x = pageable ? (double*)(hp_out + o_x) : x;
+  double* ho_der = pageable ? (double*)(hp_out + o_der) : deriv;
+  int32_t* ho_st = pageable ? (int32_t*)(hp_out + o_st) : status;
+  int32_t* ho_it = pageable ? (int32_t*)(hp_out + o_it) : iters;
+  double* ho_mu = pageable ? (double*)(hp_out + o_mu) : ctx->mu_out;
+  std::vector<CopyJob> jobs;
+  int drained = 0;                              // result chunks already copied out of the staging area
+  std::vector<int64_t> cb;                      // chunk boundaries (filled below)
+  auto unstage = [&](int k) {                   // results of chunk k: pinned staging -> the caller's arrays
+    const int64_t k0 = cb[k], nk_ = cb[k + 1] - cb[k];
+    jobs.clear();
+    HostCopier::add(jobs, alpha + k0, ho_alpha + k0, sizeof(double) * nk_);
+    if (x) HostCopier::add(jobs, x + 3 * k0, ho_x + 3 * k0, sizeof(double) * 3 * nk_);
+    if (dsz) HostCopier::add(jobs, deriv + dsz * k0, ho_der + dsz * k0, sizeof(double) * dsz * nk_);
+    if (status) HostCopier::add(jobs, status + k0, ho_st + k0, sizeof(int32_t) * nk_);
+    if (iters) HostCopier::add(jobs, iters + k0, ho_it + k0, sizeof(int32_t) * nk_);
+    if (ctx->mu_out) HostCopier::add(jobs, ctx->mu_out + k0, ho_mu + k0, sizeof(double) * nk_);
+    ctx->copier->run(jobs);
+  };
   const int jac = query;                       // kernel variant = query kind
   cudaStream_t S = ctx->stream();
   const bool piped = (nchunks > 1) || async;                  // three-stream pipeline (always for asynchronous submissions)
@@ -1227,14 +1414,20 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   if (staged) CK(cudaMemcpyAsync(di, ctx->h_stage, b_in, cudaMemcpyHostToDevice, S));
   if (indexed && in_mem == DCOL_MEM_HOST && !staged) {       // pose tables go up once, ahead of the first chunk's pair lists
     cudaStream_t SI = piped ? ctx->s_copy : S;
-    CK(cudaMemcpyAsync(di + o_r1, r1, sizeof(double) * 3 * np1, cudaMemcpyHostToDevice, SI));
-    CK(cudaMemcpyAsync(di + o_a1, att1, sizeof(double) * na * np1, cudaMemcpyHostToDevice, SI));
-    CK(cudaMemcpyAsync(di + o_r2, r2, sizeof(double) * 3 * np2, cudaMemcpyHostToDevice, SI));
-    CK(cudaMemcpyAsync(di + o_a2, att2, sizeof(double) * na * np2, cudaMemcpyHostToDevice, SI));
+    if (pageable) {
+      jobs.clear();
+      HostCopier::add(jobs, hp_in + o_r1, r1, sizeof(double) * 3 * np1); HostCopier::add(jobs, hp_in + o_a1, att1, sizeof(double) * na * np1);
+      HostCopier::add(jobs, hp_in + o_r2, r2, sizeof(double) * 3 * np2); HostCopier::add(jobs, hp_in + o_a2, att2, sizeof(double) * na * np2);
+      ctx->copier->run(jobs);
+    }
+    CK(cudaMemcpyAsync(di + o_r1, hr1, sizeof(double) * 3 * np1, cudaMemcpyHostToDevice, SI));
+    CK(cudaMemcpyAsync(di + o_a1, ha1, sizeof(double) * na * np1, cudaMemcpyHostToDevice, SI));
+    CK(cudaMemcpyAsync(di + o_r2, hr2, sizeof(double) * 3 * np2, cudaMemcpyHostToDevice, SI));
+    CK(cudaMemcpyAsync(di + o_a2, ha2, sizeof(double) * na * np2, cudaMemcpyHostToDevice, SI));
   }
   // chunk boundaries: a short first chunk lets the kernels start early while the bulk is still crossing PCIe
   for (int c = 0; c < nchunks; c++) L.h_bad[c] = 0;
-  std::vector<int64_t> cb(nchunks + 1, 0);
+  cb.assign(nchunks + 1, 0);
   {
     const int64_t first = (nchunks > 1) ? std::min<int64_t>(n / (2 * nchunks), 120000) : n;
     cb[nchunks] = n;
@@ -1259,17 +1452,32 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     src.oidx = oidx ? oidx + c0 : nullptr;
     if (in_mem == DCOL_MEM_HOST) {
       cudaStream_t SI = piped ? ctx->s_copy : S;
+      if (pageable) {      // this chunk's inputs: the caller's arrays -> pinned staging (the GPU is busy with the previous chunk meanwhile)
+        jobs.clear();
+        HostCopier::add(jobs, hp_in + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc);
+        HostCopier::add(jobs, hp_in + o_s2 + sizeof(int32_t) * c0, shape2 + c0, sizeof(int32_t) * nc);
+        if (indexed) {
+          HostCopier::add(jobs, hp_in + o_p1 + sizeof(int32_t) * c0, pose1 + c0, sizeof(int32_t) * nc);
+          HostCopier::add(jobs, hp_in + o_p2 + sizeof(int32_t) * c0, pose2 + c0, sizeof(int32_t) * nc);
+        } else {
+          HostCopier::add(jobs, hp_in + o_r1 + sizeof(double) * 3 * c0, r1 + 3 * c0, sizeof(double) * 3 * nc);
+          HostCopier::add(jobs, hp_in + o_a1 + sizeof(double) * na * c0, att1 + na * c0, sizeof(double) * na * nc);
+          HostCopier::add(jobs, hp_in + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc);
+          HostCopier::add(jobs, hp_in + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc);
+        }
+        ctx->copier->run(jobs);
+      }
       if (!staged) {
-      CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, shape1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
-      CK(cudaMemcpyAsync(di + o_s2 + sizeof(int32_t) * c0, shape2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_s1 + sizeof(int32_t) * c0, hs1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+      CK(cudaMemcpyAsync(di + o_s2 + sizeof(int32_t) * c0, hs2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       if (indexed) {
-        CK(cudaMemcpyAsync(di + o_p1 + sizeof(int32_t) * c0, pose1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
-        CK(cudaMemcpyAsync(di + o_p2 + sizeof(int32_t) * c0, pose2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_p1 + sizeof(int32_t) * c0, hq1 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_p2 + sizeof(int32_t) * c0, hq2 + c0, sizeof(int32_t) * nc, cudaMemcpyHostToDevice, SI));
       } else {
-        CK(cudaMemcpyAsync(di + o_r1 + sizeof(double) * 3 * c0, r1 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
-        CK(cudaMemcpyAsync(di + o_a1 + sizeof(double) * na * c0, att1 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
-        CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, r2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
-        CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, att2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_r1 + sizeof(double) * 3 * c0, hr1 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_a1 + sizeof(double) * na * c0, ha1 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_r2 + sizeof(double) * 3 * c0, hr2 + 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, SI));
+        CK(cudaMemcpyAsync(di + o_a2 + sizeof(double) * na * c0, ha2 + na * c0, sizeof(double) * na * nc, cudaMemcpyHostToDevice, SI));
       }
       }
       if (piped) { CK(cudaEventRecord(L.ev_in[c], SI)); CK(cudaStreamWaitEvent(SC, L.ev_in[c], 0)); }
@@ -1330,11 +1538,17 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     if (ctx->copy_only) {
       // measurement mode: the copies of this call with the same buffers, streams and chunking, and no kernels
     } else if (small) {
+      // one preparation launch (which also packs up to SMALL_FUSED pairs) and one solver launch over the merged tier
+      const bool fused = nc <= SMALL_FUSED;
+      const LaunchTable* plan = (const LaunchTable*)ctx->d_plan.p + (ctx->has_small ? nt_tiers : 0);
       k_small_prep<<<1, SMALL_THREADS, sizeof(int) * (nk + 1), SC>>>(src, (int)nc, (const int32_t*)ctx->d_cls.p, d_keymap, ctx->n_shapes, nk,
                                                                       d_off, d_counter, (2 + MAX_LEVELS) * NSIDE, d_bad, d_inv,
-                                                                      (const LaunchTable*)ctx->d_plan.p, d_tab, nt_tiers, d_ovc, P);
-      k_pack<<<(int)std::min<int64_t>((nc + PACK_THREADS - 1) / PACK_THREADS, 148 * 8), PACK_THREADS, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
-      ctx->launches += 2;
+                                                                      plan, d_tab, ctx->has_small ? 1 : nt_tiers, d_ovc, P, fused ? d_recs : nullptr);
+      ctx->launches += 1;
+      if (!fused) {
+        k_pack<<<(int)std::min<int64_t>((nc + PACK_THREADS - 1) / PACK_THREADS, 148 * 8), PACK_THREADS, 0, SC>>>(src, nc, (const int32_t*)ctx->d_cls.p, d_inv, d_recs);
+        ctx->launches += 1;
+      }
     } else {
       CK(cudaMemsetAsync(d_hist, 0, sizeof(int) * hist_ints, SC));
       int threads = 256;
@@ -1349,12 +1563,16 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     CK(cudaEventRecord(L.ev_t0[c], SC));
     // per tier, on the tier's stream: first pass, then (right behind it) the resume passes that finish the handed-over
     // stragglers in dense tiles — the resume pass of one tier overlaps the first pass of the next
-    if (nt_tiers > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
-    for (int t = 0; t < nt_tiers && !ctx->copy_only; t++) {
-      const dcol_ctx::Tier& TR = ctx->tiers[t];
-      cudaStream_t st = (nt_tiers == 1) ? SC : ctx->side[t % NSIDE];
+    const bool one_launch = small && ctx->has_small;
+    const int n_launch = one_launch ? 1 : nt_tiers;
+    if (n_launch > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
+    for (int t = 0; t < n_launch && !ctx->copy_only; t++) {
+      const dcol_ctx::Tier& TR = one_launch ? ctx->small_tier : ctx->tiers[t];
+      cudaStream_t st = (n_launch == 1) ? SC : ctx->side[t % NSIDE];
       if (st != SC) CK(cudaStreamWaitEvent(st, ctx->ev_join[NSIDE - 1], 0));
-      CK(launch_persistent(jac, TR.grid[jac], TR.block, TR.smem, st, d_tab + t, d_counter + t));
+      // small batches: no more CTAs than there can be tiles (every bin may end in a partial tile)
+      const int grid = small ? (int)std::min<int64_t>(TR.grid[jac], nc / TR.block + TR.n_bins + 1) : TR.grid[jac];
+      CK(launch_persistent(jac, grid, TR.block, TR.smem, st, d_tab + t, d_counter + t));
       ctx->launches++;
       for (int lv = 1; lv <= levels && spill_div > 0 && !small; lv++) {
         LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers) + t;
@@ -1377,12 +1595,17 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     } else if (mem == DCOL_MEM_HOST) {
       cudaStream_t SO = piped ? ctx->s_out : S;
       if (piped) { CK(cudaEventRecord(L.ev_done[c], SC)); CK(cudaStreamWaitEvent(SO, L.ev_done[c], 0)); }
-      CK(cudaMemcpyAsync(alpha + c0, dout + o_alpha + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
-      if (x) CK(cudaMemcpyAsync(x + 3 * c0, dout + o_x + sizeof(double) * 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, SO));
-      if (dsz) CK(cudaMemcpyAsync(deriv + dsz * c0, dout + o_der + sizeof(double) * dsz * c0, sizeof(double) * dsz * nc, cudaMemcpyDeviceToHost, SO));
-      if (status) CK(cudaMemcpyAsync(status + c0, dout + o_st + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
-      if (iters) CK(cudaMemcpyAsync(iters + c0, dout + o_it + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
-      if (ctx->mu_out) CK(cudaMemcpyAsync(ctx->mu_out + c0, dout + o_mu + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
+      CK(cudaMemcpyAsync(ho_alpha + c0, dout + o_alpha + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
+      if (x) CK(cudaMemcpyAsync(ho_x + 3 * c0, dout + o_x + sizeof(double) * 3 * c0, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, SO));
+      if (dsz) CK(cudaMemcpyAsync(ho_der + dsz * c0, dout + o_der + sizeof(double) * dsz * c0, sizeof(double) * dsz * nc, cudaMemcpyDeviceToHost, SO));
+      if (status) CK(cudaMemcpyAsync(ho_st + c0, dout + o_st + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
+      if (iters) CK(cudaMemcpyAsync(ho_it + c0, dout + o_it + sizeof(int32_t) * c0, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, SO));
+      if (ctx->mu_out) CK(cudaMemcpyAsync(ho_mu + c0, dout + o_mu + sizeof(double) * c0, sizeof(double) * nc, cudaMemcpyDeviceToHost, SO));
+      if (pageable) {
+        CK(cudaEventRecord(L.ev_out[c], SO));
+        // results of earlier chunks that have landed meanwhile go to the caller's arrays now (never waits)
+        while (drained < c && cudaEventQuery(L.ev_out[drained]) == cudaSuccess) unstage(drained++);
+      }
     }
   }
   // ---- the join is finish_query (the only host synchronisation); the bad-shape flags are mapped host memory
@@ -1394,6 +1617,9 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   CK(cudaEventRecord(L.ev_end, SL));
   L.pending = true; L.nchunks = nchunks; L.piped = piped; L.result = 0;
   if (async) return 0;
+  if (pageable) {
+    for (; drained < nchunks; drained++) { CK(cudaEventSynchronize(L.ev_out[drained])); unstage(drained); }
+  }
   const int rc = finish_query(ctx, slot);
   if (staged && rc == 0) {
     const char* ho = ctx->h_stage + STAGE_MAX;

@@ -47,8 +47,14 @@ __device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, const 
   }
 }
 
+// DCOL_MAXNREG (tuning builds): an exact register budget instead of the one derived from the launch bounds
+#ifdef DCOL_MAXNREG
+#define DCOL_KERNEL_BOUNDS __maxnreg__(DCOL_MAXNREG)
+#else
+#define DCOL_KERNEL_BOUNDS __launch_bounds__(DCOL_MAXTHREADS, DCOL_MINBLOCKS)
+#endif
 template <int VAR>
-__global__ void __launch_bounds__(DCOL_MAXTHREADS, DCOL_MINBLOCKS) proximity_persistent(LaunchTable* __restrict__ tt, int* __restrict__ counter) {
+__global__ void DCOL_KERNEL_BOUNDS proximity_persistent(LaunchTable* __restrict__ tt, int* __restrict__ counter) {
   __shared__ int s_tile;
   const int n_tiles = tt->n_tiles;
   const int tile_sz = blockDim.x;

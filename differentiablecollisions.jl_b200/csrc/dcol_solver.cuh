@@ -38,10 +38,23 @@ __device__ __forceinline__ double dmax(double a, double b) {
 __device__ __forceinline__ double dmin(double a, double b) {
   double r; asm("{ .reg .pred p; setp.lt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b)); return r;
 }
+#ifndef DCOL_LEAN_SQRT
+#define DCOL_LEAN_SQRT 1
+#endif
 __device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 ; sqrt(0) = 0
+#if DCOL_LEAN_SQRT
+  // hardware seed y ~ 1/sqrt(x), g = x y ~ sqrt(x), e = 1 - x y^2 (|e| ~ 2^-19): sqrt(x) = g (1 - e)^(-1/2) = g (1 + e/2 + 3e^2/8 + O(e^3)),
+  // 7 instructions, ~1 ulp (the step lengths it feeds are damped by 0.99; 12 instructions bought the last half ulp before)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x + 0x1p-1000));   // keeps the seed finite at 0; x + 2^-1000 == x for every x >= 2^-947
+  const double g = x * y;
+  const double e = fma(-g, y, 1.0);
+  return fma(g, fma(e, 0.375, 0.5) * e, g);
+#else
   double r = fast_rsqrt(x + 0x1p-1000);                    // keeps rsqrt(0) finite; x + 2^-1000 == x for every x >= 2^-947
   double sq = x * r;
   return fma(fma(-sq, sq, x), 0.5 * r, sq);               // one correction step on the product
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -67,9 +80,40 @@ struct RelPoseT { const double* p; __device__ __forceinline__ double operator[](
 // ---------------------------------------------------------------------------
 // small dense helpers (upper-triangular storage in full arrays; fully unrolled)
 // ---------------------------------------------------------------------------
+// The reference factors the KKT matrix by Cholesky (static_solver2.jl:92,153).  Here M = U'DU with U UNIT upper
+// triangular (right-looking, in place; id = 1/D): the same solution to round-off, but the pivots need a reciprocal
+// instead of a reciprocal square root and the triangular sweeps are one dependent FMA per step instead of an FMA and a
+// multiply -- the factor-and-solve chain is the longest serial stretch of an iteration, and with two warps per scheduler
+// its latency is exposed.  Positive definiteness is still the test "every pivot > 0".
+// (nx = 8, polygon-polygon pairs only, keeps the Cholesky form: the right-looking update of a full 8x8 factor next to two
+// polygon cone blocks made ptxas spill inside the loop: 138 -> 381 local-memory instructions, +19 % on that class pair)
+#ifndef DCOL_LDL
+#define DCOL_LDL 1
+#endif
+#ifndef DCOL_LDL_MAXN
+#define DCOL_LDL_MAXN 7
+#endif
 template <int N>
-__device__ __forceinline__ bool chol_upper(double (&M)[N][N], double (&id)[N]) {   // M = U'U in place, id = 1/diag(U)
+__device__ __forceinline__ bool chol_upper(double (&M)[N][N], double (&id)[N]) {
+  if constexpr (DCOL_LDL && N <= DCOL_LDL_MAXN) {
   bool ok = true;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    const double d = M[j][j];
+    ok = ok && (d > 0.0);
+    const double inv = fast_rcp(d);
+    id[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      const double u = M[j][i] * inv;                      // U[j][i]; row j still holds D_j U[j][l] for l >= i
+#pragma unroll
+      for (int l = i; l < N; l++) M[i][l] = fma(-u, M[j][l], M[i][l]);
+      M[j][i] = u;
+    }
+  }
+  return ok;
+  } else {
+  bool ok = true;                                          // M = U'U in place, id = 1/diag(U)
 #pragma unroll
   for (int j = 0; j < N; j++) {
     double d = M[j][j];
@@ -88,10 +132,23 @@ __device__ __forceinline__ bool chol_upper(double (&M)[N][N], double (&id)[N]) {
     }
   }
   return ok;
+  }
 }
 template <int N>
 __device__ __forceinline__ void chol_solve(const double (&U)[N][N], const double (&id)[N], const double (&b)[N], double (&x)[N]) {
   double y[N];
+  if constexpr (DCOL_LDL && N <= DCOL_LDL_MAXN) {
+#pragma unroll
+  for (int i = 0; i < N; i++) { double a = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) a = fma(-U[k][i], y[k], a);
+    y[i] = a; }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) { double a = y[i] * id[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) a = fma(-U[i][k], x[k], a);
+    x[i] = a; }
+  } else {
 #pragma unroll
   for (int i = 0; i < N; i++) { double a = b[i];
 #pragma unroll
@@ -102,6 +159,7 @@ __device__ __forceinline__ void chol_solve(const double (&U)[N][N], const double
 #pragma unroll
     for (int k = i + 1; k < N; k++) a -= U[i][k] * x[k];
     x[i] = a * id[i]; }
+  }
 }
 
 // ---------------------------------------------------------------------------

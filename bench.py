@@ -320,6 +320,21 @@ def main():
                 copy_s = pipelined()
             finally:
                 ctx.set_copy_only(False)
+        # the default caller path: blocking calls on PAGEABLE arrays (plain numpy / Julia Arrays, outputs reused) — the library's
+        # own staging pipeline (copy threads + pinned staging, dcol_capi.cu HostCopier) instead of page-locked caller buffers
+        pageable_s = None
+        if e2e and world == 1:
+            np_in = [h.numpy().copy() for h in host]
+            np_out = [np.empty_like(tn.numpy()) if tn is not None else None for tn in (h_alpha, h_x, h_der, h_st, h_it)]
+
+            def pageable_step():
+                ctx.query_raw(kind, n, *np_in, att_kind, PDIP_TOL, dc.MEM_HOST, *np_out)
+            pageable_step(); pageable_step()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                pageable_step()
+            pageable_s = time.perf_counter() - t0
+            del np_in, np_out
         # optional result gather over NVLink: all-gather of the alpha rows, outside the timed step
         gather = None
         if world > 1:
@@ -340,7 +355,7 @@ def main():
         in_b = n * (8 + 8 * (6 + 2 * na))
         out_b = n * (8 + 8 * (1 + 3 + (4 * nt if kind == 2 else 0)))
         return {"n": n, "dev_ms": dev_ms, "steps": steps, "kernel_ms": float(np.mean(kms)), "launches": launches, "clocks": clocks,
-                "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s, "copy_s": copy_s, "e2e_steps": e2e_steps, "variant": variant, "flops": flops, "in_bytes": in_b, "out_bytes": out_b,
+                "e2e_s": e2e_s, "e2e_sync_s": e2e_sync_s, "copy_s": copy_s, "pageable_s": pageable_s, "e2e_steps": e2e_steps, "variant": variant, "flops": flops, "in_bytes": in_b, "out_bytes": out_b,
                 "mean_iters": float(iters.mean()), "max_iters": int(iters.max()), "failed": int((status != 0).sum()), "gather": gather}
 
     # FP64 roofline denominator: 0.6 s of back-to-back DFMA-only launches (median launch), SM clock sampled meanwhile
@@ -448,7 +463,9 @@ def main():
                         "one_call_at_a_time": world * prox["n"] * prox["e2e_steps"] / prox["e2e_sync_s"],
                         "copy_bound": world * prox["n"] * prox["e2e_steps"] / prox["copy_s"],
                         "frac_of_copy_bound": prox["copy_s"] / prox["e2e_s"],
-                        "copy_bound_how": "same loop, buffers, streams and submission depth with the kernels switched off (dcol_set_copy_only)"},
+                        "copy_bound_how": "same loop, buffers, streams and submission depth with the kernels switched off (dcol_set_copy_only)",
+                        "pageable_arrays_one_call_at_a_time": (prox["n"] * prox["e2e_steps"] / prox["pageable_s"]) if prox["pageable_s"] else None,
+                        "pageable_how": "blocking dcol_proximity on plain (pageable) numpy arrays, outputs reused: the library stages through its own pinned buffers with copy threads"},
                 "gpu_launches": prox["launches"], "clocks": prox["clocks"], "roofline": roof(prox, "proximity"),
                 "solver": {"mean_iters": prox["mean_iters"], "max_iters": prox["max_iters"], "failed_pairs": prox["failed"]}}
         r2 = roof(prox2, "proximity_" + prox2["variant"]) if prox2 else None
@@ -478,7 +495,8 @@ def main():
                         "api": "dcol_submit/dcol_wait, three submissions in flight, pinned host buffers",
                         "one_call_at_a_time": world * jac["n"] * jac["e2e_steps"] / jac["e2e_sync_s"],
                         "copy_bound": world * jac["n"] * jac["e2e_steps"] / jac["copy_s"],
-                        "frac_of_copy_bound": jac["copy_s"] / jac["e2e_s"]},
+                        "frac_of_copy_bound": jac["copy_s"] / jac["e2e_s"],
+                        "pageable_arrays_one_call_at_a_time": (jac["n"] * jac["e2e_steps"] / jac["pageable_s"]) if jac["pageable_s"] else None},
                 "gpu_launches": jac["launches"], "clocks": jac["clocks"], "roofline": roof(jac, "jacobian"),
                 "solver": {"mean_iters": jac["mean_iters"], "max_iters": jac["max_iters"], "failed_pairs": jac["failed"]}}
         print(json.dumps(line), flush=True)

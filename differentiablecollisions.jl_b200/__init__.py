@@ -11,7 +11,7 @@ from .primitives import (  # noqa: F401
 )
 from .shapes import ShapeTable  # noqa: F401
 from .api import (  # noqa: F401
-    Context, default_context, proximity, proximity_gradient, proximity_jacobian, MEM_HOST, MEM_DEVICE,
+    Context, Group, default_context, proximity, proximity_gradient, proximity_jacobian, MEM_HOST, MEM_DEVICE,
 )
 from . import flops_model  # noqa: F401
 from .sharding import shard, shard_bounds, gather_rows, bind_to_gpu_numa_node, bind_disjoint_cpus  # noqa: F401

@@ -56,6 +56,15 @@ SYMBOLS = {
     "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops_for": (C.c_double, [C.c_void_p, C.c_double]),
     "dcol_set_copy_only": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcol_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),
+    "dcol_group_destroy": (None, [C.c_void_p]),
+    "dcol_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "dcol_group_size": (C.c_int, [C.c_void_p]),
+    "dcol_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "dcol_group_set_shapes": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "dcol_group_query": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_group_last_kernel_ms": (C.c_double, [C.c_void_p]),
 }
 
 _lib = None

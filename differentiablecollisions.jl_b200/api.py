@@ -338,6 +338,102 @@ class Context:
         return self._batch(2, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 
 
+class Group:
+    """Several GPUs from one process (`dcol_group`): one context per listed device, every batched query cut into contiguous
+    index slices that run concurrently, one per member.  Same batch methods and result layout as `Context`; results are
+    bit-identical to the single-context call.  Host arrays only."""
+
+    def __init__(self, devices):
+        self._lib = _capi.load()
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        rc = self._lib.dcol_group_create(C.byref(h), _ptr(devs), len(devs))
+        if rc != 0:
+            raise RuntimeError(self._lib.dcol_group_last_error(None).decode())
+        self._h = h
+        self.devices = [int(d) for d in devs]
+        self.table = ShapeTable()
+        self._table_version = -1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dcol_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.dcol_group_size(self._h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"dcol error {rc}: {self._lib.dcol_group_last_error(self._h).decode()}")
+
+    def add_shape(self, prim) -> int:
+        if self._table_version is None:
+            self._table_version = -1
+        return self.table.add(prim)
+
+    def set_shape_arrays(self, types, offs, params):
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(self._lib.dcol_group_set_shapes(self._h, len(types), _ptr(types), _ptr(offs), _ptr(params), params.shape[0]))
+        self._table_version = None
+
+    def sync_shapes(self):
+        if self._table_version != self.table.version:
+            t, o, p = self.table.arrays()
+            self._check(self._lib.dcol_group_set_shapes(self._h, len(t), _ptr(t), _ptr(o), _ptr(p), p.shape[0]))
+            self._table_version = self.table.version
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.dcol_group_last_kernel_ms(self._h))
+
+    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        if self._table_version is not None:
+            self.sync_shapes()
+        shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
+        shape2 = np.ascontiguousarray(shape2, dtype=np.int32).reshape(-1)
+        n = shape1.shape[0]
+        if shape2.shape[0] != n:
+            raise ValueError("shape1 and shape2 must have the same length")
+        na = 4 if att_kind == ATT_QUAT else 3
+        nt = 6 + 2 * na
+        r1 = np.ascontiguousarray(r1, dtype=np.float64).reshape(n, 3)
+        r2 = np.ascontiguousarray(r2, dtype=np.float64).reshape(n, 3)
+        att1 = np.ascontiguousarray(att1, dtype=np.float64).reshape(n, na)
+        att2 = np.ascontiguousarray(att2, dtype=np.float64).reshape(n, na)
+        alpha = np.empty(n)
+        x = np.empty((n, 3)) if kind != 1 else None
+        deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
+        status = np.empty(n, dtype=np.int32)
+        iters = np.empty(n, dtype=np.int32)
+        self._check(self._lib.dcol_group_query(self._h, int(kind), n, _ptr(shape1), _ptr(shape2), _ptr(r1), _ptr(att1), _ptr(r2), _ptr(att2),
+                                               int(att_kind), float(pdip_tol), _ptr(alpha), _ptr(x), _ptr(deriv), _ptr(status), _ptr(iters)))
+        out = {"alpha": alpha, "status": status, "iters": iters}
+        if x is not None:
+            out["x"] = x
+        if kind == 1:
+            out["grad"] = deriv
+        elif kind == 2:
+            out["J"] = deriv.transpose(0, 2, 1)
+        return out
+
+    def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+
+    def proximity_gradient_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        return self._batch(1, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+
+    def proximity_jacobian_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        return self._batch(2, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol)
+
+
 _default_ctx = None
 
 

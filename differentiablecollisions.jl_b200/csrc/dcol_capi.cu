@@ -187,6 +187,7 @@ struct dcol_ctx {
   // pinned staging + copy threads of large calls on pageable caller memory (created on first use)
   char* h_pin = nullptr; size_t h_pin_cap = 0;
   HostCopier* copier = nullptr;
+  int copy_threads = 0;                 // 0: min(8, cores / 2); groups divide that between their members
   int host_pipe = -1;                   // -1: not probed yet (DCOL_HOST_PIPE=0 disables, DCOL_HOST_THREADS sets the thread count)
   cudaStream_t s_copy = nullptr, s_out = nullptr, s_comp = nullptr;
   int n_sm = 148;
@@ -1215,6 +1216,15 @@ double dcol_measure_fp64_tflops(dcol_ctx* ctx) { return dcol_measure_fp64_tflops
 // query driver
 // ---------------------------------------------------------------------------
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+static HostCopier* host_copier(dcol_ctx* ctx) {     // copy threads, created on first use
+  if (!ctx->copier) {
+    int nth = ctx->copy_threads > 0 ? ctx->copy_threads : (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+    if (const char* e = getenv("DCOL_HOST_THREADS")) nth = std::max(1, std::min(64, atoi(e)));
+    ctx->copier = new HostCopier();
+    ctx->copier->start(nth - 1);                    // the calling thread copies too
+  }
+  return ctx->copier;
+}
 
 // pose1/pose2 == NULL: r*/att* have one row per pair.  Otherwise they are tables of np1 / np2 rows and pair k uses
 // rows pose1[k] / pose2[k].  in_mem: where the INPUT arrays live (lets the scene operator feed device-generated
@@ -1258,6 +1268,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   // behind the D2H copy, overlapping the GPU work of the neighbouring chunks.  Page-locked arrays (cudaHostAlloc,
   // dcol_host_register) keep the direct path.
   constexpr size_t STAGE_MAX = 8u << 20;      // below this, one packed staging copy per direction (the small-call path further down)
+  constexpr size_t STAGE_THREADS_MIN = 1u << 20;   // ... filled by the copy threads from this size on
   bool pageable = false;
   {
     const size_t approx = (size_t)n * (8 + 8 * (6 + 2 * (size_t)na) + 8 + 24 + 8 * dsz + 8 + (ctx->mu_out ? 8 : 0));
@@ -1349,10 +1360,13 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       ctx->h_stage_cap = 2 * STAGE_MAX;
     }
     char* hs = ctx->h_stage;
-    memcpy(hs + o_s1, shape1, sizeof(int32_t) * n); memcpy(hs + o_s2, shape2, sizeof(int32_t) * n);
-    if (indexed) { memcpy(hs + o_p1, pose1, sizeof(int32_t) * n); memcpy(hs + o_p2, pose2, sizeof(int32_t) * n); }
-    memcpy(hs + o_r1, r1, sizeof(double) * 3 * rows1); memcpy(hs + o_a1, att1, sizeof(double) * na * rows1);
-    memcpy(hs + o_r2, r2, sizeof(double) * 3 * rows2); memcpy(hs + o_a2, att2, sizeof(double) * na * rows2);
+    std::vector<CopyJob> J;
+    HostCopier::add(J, hs + o_s1, shape1, sizeof(int32_t) * n); HostCopier::add(J, hs + o_s2, shape2, sizeof(int32_t) * n);
+    if (indexed) { HostCopier::add(J, hs + o_p1, pose1, sizeof(int32_t) * n); HostCopier::add(J, hs + o_p2, pose2, sizeof(int32_t) * n); }
+    HostCopier::add(J, hs + o_r1, r1, sizeof(double) * 3 * rows1); HostCopier::add(J, hs + o_a1, att1, sizeof(double) * na * rows1);
+    HostCopier::add(J, hs + o_r2, r2, sizeof(double) * 3 * rows2); HostCopier::add(J, hs + o_a2, att2, sizeof(double) * na * rows2);
+    if (b_in + b_out >= STAGE_THREADS_MIN && ctx->host_pipe) host_copier(ctx)->run(J);      // megabytes: the copy threads help
+    else for (const CopyJob& j : J) memcpy(j.dst, j.src, j.bytes);
   }
   // ---- pageable-memory pipeline: pinned staging for the whole call (inputs | results), copy threads on first use
   char* hp_in = nullptr; char* hp_out = nullptr;
@@ -1368,12 +1382,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (cudaHostAlloc((void**)&ctx->h_pin, cap, cudaHostAllocDefault) == cudaSuccess) ctx->h_pin_cap = cap;
       else { (void)cudaGetLastError(); ctx->h_pin = nullptr; pageable = false; }      // no pinned memory to spare: the driver's pageable path
     }
-    if (pageable && !ctx->copier) {
-      int nth = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
-      if (const char* e = getenv("DCOL_HOST_THREADS")) nth = std::max(1, std::min(64, atoi(e)));
-      ctx->copier = new HostCopier();
-      ctx->copier->start(nth - 1);                // the calling thread copies too
-    }
+    if (pageable) (void)host_copier(ctx);
     if (pageable) { hp_in = ctx->h_pin; hp_out = ctx->h_pin + align256(b_in); }
   }
   // host-side source / destination of the copies: the caller's arrays, or their image in the pinned staging area
@@ -1574,7 +1583,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       const int grid = small ? (int)std::min<int64_t>(TR.grid[jac], nc / TR.block + TR.n_bins + 1) : TR.grid[jac];
       CK(launch_persistent(jac, grid, TR.block, TR.smem, st, d_tab + t, d_counter + t));
       ctx->launches++;
-      for (int lv = 1; lv <= levels && spill_div > 0 && !small; lv++) {
+      static const bool skip_resume = getenv("DCOL_SKIP_RESUME") != nullptr;      // timing experiments only: stragglers stay unfinished
+      for (int lv = 1; lv <= levels && spill_div > 0 && !small && !skip_resume; lv++) {
         LaunchTable* prev = d_tab + (size_t)(lv - 1) * std::max(1, nt_tiers) + t;
         LaunchTable* cur = d_tab + (size_t)lv * std::max(1, nt_tiers) + t;
         k_build_tables2<<<1, TABLE_THREADS, 0, st>>>(prev, cur, d_ovc + (size_t)(lv & 1) * ov_doubles, lv < levels ? 1 : 0);
@@ -1604,7 +1614,10 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       if (pageable) {
         CK(cudaEventRecord(L.ev_out[c], SO));
         // results of earlier chunks that have landed meanwhile go to the caller's arrays now (never waits)
-        while (drained < c && cudaEventQuery(L.ev_out[drained]) == cudaSuccess) unstage(drained++);
+        while (drained < c) {
+          if (cudaEventQuery(L.ev_out[drained]) != cudaSuccess) { (void)cudaGetLastError(); break; }   // not ready is not an error (a real one is sticky and resurfaces at the join)
+          unstage(drained++);
+        }
       }
     }
   }
@@ -1623,12 +1636,15 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   const int rc = finish_query(ctx, slot);
   if (staged && rc == 0) {
     const char* ho = ctx->h_stage + STAGE_MAX;
-    memcpy(alpha, ho + o_alpha, sizeof(double) * n);
-    if (x) memcpy(x, ho + o_x, sizeof(double) * 3 * n);
-    if (dsz) memcpy(deriv, ho + o_der, sizeof(double) * dsz * n);
-    if (status) memcpy(status, ho + o_st, sizeof(int32_t) * n);
-    if (iters) memcpy(iters, ho + o_it, sizeof(int32_t) * n);
-    if (ctx->mu_out) memcpy(ctx->mu_out, ho + o_mu, sizeof(double) * n);
+    std::vector<CopyJob> J;
+    HostCopier::add(J, alpha, ho + o_alpha, sizeof(double) * n);
+    if (x) HostCopier::add(J, x, ho + o_x, sizeof(double) * 3 * n);
+    if (dsz) HostCopier::add(J, deriv, ho + o_der, sizeof(double) * dsz * n);
+    if (status) HostCopier::add(J, status, ho + o_st, sizeof(int32_t) * n);
+    if (iters) HostCopier::add(J, iters, ho + o_it, sizeof(int32_t) * n);
+    if (ctx->mu_out) HostCopier::add(J, ctx->mu_out, ho + o_mu, sizeof(double) * n);
+    if (b_in + b_out >= STAGE_THREADS_MIN && ctx->host_pipe) host_copier(ctx)->run(J);
+    else for (const CopyJob& j : J) memcpy(j.dst, j.src, j.bytes);
   }
   return rc;
 }
@@ -2020,6 +2036,94 @@ int dcol_wait(dcol_ctx* ctx, int ticket) {
     if (ctx->done_ticket[h] == ticket) { if (ctx->done_result[h]) ctx->err = ctx->done_err[h]; return ctx->done_result[h]; }
   ctx->err = "dcol_wait: unknown ticket (the outcomes of the last 16 submissions are kept)";
   return -1;
+}
+
+// ---- device groups: one context per listed device, contiguous index slices, one host thread per member and call
+struct dcol_group {
+  std::vector<dcol_ctx*> members;
+  std::string err;
+  double last_ms = -1.0;
+};
+thread_local std::string g_group_create_err;
+
+int dcol_group_create(dcol_group** out, const int* device_ids, int n_devices) {
+  if (!out) { g_group_create_err = "dcol_group_create: out is NULL"; return -1; }
+  *out = nullptr;
+  if (!device_ids || n_devices < 1 || n_devices > 64) { g_group_create_err = "dcol_group_create: need 1..64 device ids"; return -1; }
+  dcol_group* g = new dcol_group();
+  for (int i = 0; i < n_devices; i++) {
+    dcol_ctx* c = nullptr;
+    const int rc = dcol_create(&c, device_ids[i]);
+    if (rc) {
+      g_group_create_err = std::string("dcol_group_create: member ") + std::to_string(i) + ": " + dcol_last_error(nullptr);
+      dcol_group_destroy(g);
+      return rc;
+    }
+    // the members copy concurrently: share the host's copy threads between them
+    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    c->copy_threads = (int)std::max(2u, std::min(8u, hw / 2) / (unsigned)n_devices);
+    g->members.push_back(c);
+  }
+  *out = g;
+  return 0;
+}
+
+void dcol_group_destroy(dcol_group* g) {
+  if (!g) return;
+  for (dcol_ctx* c : g->members) dcol_destroy(c);
+  delete g;
+}
+
+const char* dcol_group_last_error(const dcol_group* g) { return g ? g->err.c_str() : g_group_create_err.c_str(); }
+int dcol_group_size(const dcol_group* g) { return g ? (int)g->members.size() : 0; }
+dcol_ctx* dcol_group_ctx(dcol_group* g, int member) { return (g && member >= 0 && member < (int)g->members.size()) ? g->members[member] : nullptr; }
+double dcol_group_last_kernel_ms(const dcol_group* g) { return g ? g->last_ms : -1.0; }
+
+int dcol_group_set_shapes(dcol_group* g, int n_shapes, const int32_t* type, const int64_t* param_off, const double* params, int64_t n_params) {
+  if (!g) return -1;
+  g->err.clear();
+  for (size_t i = 0; i < g->members.size(); i++) {
+    const int rc = dcol_set_shapes(g->members[i], n_shapes, type, param_off, params, n_params);
+    if (rc) { g->err = "member " + std::to_string(i) + ": " + dcol_last_error(g->members[i]); return rc; }
+  }
+  return 0;
+}
+
+int dcol_group_query(dcol_group* g, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                     const double* r1, const double* att1, const double* r2, const double* att2,
+                     int att_kind, double pdip_tol,
+                     double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  if (!g) return -1;
+  g->err.clear(); g->last_ms = -1.0;
+  if (query != Q_PROX && query != Q_GRAD && query != Q_JAC) { g->err = "dcol_group_query: query must be 0 (proximity), 1 (gradient) or 2 (jacobian)"; return -1; }
+  if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { g->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
+  if (n < 0) { g->err = "dcol: n out of range"; return -1; }
+  const int m = (int)g->members.size();
+  const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3, nt = 6 + 2 * na;
+  const int64_t dsz = (query == Q_GRAD) ? nt : (query == Q_JAC ? 4 * nt : 0);
+  std::vector<int> rc(m, 0);
+  auto slice = [&](int i) {
+    const int64_t base = n / m, rem = n % m;
+    const int64_t b = i * base + std::min<int64_t>(i, rem), e = b + base + (i < rem ? 1 : 0);
+    if (e == b) return;
+    // (argument checks, including NULL pointers, are run_query's: offsetting a NULL base is avoided here)
+    auto off = [](auto* p, int64_t k) { return p ? p + k : p; };
+    rc[i] = run_query(g->members[i], query, e - b, off(shape1, b), off(shape2, b), off(r1, 3 * b), off(att1, na * b), off(r2, 3 * b), off(att2, na * b),
+                      att_kind, pdip_tol, DCOL_MEM_HOST, off(alpha, b), off(x, 3 * b), off(deriv, dsz * b), off(status, b), off(iters, b));
+  };
+  if (m == 1 || n < 2) {
+    for (int i = 0; i < m; i++) slice(i);
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 1; i < m; i++) th.emplace_back(slice, i);
+    slice(0);
+    for (std::thread& t : th) t.join();
+  }
+  for (int i = 0; i < m; i++) {
+    g->last_ms = std::max(g->last_ms, g->members[i]->last_ms);
+    if (rc[i]) { g->err = "member " + std::to_string(i) + " (device " + std::to_string(g->members[i]->device) + "): " + g->members[i]->err; return rc[i]; }
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -237,6 +237,31 @@ double  dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds);
  * gives the copy-only bound of the end-to-end path */
 int     dcol_set_copy_only(dcol_ctx* ctx, int on);
 
+/* ---- device groups: one process, several GPUs ------------------------------------------------
+ * The reference's callers are single-process Julia programs; a group lets such a caller use every GPU of the box
+ * through one call.  A group owns one context per entry of device_ids (a device may appear more than once).  Pairs are
+ * independent, so dcol_group_query cuts the pair range into contiguous slices of equal size (sizes differ by at most
+ * one, member i takes the i-th slice), runs the same query on every member concurrently (one host thread per member)
+ * and returns when all are done.  No data-path collective: every member reads its slice of the caller's HOST arrays
+ * and writes its slice of the results; results are bit-identical to the single-context call.
+ * query: 0 proximity (deriv unused), 1 gradient (x unused), 2 jacobian.  All pointers are host memory.
+ * A group is NOT thread-safe.  dcol_group_ctx returns member i (for dcol_host_register, dcol_set_max_iters, ...);
+ * it stays owned by the group.  Errors: the first failing member's return value; dcol_group_last_error names it. */
+typedef struct dcol_group dcol_group;
+int  dcol_group_create(dcol_group** out, const int* device_ids, int n_devices);
+void dcol_group_destroy(dcol_group* g);
+const char* dcol_group_last_error(const dcol_group* g);
+int  dcol_group_size(const dcol_group* g);
+dcol_ctx* dcol_group_ctx(dcol_group* g, int member);
+int  dcol_group_set_shapes(dcol_group* g, int n_shapes, const int32_t* type, const int64_t* param_off,
+                           const double* params, int64_t n_params);
+int  dcol_group_query(dcol_group* g, int query, int64_t n, const int32_t* shape1, const int32_t* shape2,
+                      const double* r1, const double* att1, const double* r2, const double* att2,
+                      int att_kind, double pdip_tol,
+                      double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
+/* device time (ms) of the solver launches of the last dcol_group_query: the maximum over the members */
+double dcol_group_last_kernel_ms(const dcol_group* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ using StaticArrays
 
 const _lib = Ref{String}("")
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)
+const _grp = Ref{Ptr{Cvoid}}(C_NULL)      # device group (dcol_group_*), set when DCOL_B200_DEVICES lists more than one GPU
 
 const ATT_QUAT = Cint(0)
 const ATT_MRP = Cint(1)
@@ -194,6 +195,11 @@ _check(rc) = rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_last_er
 function set_shapes!(t::ShapeTable)
     _check(ccall((:dcol_set_shapes, _lib[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Float64}, Int64),
                  _ctx[], length(t.types), t.types, t.offs, t.params, length(t.params)))
+    if _grp[] != C_NULL
+        rc = ccall((:dcol_group_set_shapes, _lib[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Float64}, Int64),
+                   _grp[], length(t.types), t.types, t.offs, t.params, length(t.params))
+        rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_group_last_error, _lib[]), Cstring, (Ptr{Cvoid},), _grp[])))
+    end
     return nothing
 end
 
@@ -204,6 +210,16 @@ function __init__()
     rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_last_error, _lib[]), Cstring, (Ptr{Cvoid},), C_NULL)))
     _ctx[] = h[]
     atexit(() -> ccall((:dcol_destroy, _lib[]), Cvoid, (Ptr{Cvoid},), _ctx[]))
+    # DCOL_B200_DEVICES=0,1,2,...: the batched queries (proximity_batch, ...) are cut into one index slice per listed GPU
+    # and run concurrently from this process (dcol_group_query); single-pair calls and the operators stay on _ctx
+    devs = Cint[parse(Cint, d) for d in split(get(ENV, "DCOL_B200_DEVICES", ""), ','; keepempty = false)]
+    if length(devs) > 1
+        g = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:dcol_group_create, _lib[]), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), g, devs, length(devs))
+        rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_group_last_error, _lib[]), Cstring, (Ptr{Cvoid},), C_NULL)))
+        _grp[] = g[]
+        atexit(() -> ccall((:dcol_group_destroy, _lib[]), Cvoid, (Ptr{Cvoid},), _grp[]))
+    end
 end
 
 # ---------------------------------------------------------------------------------------------
@@ -223,6 +239,16 @@ function _query(sym::Symbol, shape1::Vector{Int32}, shape2::Vector{Int32}, r1, a
     nt = 6 + 2 * size(a1, 1)
     α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
     x = Matrix{Float64}(undef, 3, sym === :dcol_proximity_gradient ? 0 : n)
+    if _grp[] != C_NULL            # several GPUs: contiguous index slices, one per device, same results
+        q = sym === :dcol_proximity ? 0 : (sym === :dcol_proximity_gradient ? 1 : 2)
+        deriv = q == 0 ? Float64[] : (q == 1 ? Matrix{Float64}(undef, nt, n) : Array{Float64}(undef, 4, nt, n))
+        rc = ccall((:dcol_group_query, _lib[]), Cint,
+                   (Ptr{Cvoid}, Cint, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                   _grp[], q, n, shape1, shape2, r1, a1, r2, a2, kind, pdip_tol, α, q == 1 ? C_NULL : x, q == 0 ? C_NULL : deriv, status, iters)
+        rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_group_last_error, _lib[]), Cstring, (Ptr{Cvoid},), _grp[])))
+        return BatchResult(α, x, deriv, status, iters)
+    end
     if sym === :dcol_proximity
         deriv = Float64[]
         _check(ccall((:dcol_proximity, _lib[]), Cint,

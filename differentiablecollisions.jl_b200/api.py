@@ -394,7 +394,22 @@ class Group:
     def last_kernel_ms(self) -> float:
         return float(self._lib.dcol_group_last_kernel_ms(self._h))
 
-    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):
+    def pin(self, arr: np.ndarray) -> np.ndarray:
+        """Page-lock a numpy array in place for every device of the group (`dcol_host_register` on member 0; the
+        registration is portable across devices).  `unpin` before the array is freed."""
+        if not arr.flags["C_CONTIGUOUS"]:
+            raise ValueError("pin: array must be C-contiguous")
+        c0 = self._lib.dcol_group_ctx(self._h, 0)
+        if self._lib.dcol_host_register(c0, arr.ctypes.data, arr.nbytes) != 0:
+            raise RuntimeError(self._lib.dcol_last_error(c0).decode())
+        return arr
+
+    def unpin(self, arr: np.ndarray):
+        c0 = self._lib.dcol_group_ctx(self._h, 0)
+        if self._lib.dcol_host_unregister(c0, arr.ctypes.data) != 0:
+            raise RuntimeError(self._lib.dcol_last_error(c0).decode())
+
+    def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
         if self._table_version is not None:
             self.sync_shapes()
         shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
@@ -408,11 +423,18 @@ class Group:
         r2 = np.ascontiguousarray(r2, dtype=np.float64).reshape(n, 3)
         att1 = np.ascontiguousarray(att1, dtype=np.float64).reshape(n, na)
         att2 = np.ascontiguousarray(att2, dtype=np.float64).reshape(n, na)
-        alpha = np.empty(n)
-        x = np.empty((n, 3)) if kind != 1 else None
-        deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
-        status = np.empty(n, dtype=np.int32)
-        iters = np.empty(n, dtype=np.int32)
+        if out is not None:        # caller-owned (e.g. pinned) buffers, laid out as Context.alloc_outputs does
+            alpha, status, iters = out["alpha"], out["status"], out["iters"]
+            x, deriv = out.get("x"), out.get("deriv")
+            want = (n, nt) if kind == 1 else (n, nt, 4)
+            if alpha.shape != (n,) or (kind != 1 and x.shape != (n, 3)) or (kind != 0 and deriv.shape != want):
+                raise ValueError("out: buffers do not match this query")
+        else:
+            alpha = np.empty(n)
+            x = np.empty((n, 3)) if kind != 1 else None
+            deriv = np.empty((n, nt)) if kind == 1 else (np.empty((n, nt, 4)) if kind == 2 else None)
+            status = np.empty(n, dtype=np.int32)
+            iters = np.empty(n, dtype=np.int32)
         self._check(self._lib.dcol_group_query(self._h, int(kind), n, _ptr(shape1), _ptr(shape2), _ptr(r1), _ptr(att1), _ptr(r2), _ptr(att2),
                                                int(att_kind), float(pdip_tol), _ptr(alpha), _ptr(x), _ptr(deriv), _ptr(status), _ptr(iters)))
         out = {"alpha": alpha, "status": status, "iters": iters}

@@ -1226,6 +1226,69 @@ static HostCopier* host_copier(dcol_ctx* ctx) {     // copy threads, created on 
   return ctx->copier;
 }
 
+static bool host_unpinned(const void* q) {
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, q) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+  return pa.type == cudaMemoryTypeUnregistered;
+}
+static bool host_pipe_on(dcol_ctx* ctx) {
+  if (ctx->host_pipe < 0) { const char* e = getenv("DCOL_HOST_PIPE"); ctx->host_pipe = (e && atoi(e) == 0) ? 0 : 1; }
+  return ctx->host_pipe != 0;
+}
+
+// Results of an operator (device scratch) to the caller's HOST arrays, then join the stream.  items: {host destination,
+// device source, bytes}.  Page-locked destinations and small totals: plain asynchronous copies.  Pageable destinations
+// above 8 MB: the bytes travel in up to 8 slabs through the pinned staging area, and the copy threads move slab k to the
+// caller's arrays while slab k+1 is still crossing PCIe (the same pipeline run_query uses for its chunks).
+static int results_to_host(dcol_ctx* ctx, cudaStream_t S, const std::vector<CopyJob>& items) {
+  size_t total = 0; bool unpinned = false;
+  for (const CopyJob& it : items) { total += it.bytes; unpinned = unpinned || host_unpinned(it.dst); }
+  size_t lim_mb = 8192;
+  if (const char* e = getenv("DCOL_PIN_MAX_MB")) lim_mb = (size_t)std::max(0, atoi(e));
+  bool pipe = host_pipe_on(ctx) && unpinned && total > (8u << 20) && total <= (lim_mb << 20) && !ctx->copy_only;
+  if (pipe && ctx->h_pin_cap < total) {
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+    if (cudaHostAlloc((void**)&ctx->h_pin, total + total / 8, cudaHostAllocDefault) == cudaSuccess) ctx->h_pin_cap = total + total / 8;
+    else { (void)cudaGetLastError(); ctx->h_pin = nullptr; pipe = false; }
+  }
+  if (!pipe) {
+    for (const CopyJob& it : items) CK(cudaMemcpyAsync(it.dst, it.src, it.bytes, cudaMemcpyDeviceToHost, S));
+    CK(cudaStreamSynchronize(S));
+    return 0;
+  }
+  HostCopier* cp = host_copier(ctx);
+  dcol_ctx::Slot& L = ctx->slots[0];                    // operators run with every submission drained: slot 0's events are free
+  const size_t slab = std::max<size_t>(4u << 20, (total + dcol_ctx::MAX_CHUNKS - 1) / dcol_ctx::MAX_CHUNKS);
+  // cut the concatenated byte range [0, total) into slabs; a slab may span several items
+  struct Piece { char* host; const char* dev; size_t stage_off, bytes; int slab; };
+  std::vector<Piece> pieces;
+  size_t pos = 0;
+  for (const CopyJob& it : items)
+    for (size_t o = 0; o < it.bytes;) {
+      const size_t room = slab - (pos % slab), take = std::min(room, it.bytes - o);
+      pieces.push_back({it.dst + o, it.src + o, pos, take, (int)(pos / slab)});
+      o += take; pos += take;
+    }
+  const int n_slabs = (int)((total + slab - 1) / slab);
+  size_t ip = 0;
+  for (int k = 0; k < n_slabs; k++) {
+    for (; ip < pieces.size() && pieces[ip].slab == k; ip++)
+      CK(cudaMemcpyAsync(ctx->h_pin + pieces[ip].stage_off, pieces[ip].dev, pieces[ip].bytes, cudaMemcpyDeviceToHost, S));
+    CK(cudaEventRecord(L.ev_out[k], S));
+  }
+  std::vector<CopyJob> jobs;
+  ip = 0;
+  for (int k = 0; k < n_slabs; k++) {
+    CK(cudaEventSynchronize(L.ev_out[k]));
+    jobs.clear();
+    for (; ip < pieces.size() && pieces[ip].slab == k; ip++) HostCopier::add(jobs, pieces[ip].host, ctx->h_pin + pieces[ip].stage_off, pieces[ip].bytes);
+    cp->run(jobs);
+  }
+  CK(cudaStreamSynchronize(S));
+  return 0;
+}
+
 // pose1/pose2 == NULL: r*/att* have one row per pair.  Otherwise they are tables of np1 / np2 rows and pair k uses
 // rows pose1[k] / pose2[k].  in_mem: where the INPUT arrays live (lets the scene operator feed device-generated
 // pair lists while the outputs still go to host buffers).
@@ -1272,13 +1335,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
   bool pageable = false;
   {
     const size_t approx = (size_t)n * (8 + 8 * (6 + 2 * (size_t)na) + 8 + 24 + 8 * dsz + 8 + (ctx->mu_out ? 8 : 0));
-    if (ctx->host_pipe < 0) { const char* e = getenv("DCOL_HOST_PIPE"); ctx->host_pipe = (e && atoi(e) == 0) ? 0 : 1; }
-    if (ctx->host_pipe && !async && mem == DCOL_MEM_HOST && !ctx->copy_only && approx > STAGE_MAX) {
-      auto unpinned = [](const void* q) {
-        cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, q) != cudaSuccess) { (void)cudaGetLastError(); return true; }
-        return pa.type == cudaMemoryTypeUnregistered;
-      };
+    if (host_pipe_on(ctx) && !async && mem == DCOL_MEM_HOST && !ctx->copy_only && approx > STAGE_MAX) {
+      auto unpinned = host_unpinned;
       pageable = unpinned(alpha) || (deriv && unpinned(deriv)) || (x && unpinned(x));
       if (in_mem == DCOL_MEM_HOST) pageable = pageable || unpinned(r1) || unpinned(att2);   // (device-generated pair lists: results only)
     }
@@ -1811,12 +1869,13 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
       if (rc) return rc;
     }
     if (host) {
-      CK(cudaMemcpyAsync(alpha, q_alpha, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
-      if (x) CK(cudaMemcpyAsync(x, q_x, sizeof(double) * 3 * (size_t)np, cudaMemcpyDeviceToHost, S));
-      if (nd) CK(cudaMemcpyAsync(deriv, q_der, sizeof(double) * (size_t)nd * (size_t)np, cudaMemcpyDeviceToHost, S));
-      if (status) CK(cudaMemcpyAsync(status, q_st, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
-      if (iters) CK(cudaMemcpyAsync(iters, q_it, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
-      CK(cudaStreamSynchronize(S));
+      std::vector<CopyJob> items;
+      items.push_back({(char*)alpha, (const char*)q_alpha, sizeof(double) * (size_t)np});
+      if (x) items.push_back({(char*)x, (const char*)q_x, sizeof(double) * 3 * (size_t)np});
+      if (nd) items.push_back({(char*)deriv, (const char*)q_der, sizeof(double) * (size_t)nd * (size_t)np});
+      if (status) items.push_back({(char*)status, (const char*)q_st, sizeof(int32_t) * (size_t)np});
+      if (iters) items.push_back({(char*)iters, (const char*)q_it, sizeof(int32_t) * (size_t)np});
+      return results_to_host(ctx, S, items);
     }
     return 0;
   }
@@ -1899,10 +1958,12 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
   CK(cudaGetLastError());
   ctx->launches++;
   if (host) {
-    CK(cudaMemcpyAsync(wrench, d_out, sizeof(double) * 6 * n_bodies, cudaMemcpyDeviceToHost, S));
-    if (alpha) CK(cudaMemcpyAsync(alpha, d_alpha, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
-    if (status) CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
-    if (iters) CK(cudaMemcpyAsync(iters, d_iters, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+    std::vector<CopyJob> items;
+    items.push_back({(char*)wrench, (const char*)d_out, sizeof(double) * 6 * (size_t)n_bodies});
+    if (alpha) items.push_back({(char*)alpha, (const char*)d_alpha, sizeof(double) * (size_t)np});
+    if (status) items.push_back({(char*)status, (const char*)d_status, sizeof(int32_t) * (size_t)np});
+    if (iters) items.push_back({(char*)iters, (const char*)d_iters, sizeof(int32_t) * (size_t)np});
+    return results_to_host(ctx, S, items);
   }
   CK(cudaStreamSynchronize(S));
   return 0;
@@ -1963,9 +2024,11 @@ int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta,
   CK(cudaGetLastError());
   ctx->launches++;
   if (host) {
-    CK(cudaMemcpyAsync(c, d_c, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, S));
-    if (Jc) CK(cudaMemcpyAsync(Jc, d_J, sizeof(double) * 3 * (size_t)np, cudaMemcpyDeviceToHost, S));
-    if (status) CK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, S));
+    std::vector<CopyJob> items;
+    items.push_back({(char*)c, (const char*)d_c, sizeof(double) * (size_t)np});
+    if (Jc) items.push_back({(char*)Jc, (const char*)d_J, sizeof(double) * 3 * (size_t)np});
+    if (status) items.push_back({(char*)status, (const char*)d_status, sizeof(int32_t) * (size_t)np});
+    return results_to_host(ctx, S, items);
   }
   CK(cudaStreamSynchronize(S));
   return 0;

@@ -245,18 +245,53 @@ __device__ __forceinline__ void soc_gram(const double* sc, const double (&B)[D][
 
 // reference SOC line search (static_solver2.jl:12-26) in reciprocal form: returns m such that the
 // step to the cone boundary is 1/m (m <= 0: no bound).  i = 1/sqrt(J(y)), den = 1/(y0*i + 1).
+// DCOL_LS_QUAD (default): the same boundary step from the quadratic J(y + a dl) = 0 directly.  With nu = J(y) > 0,
+// zeta = y'J dl and a = J(dl):  rho0 = zeta/nu and |rho_v|^2 = rho0^2 - a/nu (the scaled point has J(rho) = J(dl)/nu),
+// so m = |rho_v| - rho0 = (sqrt(zeta^2 - a nu) - zeta)/nu: the identical number with the identical cancellation
+// structure, in 20 instructions instead of 26 and without the two reciprocals 1/(y0/sqrt(nu) + 1) per cone and iteration.
+// zeta^2 >= a nu for every y inside the cone (reversed Cauchy-Schwarz); |.| keeps a round-off negative out of the root.
+#ifndef DCOL_LS_QUAD
+#define DCOL_LS_QUAD 1
+#endif
+// DCOL_LS_SCALED (default): both line searches of a cone block on the NT-scaled point.  W maps the cone onto itself
+// and lambda = W z = W^-1 s, so  s + a ds in K  <=>  lambda + a W^-1 ds in K  and  z + a dz in K  <=>  lambda + a W dz in K:
+// the same two boundary steps from the scaled directions the passes hold anyway, with one base point whose
+// J(lambda) = sqrt(J(s) J(z)) is known from the scaling.  For the affine direction W^-1 ds = -v and W dz = v - lambda
+// share their discriminant (zeta_v^2 - J(v) J(lambda)), so the two searches cost one square root and, like the
+// orthant rows, one maximum:  max(m_s, m_z) = sq/nu + 1/2 + |zeta_v/nu - 1/2|; the unscaled affine dz is never formed.
+// The first-order term of rho needs no sum either: s'dz_a + z'ds_a = -s'z for every block by construction of dz_a.
+#ifndef DCOL_LS_SCALED
+#define DCOL_LS_SCALED 1
+#endif
 template <int D>
 __device__ __forceinline__ double soc_linesearch_m(const double (&y)[D], const double (&dl)[D], double i, double den) {
   double zeta = y[0] * dl[0];
 #pragma unroll
   for (int k = 1; k < D; k++) zeta -= y[k] * dl[k];
   const double i2 = i * i;
+#if DCOL_LS_QUAD
+  const double nu = den;                       // J(y), kept from pass A in place of 1/(y0 i + 1)
+  double a = dl[0] * dl[0];
+#pragma unroll
+  for (int k = 1; k < D; k++) a -= dl[k] * dl[k];
+  const double disc = fma(zeta, zeta, -a * nu);
+  return (fast_sqrt(fabs(disc)) - zeta) * i2;
+#else
   const double rho0 = zeta * i2;
   const double f = (zeta * i + dl[0]) * den * i2;
   double nr = 0.0;
 #pragma unroll
   for (int k = 1; k < D; k++) { double r = dl[k] * i - f * y[k]; nr += r * r; }
   return fast_sqrt(nr) - rho0;
+#endif
+}
+
+// zeta = y' J d and a = J(d) = d0^2 - |d_v|^2 of a direction d at the point y
+template <int D>
+__device__ __forceinline__ void soc_zeta_a(const double (&y)[D], const double (&d)[D], double& zeta, double& a) {
+  zeta = y[0] * d[0]; a = d[0] * d[0];
+#pragma unroll
+  for (int k = 1; k < D; k++) { zeta -= y[k] * d[k]; a -= d[k] * d[k]; }
 }
 
 // ---------------------------------------------------------------------------
@@ -341,7 +376,8 @@ struct Prim {
   double s[DD], z[DD];                 // SOC block iterates
   double wb[DD], bb;                   // NT scaling point wbar and 1/(1+wbar0):  Wbar^-1 = J Wbar J (rank-one form)
   double ie;                           // 1/eta
-  double irs, irz, dens, denz;         // 1/sqrt(J(s)), 1/sqrt(J(z)), 1/(s0*irs+1), 1/(z0*irz+1)  (line searches)
+  double irs, irz, dens, denz;         // 1/sqrt(J(s)), 1/sqrt(J(z)); line searches: dens = J(lambda), denz = 1/J(lambda)
+                                       // [DCOL_LS_SCALED=0: J(s), J(z);  DCOL_LS_QUAD=0 as well: 1/(s0*irs+1), 1/(z0*irz+1)]
   double lam[DD], rz[DD], v[DD], wc[DD];
 
   // out = Wbar^-1 t  with Wbar^-1 = [wb0, -wbv'; -wbv, I + bb wbv wbv']
@@ -481,7 +517,14 @@ struct Prim {
       const bool ok = (Js > 0.0) && (Jz > 0.0);
       // Nesterov-Todd scaling (NT_scaling_chol_2.jl:95-112)
       irs = fast_rsqrt(Js); irz = fast_rsqrt(Jz);
+#if DCOL_LS_SCALED
+      dens = (Js * irs) * (Jz * irz);          // J(lambda) = sqrt(J(s) J(z))
+      denz = irs * irz;                        // 1 / J(lambda)
+#elif DCOL_LS_QUAD
+      dens = Js; denz = Jz;
+#else
       dens = fast_rcp(s[0] * irs + 1.0); denz = fast_rcp(z[0] * irz + 1.0);
+#endif
       const double kk = 0.5 * fast_rsqrt(0.5 * (1.0 + dot * irs * irz));     // 1/(2 gamma)
       wb[0] = kk * (s[0] * irs + z[0] * irz);
 #pragma unroll
@@ -543,26 +586,42 @@ struct Prim {
       mh = dmax(mh, fabs(q - 0.5));
       const double pp = -t * dza;
       rs(F_P, row0 + i) = pp;
+#if DCOL_LS_SCALED
+      dot2 += pp;                               // (s'dza + z'dsa = -s'z exactly: no sum needed, see DCOL_LS_SCALED)
+#else
       dot1 += si * dza - zi * t; dot2 += pp;
+#endif
     });
   }
   __device__ __forceinline__ void passB_soc(const double (&dyh)[NV], double& m, double& dot1, double& dot2) {
     if constexpr (D > 0) {
-      double cd[D], t[D], dsa[D], dza[D], w[D];
+      double cd[D], t[D], w[D];
       soc_apply<CLS, NV, D>(sc, dyh, cd);
 #pragma unroll
-      for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; dsa[i] = -t[i]; }
-      // v = W^-1 t ; dza = W^-1 (v - lambda)  [= W^-2 t - z, subtraction done in the scaled space]
+      for (int i = 0; i < D; i++) t[i] = rz[i] - cd[i];
+      // v = W^-1 t = -W^-1 dsa ; w = v - lambda = W dza   [dza = W^-2 t - z, subtraction done in the scaled space]
       applyV(t, v);
 #pragma unroll
       for (int i = 0; i < D; i++) { v[i] *= ie; w[i] = v[i] - lam[i]; }
+#if DCOL_LS_SCALED
+      {
+        double zv, av;
+        soc_zeta_a<D>(lam, v, zv, av);
+        const double sq = fast_sqrt(fabs(fma(zv, zv, -av * dens)));
+        m = dmax(m, fma(sq, denz, 0.5) + fabs(fma(zv, denz, -0.5)));      // max(m_s, m_z), see DCOL_LS_SCALED
+#pragma unroll
+        for (int i = 0; i < D; i++) dot2 -= v[i] * w[i];                   // dsa'dza = -(W^-1 dsa)'(W dza)... = -v'w
+      }
+#else
+      double dsa[D], dza[D];
       applyV(w, dza);
 #pragma unroll
-      for (int i = 0; i < D; i++) dza[i] *= ie;
+      for (int i = 0; i < D; i++) { dsa[i] = -t[i]; dza[i] *= ie; }
       m = dmax(m, soc_linesearch_m<D>(s, dsa, irs, dens));
       m = dmax(m, soc_linesearch_m<D>(z, dza, irz, denz));
 #pragma unroll
       for (int i = 0; i < D; i++) { dot1 += s[i] * dza[i] + z[i] * dsa[i]; dot2 += dsa[i] * dza[i]; }
+#endif
       // -(W^-1 dsa) o (W dza) = v o (v - lambda)   (static_solver2.jl:164)
       double c0 = 0.0;
 #pragma unroll
@@ -634,6 +693,20 @@ struct Prim {
       for (int i = 0; i < D; i++) { t[i] = rz[i] - cd[i]; ds[i] = -t[i]; }
       // dz = W^-1 (W^-1 t - lambda + kappa)   (scaled-space accumulation, static_solver2.jl:165-168)
       applyV(t, v2);
+#if DCOL_LS_SCALED
+      {
+        double p[D], zp, ap, z2, a2;
+#pragma unroll
+        for (int i = 0; i < D; i++) { p[i] = ie * v2[i]; v2[i] = p[i] - lam[i] + wc[i]; }     // p = -W^-1 ds, v2 = W dz
+        soc_zeta_a<D>(lam, p, zp, ap);
+        soc_zeta_a<D>(lam, v2, z2, a2);
+        m = dmax(m, (fast_sqrt(fabs(fma(zp, zp, -ap * dens))) + zp) * denz);                 // direction -p
+        m = dmax(m, (fast_sqrt(fabs(fma(z2, z2, -a2 * dens))) - z2) * denz);
+      }
+      applyV(v2, dz);
+#pragma unroll
+      for (int i = 0; i < D; i++) dz[i] *= ie;
+#else
 #pragma unroll
       for (int i = 0; i < D; i++) v2[i] = ie * v2[i] - lam[i] + wc[i];
       applyV(v2, dz);
@@ -641,6 +714,7 @@ struct Prim {
       for (int i = 0; i < D; i++) dz[i] *= ie;
       m = dmax(m, soc_linesearch_m<D>(s, ds, irs, dens));
       m = dmax(m, soc_linesearch_m<D>(z, dz, irz, denz));
+#endif
 #pragma unroll
       for (int i = 0; i < D; i++) { rz[i] = ds[i]; v[i] = dz[i]; }
     }
@@ -1065,7 +1139,11 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
         A.passB_soc(y1, m, dot1, dot2);
         B.passB_soc(y2, m, dot1, dot2);
         const double aa = fast_rcp(dmax(1.0, dmax(mh + 0.5, m)));   // min(1, step to the boundary)  :159
+#if DCOL_LS_SCALED
+        const double rho = fma(aa * aa * dot2, fast_rcp(sz), 1.0 - aa);      // (s + a ds)'(z + a dz) / s'z with s'dz + z'ds = -s'z
+#else
         const double rho = (sz + aa * (dot1 + aa * dot2)) * fast_rcp(sz);
+#endif
         double sig = dmax(0.0, dmin(1.0, rho)); sig = sig * sig * sig;   // :161
         const double sigmu = sig * mu;
         {

@@ -263,6 +263,14 @@ __device__ __forceinline__ void soc_gram(const double* sc, const double (&B)[D][
 #ifndef DCOL_LS_SCALED
 #define DCOL_LS_SCALED 1
 #endif
+// DCOL_ETA_FREE (default, needs DCOL_LS_SCALED): the scaled quantities are kept multiplied by eta = (J(s)/J(z))^(1/4), so
+// that eta itself (a reciprocal square root behind two others in pass A's dependency chain) is never formed:
+//   lam~ = eta lambda = Wbar^-1 s,  v~ = eta W^-1 t = Wbar^-1 t,  J(lam~) = J(s),  kappa~ = lam~ \ (v~ o w~ + eta^2 sigma mu e),
+//   W^-1 kappa = eta^-2 Wbar^-1 kappa~,  dz = eta^-2 Wbar^-1 (p~ - lam~ + kappa~);  the line searches are ratios, unchanged.
+// Only eta^2 = sqrt(J(s)/J(z)) and eta^-2 enter, both products of numbers pass A has anyway.
+#ifndef DCOL_ETA_FREE
+#define DCOL_ETA_FREE DCOL_LS_SCALED
+#endif
 template <int D>
 __device__ __forceinline__ double soc_linesearch_m(const double (&y)[D], const double (&dl)[D], double i, double den) {
   double zeta = y[0] * dl[0];
@@ -375,7 +383,8 @@ struct Prim {
   double sc[9];
   double s[DD], z[DD];                 // SOC block iterates
   double wb[DD], bb;                   // NT scaling point wbar and 1/(1+wbar0):  Wbar^-1 = J Wbar J (rank-one form)
-  double ie;                           // 1/eta
+  double ie;                           // 1/eta  (DCOL_ETA_FREE: 1/eta^2)
+  double eta2;                         // DCOL_ETA_FREE: eta^2
   double irs, irz, dens, denz;         // 1/sqrt(J(s)), 1/sqrt(J(z)); line searches: dens = J(lambda), denz = 1/J(lambda)
                                        // [DCOL_LS_SCALED=0: J(s), J(z);  DCOL_LS_QUAD=0 as well: 1/(s0*irs+1), 1/(z0*irz+1)]
   double lam[DD], rz[DD], v[DD], wc[DD];
@@ -517,7 +526,9 @@ struct Prim {
       const bool ok = (Js > 0.0) && (Jz > 0.0);
       // Nesterov-Todd scaling (NT_scaling_chol_2.jl:95-112)
       irs = fast_rsqrt(Js); irz = fast_rsqrt(Jz);
-#if DCOL_LS_SCALED
+#if DCOL_ETA_FREE
+      // (set with the scaling below)
+#elif DCOL_LS_SCALED
       dens = (Js * irs) * (Jz * irz);          // J(lambda) = sqrt(J(s) J(z))
       denz = irs * irz;                        // 1 / J(lambda)
 #elif DCOL_LS_QUAD
@@ -531,9 +542,15 @@ struct Prim {
       for (int i = 1; i < D; i++) wb[i] = kk * (s[i] * irs - z[i] * irz);
       bb = fast_rcp(wb[0] + 1.0);
       const double x = irs * (Jz * irz);          // sqrt(J(z)/J(s)) = 1/eta^2
+      const double ie2 = x;
+#if DCOL_ETA_FREE
+      ie = x;                                     // eta^-2
+      eta2 = (Js * irs) * irz;                    // eta^2
+      dens = Js; denz = irs * irs;                // J(lam~) and its reciprocal
+      applyV(s, lam);                             // lam~ = eta lambda = Wbar^-1 s
+#else
       const double eta = fast_rsqrt(x);           // (J(s)/J(z))^(1/4)
       ie = x * eta;
-      const double ie2 = x;
       // lambda = W z = eta * Wbar z
       double wz = 0.0;
 #pragma unroll
@@ -542,6 +559,7 @@ struct Prim {
       const double fz = z[0] + bb * wz;
 #pragma unroll
       for (int i = 1; i < D; i++) lam[i] = eta * (z[i] + wb[i] * fz);
+#endif
       // Vsq = V'V with V = Wbar^-1, expanded entrywise (a Gram product: PSD to round-off, no use of
       // the identity wb0^2 - |wbv|^2 = 1, which loses accuracy as the iterates approach the boundary)
       double nw = 0.0;
@@ -601,16 +619,27 @@ struct Prim {
       for (int i = 0; i < D; i++) t[i] = rz[i] - cd[i];
       // v = W^-1 t = -W^-1 dsa ; w = v - lambda = W dza   [dza = W^-2 t - z, subtraction done in the scaled space]
       applyV(t, v);
+#if DCOL_ETA_FREE
+#pragma unroll
+      for (int i = 0; i < D; i++) w[i] = v[i] - lam[i];                    // v~, w~ (both carry a factor eta)
+#else
 #pragma unroll
       for (int i = 0; i < D; i++) { v[i] *= ie; w[i] = v[i] - lam[i]; }
+#endif
 #if DCOL_LS_SCALED
       {
         double zv, av;
         soc_zeta_a<D>(lam, v, zv, av);
         const double sq = fast_sqrt(fabs(fma(zv, zv, -av * dens)));
         m = dmax(m, fma(sq, denz, 0.5) + fabs(fma(zv, denz, -0.5)));      // max(m_s, m_z), see DCOL_LS_SCALED
+        double vw = 0.0;                                                   // dsa'dza = -(W^-1 dsa)'(W dza) = -v'w
 #pragma unroll
-        for (int i = 0; i < D; i++) dot2 -= v[i] * w[i];                   // dsa'dza = -(W^-1 dsa)'(W dza)... = -v'w
+        for (int i = 0; i < D; i++) vw += v[i] * w[i];
+#if DCOL_ETA_FREE
+        dot2 -= ie * vw;
+#else
+        dot2 -= vw;
+#endif
       }
 #else
       double dsa[D], dza[D];
@@ -647,7 +676,11 @@ struct Prim {
   }
   __device__ __forceinline__ void passC_soc(double sigmu, double (&g2)[NV]) {
     if constexpr (D > 0) {
+#if DCOL_ETA_FREE
+      wc[0] += eta2 * sigmu;
+#else
       wc[0] += sigmu;
+#endif
       double kap[D], wk[D];
       soc_jdiv_fast(lam, wc, kap);              // kappa = lambda \ corr  (soc_utils.jl:52-67)
       applyV(kap, wk);
@@ -657,11 +690,20 @@ struct Prim {
     }
   }
   __device__ __forceinline__ void soc_jdiv_fast(const double (&l)[DD], const double (&w)[DD], double (&out)[DD]) const {
+#if DCOL_LS_SCALED
+    // J(lambda) = sqrt(J(s) J(z)) and its reciprocal are known from the scaling (denz), no sum and no reciprocal here
+    double nu = 0.0;
+#pragma unroll
+    for (int i = 1; i < D; i++) nu += l[i] * w[i];
+    const double il0 = fast_rcp(l[0]);
+    const double irho = denz;
+#else
     double rho = l[0] * l[0], nu = 0.0;
 #pragma unroll
     for (int i = 1; i < D; i++) { rho -= l[i] * l[i]; nu += l[i] * w[i]; }
     const double il0 = fast_rcp(l[0]);
     const double irho = fast_rcp(rho);
+#endif
     out[0] = irho * (l[0] * w[0] - nu);
     const double f1 = irho * (nu * il0 - w[0]);
 #pragma unroll
@@ -697,7 +739,11 @@ struct Prim {
       {
         double p[D], zp, ap, z2, a2;
 #pragma unroll
+#if DCOL_ETA_FREE
+        for (int i = 0; i < D; i++) { p[i] = v2[i]; v2[i] = p[i] - lam[i] + wc[i]; }          // p~ = -eta W^-1 ds, v2~ = eta W dz
+#else
         for (int i = 0; i < D; i++) { p[i] = ie * v2[i]; v2[i] = p[i] - lam[i] + wc[i]; }     // p = -W^-1 ds, v2 = W dz
+#endif
         soc_zeta_a<D>(lam, p, zp, ap);
         soc_zeta_a<D>(lam, v2, z2, a2);
         m = dmax(m, (fast_sqrt(fabs(fma(zp, zp, -ap * dens))) + zp) * denz);                 // direction -p

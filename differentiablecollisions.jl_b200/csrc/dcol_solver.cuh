@@ -877,6 +877,19 @@ struct Prim {
 // pair-level assembly in primitive-1's body frame.  Pair variables
 // y = [xi(3), alpha, e1(NE1), e2(NE2)]  (column order of combine_problem_matrices.jl:57-84).
 // ---------------------------------------------------------------------------
+// DCOL_SPHERE_FRAME (default): a sphere has no orientation the solve could see (||x - r~|| <= R alpha), so in a pair with
+// a sphere the sphere's frame is taken equal to the OTHER primitive's for the duration of the interior-point loop: the
+// relative rotation is the identity (tag IdentityR: no rotation of Gram blocks, right-hand sides or local vectors), and
+// the iterates are a rotation of the ones in the sphere's own body frame (a rotation of a ball block's vector part is a
+// cone automorphism: same mu, alpha, x, iteration counts).  The derivative epilogues, which look at the sphere's true
+// frame (its offset r_offset turns with it), get the iterate converted back at the loop exit (solve_pair).
+#ifndef DCOL_SPHERE_FRAME
+#define DCOL_SPHERE_FRAME 1
+#endif
+struct IdentityR { __device__ IdentityR() {} template <class T> __device__ explicit IdentityR(const T&) {} };
+template <class RM> struct is_identity_r : std::false_type {};
+template <> struct is_identity_r<IdentityR> : std::true_type {};
+
 template <int NE1, int NE2>
 struct PairMap {
   static constexpr int NX = 4 + NE1 + NE2, NV1 = 4 + NE1, NV2 = 4 + NE2;
@@ -889,8 +902,13 @@ struct PairMap {
                                                   double (&y1)[NV1], double (&y2)[NV2]) {
 #pragma unroll
     for (int a = 0; a < NV1; a++) y1[a] = y[a];
+    if constexpr (is_identity_r<RM>::value) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) y2[a] = R[a][0] * y[0] + R[a][1] * y[1] + R[a][2] * y[2] + (with_t ? t[a] : 0.0);
+      for (int a = 0; a < 3; a++) y2[a] = with_t ? y[a] + t[a] : y[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++) y2[a] = R[a][0] * y[0] + R[a][1] * y[1] + R[a][2] * y[2] + (with_t ? t[a] : 0.0);
+    }
     y2[3] = y[3];
 #pragma unroll
     for (int a = 4; a < NV2; a++) y2[a] = y[g2(a)];
@@ -903,6 +921,19 @@ struct PairMap {
     for (int a = 0; a < NX; a++)
 #pragma unroll
       for (int b = a; b < NX; b++) M[a][b] = (a < NV1 && b < NV1) ? N1[a][b] : 0.0;
+    if constexpr (is_identity_r<RM>::value) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = a; b < 3; b++) M[a][b] += N2[a][b];
+#pragma unroll
+        for (int l = 3; l < NV2; l++) M[a][g2(l)] += N2[a][l];
+      }
+#pragma unroll
+      for (int l = 3; l < NV2; l++)
+#pragma unroll
+        for (int m = l; m < NV2; m++) M[g2(l)][g2(m)] += N2[l][m];
+    } else {
     double tmp[3][3];
 #pragma unroll
     for (int c = 0; c < 3; c++)
@@ -924,13 +955,19 @@ struct PairMap {
     for (int l = 3; l < NV2; l++)
 #pragma unroll
       for (int m = l; m < NV2; m++) M[g2(l)][g2(m)] += N2[l][m];
+    }
   }
   template <class RM>
   __device__ static __forceinline__ void assemble_vec(const double (&g1)[NV1], const double (&g2v)[NV2], const RM& R, double (&b)[NX]) {
 #pragma unroll
     for (int a = 0; a < NX; a++) b[a] = (a < NV1) ? g1[a] : 0.0;
+    if constexpr (is_identity_r<RM>::value) {
 #pragma unroll
-    for (int a = 0; a < 3; a++) b[a] += R[0][a] * g2v[0] + R[1][a] * g2v[1] + R[2][a] * g2v[2];
+      for (int a = 0; a < 3; a++) b[a] += g2v[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++) b[a] += R[0][a] * g2v[0] + R[1][a] * g2v[1] + R[2][a] * g2v[2];
+    }
 #pragma unroll
     for (int l = 3; l < NV2; l++) b[g2(l)] += g2v[l];
   }
@@ -956,6 +993,9 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   using P1 = Prim<C1>; using P2 = Prim<C2>;
   using PM = PairMap<P1::NE, P2::NE>;
   constexpr int NX = PM::NX, NV1 = PM::NV1, NV2 = PM::NV2;
+  // sphere frames (see IdentityR): SPH2 = primitive 2 is a sphere; SPH1 = primitive 1 is and primitive 2 is not
+  constexpr bool SPH2 = DCOL_SPHERE_FRAME && (C2 == CLS_SPHERE);
+  constexpr bool SPH1 = DCOL_SPHERE_FRAME && (C1 == CLS_SPHERE) && !SPH2;
 
   // first pass: idx is a position of the sorted, packed pair list; resume pass: idx is a slot of the bin's overflow
   // list, whose first field is the pair's sorted position.
@@ -997,19 +1037,25 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     build_frame(S1, pose, pose + 3, p.att_kind, F1);
     build_frame(S2, pose + 7, pose + 10, p.att_kind, F2);
     double dr[3] = {F1.r[0] - F2.r[0], F1.r[1] - F2.r[1], F1.r[2] - F2.r[2]};
+    // loop frames (DCOL_SPHERE_FRAME): sphere as primitive 2 -> its frame := primitive 1's (t in primitive 1's frame);
+    // sphere as primitive 1 only -> the pair frame := primitive 2's (t as always, x = r~1 + Q2 xi)
+    const double (&Qt)[3][3] = SPH2 ? F1.Q : F2.Q;          // frame the offset t is expressed in
+    const double (&Qx)[3][3] = SPH1 ? F2.Q : F1.Q;          // frame of the pair variable xi
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      t[a] = F2.Q[0][a] * dr[0] + F2.Q[1][a] * dr[1] + F2.Q[2][a] * dr[2];
+      t[a] = Qt[0][a] * dr[0] + Qt[1][a] * dr[1] + Qt[2][a] * dr[2];
 #pragma unroll
       for (int b = 0; b < 3; b++) R[a][b] = F2.Q[0][a] * F1.Q[0][b] + F2.Q[1][a] * F1.Q[1][b] + F2.Q[2][a] * F1.Q[2][b];
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) { rs.base[9 + a] = t[a]; rs.base[21 + a] = F1.r[a];
 #pragma unroll
-      for (int b = 0; b < 3; b++) { rs.base[3 * a + b] = R[a][b]; rs.base[12 + 3 * a + b] = F1.Q[a][b]; } }
+      for (int b = 0; b < 3; b++) { rs.base[3 * a + b] = R[a][b]; rs.base[12 + 3 * a + b] = Qx[a][b]; } }
   }
-  const RelPoseR R{rs.base};
+  const RelPoseR Rtrue{rs.base};                 // the true relative rotation Q2'Q1 (derivative epilogues)
   const RelPoseT t{rs.base};
+  using RLoop = std::conditional_t<SPH1 || SPH2, IdentityR, RelPoseR>;
+  const RLoop R{Rtrue};                          // the rotation the loop sees
 
   double y[NX];
   double M[NX][NX], idg[NX];
@@ -1235,15 +1281,46 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
   if (p.iters) p.iters[oi] = it;
   if (p.mu) p.mu[oi] = sz * inv_deg;
   const int nt = 6 + 2 * na;
+  if constexpr (VAR != Q_PROX && (SPH1 || SPH2)) {
+    // The loop ran with the sphere's frame set equal to its partner's (IdentityR).  The derivative epilogues work with
+    // the true frames, the true relative pose and body coordinates: convert the iterate (rotations of the pair point
+    // and of the sphere's ball block by R = Q2'Q1; nothing else depends on the sphere's orientation).
+    auto rot = [&](double (&v)[4], bool transpose) {
+      const double a0 = v[1], a1 = v[2], a2 = v[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        v[1 + i] = transpose ? (Rtrue[0][i] * a0 + Rtrue[1][i] * a1 + Rtrue[2][i] * a2) : (Rtrue[i][0] * a0 + Rtrue[i][1] * a1 + Rtrue[i][2] * a2);
+    };
+    if constexpr (SPH2) {
+      rot(B.s, false); rot(B.z, false);                                   // frame 1 -> the sphere's body frame
+      const double t0 = t[0], t1 = t[1], t2 = t[2];                         // t was Q1'(r~1 - r~2); the epilogues want Q2'(r~1 - r~2) = R t
+#pragma unroll
+      for (int i = 0; i < 3; i++) rs.base[9 + i] = Rtrue[i][0] * t0 + Rtrue[i][1] * t1 + Rtrue[i][2] * t2;
+    } else {
+      rot(A.s, true); rot(A.z, true);                                     // frame 2 -> the sphere's body frame
+      const double y0 = y[0], y1 = y[1], y2 = y[2];                         // xi: frame 2 -> frame 1 (R')
+#pragma unroll
+      for (int i = 0; i < 3; i++) y[i] = Rtrue[0][i] * y0 + Rtrue[1][i] * y1 + Rtrue[2][i] * y2;
+      double Q1[3][3];                                                      // slots 12..20 held Q2; Q1 = Q2 R
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Q1[i][j] = F1.Q[i][0] * Rtrue[0][j] + F1.Q[i][1] * Rtrue[1][j] + F1.Q[i][2] * Rtrue[2][j];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) F1.Q[i][j] = Q1[i][j];
+    }
+  }
 
   if constexpr (VAR == Q_GRAD) {
     // ---- proximity_gradient (src/proximity_gradient.jl:41-78): -z' du/dtheta
     {
       double* g = p.deriv + (int64_t)nt * pair;
       if (status == ST_OK) {
-        frame2_from_relative(F1, R, t, F2);
+        frame2_from_relative(F1, Rtrue, t, F2);
         double y1[NV1], y2[NV2];
-        PM::to_local(y, R, t, true, y1, y2);
+        PM::to_local(y, Rtrue, t, true, y1, y2);
         SideVecs V1, V2;
         A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
         grad_side(S1, F1, rec->a1, p.att_kind, V1, g + (swp ? 3 + na : 0));
@@ -1258,12 +1335,12 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
     double* Jo = p.deriv + (int64_t)4 * nt * pair;
     bool ok = (status == ST_OK);
     if (ok) {
-      frame2_from_relative(F1, R, t, F2);
+      frame2_from_relative(F1, Rtrue, t, F2);
       double K1[4][3], K2[4][3], Kb1[4][3], Kb2[4][3], Ye1[4][2], Ye2[4][2], Hw[4][3];
       SideVecs V1, V2;
       {
         double y1[NV1], y2[NV2];
-        PM::to_local(y, R, t, true, y1, y2);
+        PM::to_local(y, Rtrue, t, true, y1, y2);
         A.side_vecs(rs, y1, V1); B.side_vecs(rs, y2, V2);
       }
       {
@@ -1275,7 +1352,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
           double e[NX], y1[NV1], y2[NV2], n1[NV1], n2[NV2], col[NX];
 #pragma unroll
           for (int a = 0; a < NX; a++) e[a] = (a == b) ? 1.0 : 0.0;
-          PM::to_local(e, R, t, false, y1, y2);
+          PM::to_local(e, Rtrue, t, false, y1, y2);
 #pragma unroll
           for (int a = 0; a < NV1; a++) { double acc = 0.0;
 #pragma unroll
@@ -1286,7 +1363,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
 #pragma unroll
             for (int c = 0; c < NV2; c++) acc += N2[a][c] * y2[c];
             n2[a] = acc; }
-          PM::assemble_vec(n1, n2, R, col);
+          PM::assemble_vec(n1, n2, Rtrue, col);
 #pragma unroll
           for (int a = 0; a < NX; a++) Mt[b][a] = col[a];
         }
@@ -1302,7 +1379,7 @@ __device__ __forceinline__ void solve_pair(const QueryParams& p, const TileCtx& 
           double yc[NX], y1[NV1], y2[NV2];
 #pragma unroll
           for (int a = 0; a < NX; a++) yc[a] = Y[a][i];
-          PM::to_local(yc, R, t, false, y1, y2);
+          PM::to_local(yc, Rtrue, t, false, y1, y2);
 #pragma unroll
           for (int c = 0; c < 3; c++) {
             double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;

@@ -13,5 +13,6 @@ from .shapes import ShapeTable  # noqa: F401
 from .api import (  # noqa: F401
     Context, Group, default_context, proximity, proximity_gradient, proximity_jacobian, MEM_HOST, MEM_DEVICE,
 )
+from .problem_matrices import problem_matrices, combine_problem_matrices, pair_problem  # noqa: F401
 from . import flops_model  # noqa: F401
 from .sharding import shard, shard_bounds, gather_rows, bind_to_gpu_numa_node, bind_disjoint_cpus  # noqa: F401

@@ -18,6 +18,8 @@ lp = C.POINTER(C.c_int64)
 _Q_ARGS = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
            C.c_int, C.c_double, C.c_int]
 
+TRACE_ROWS, TRACE_COLS = 50, 5     # DCOL_TRACE_ROWS / DCOL_TRACE_COLS of include/dcol_b200.h
+
 # name -> (restype, argtypes); this is the complete list of symbols include/dcol_b200.h declares
 SYMBOLS = {
     "dcol_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -47,6 +49,8 @@ SYMBOLS = {
     "dcol_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcol_solve_socp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_solve_socp_trace": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_warm_stride": (C.c_int64, [C.c_void_p]),
     "dcol_set_warm_start": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
     "dcol_set_mu_output": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -56,6 +60,7 @@ SYMBOLS = {
     "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops_for": (C.c_double, [C.c_void_p, C.c_double]),
     "dcol_set_copy_only": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcol_host_copy_selftest": (C.c_int, [C.c_int, C.c_int64, C.c_int]),
     "dcol_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),
     "dcol_group_destroy": (None, [C.c_void_p]),
     "dcol_group_last_error": (C.c_char_p, [C.c_void_p]),

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _capi
 from .primitives import ATT_MRP, ATT_QUAT, AbstractPrimitive
+from .problem_matrices import format_trace, pair_problem
 from .shapes import ShapeTable
 
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -158,9 +159,11 @@ class Context:
         return out
 
     # ---- batched host API ----------------------------------------------------------------------
-    def solve_socp(self, c, G, h, n_ort, d1, d2, pdip_tol=1e-4):
+    def solve_socp(self, c, G, h, n_ort, d1, d2, pdip_tol=1e-4, verbose=False, trace=False):
         """`dcol_solve_socp`: the reference's solve_socp (static_solver2.jl:106-191; default pdip_tol 1e-4 as there, :112) on
-        one problem (G: ns x nx) or a batch (G: n x ns x nx).  Returns (x, s, z, status, iters)."""
+        one problem (G: ns x nx) or a batch (G: n x ns x nx).  Returns (x, s, z, status, iters); with `trace=True` also the
+        per-iteration record of `dcol_solve_socp_trace` (n x 50 x 5, NaN past a problem's last iteration).  `verbose=True`
+        prints the reference's iteration table (:117-120, :179-183) for every problem of the call."""
         G = np.ascontiguousarray(G, dtype=np.float64)
         single = G.ndim == 2
         if single:
@@ -170,11 +173,19 @@ class Context:
         h = np.ascontiguousarray(np.broadcast_to(np.asarray(h, dtype=np.float64).reshape(-1, ns), (n, ns)))
         x = np.empty((n, nx)); s = np.empty((n, ns)); z = np.empty((n, ns))
         status = np.empty(n, dtype=np.int32); iters = np.empty(n, dtype=np.int32)
-        self._check(self._lib.dcol_solve_socp(self._h, n, nx, int(n_ort), int(d1), int(d2), _ptr(c), _ptr(G), _ptr(h), float(pdip_tol),
-                                              MEM_HOST, _ptr(x), _ptr(s), _ptr(z), _ptr(status), _ptr(iters)))
+        if verbose or trace:
+            tr = np.full((n, _capi.TRACE_ROWS, _capi.TRACE_COLS), np.nan)
+            self._check(self._lib.dcol_solve_socp_trace(self._h, n, nx, int(n_ort), int(d1), int(d2), _ptr(c), _ptr(G), _ptr(h),
+                                                        float(pdip_tol), MEM_HOST, _ptr(x), _ptr(s), _ptr(z), _ptr(status), _ptr(iters), _ptr(tr)))
+            if verbose:
+                for k in range(n):
+                    print(format_trace(tr[k], iters[k]))
+        else:
+            self._check(self._lib.dcol_solve_socp(self._h, n, nx, int(n_ort), int(d1), int(d2), _ptr(c), _ptr(G), _ptr(h), float(pdip_tol),
+                                                  MEM_HOST, _ptr(x), _ptr(s), _ptr(z), _ptr(status), _ptr(iters)))
         if single:
-            return x[0], s[0], z[0], int(status[0]), int(iters[0])
-        return x, s, z, status, iters
+            return (x[0], s[0], z[0], int(status[0]), int(iters[0])) + ((tr[0],) if trace else ())
+        return (x, s, z, status, iters) + ((tr,) if trace else ())
 
     def warm_stride(self) -> int:
         if self._table_version is not None:
@@ -466,12 +477,17 @@ def default_context() -> Context:
     return _default_ctx
 
 
-def _single(kind, prim1, prim2, pdip_tol, ctx):
+def _single(kind, prim1, prim2, pdip_tol, ctx, verbose=False):
     if not isinstance(prim1, AbstractPrimitive) or not isinstance(prim2, AbstractPrimitive):
         raise TypeError("proximity expects two primitives")
     if prim1.att_kind != prim2.att_kind:
         raise TypeError("no method: both primitives must be quaternion (AbstractPrimitive) or both MRP (AbstractPrimitiveMRP)")
     ctx = ctx or default_context()
+    if verbose:
+        # the reference prints one row per interior-point iteration (static_solver2.jl:117-120, 179-183).  The fast
+        # kernels keep no per-iteration record, so the table comes from the pair's dense (c, G, h) solved by
+        # dcol_solve_socp_trace on the GPU: the same iterates up to round-off; the values returned below are the fast path's.
+        ctx.solve_socp(*pair_problem(prim1, prim2), pdip_tol=pdip_tol, verbose=True)
     s1, s2 = ctx.add_shape(prim1), ctx.add_shape(prim2)
     out = ctx._batch(kind, [s1], [s2], prim1.r, prim1.att, prim2.r, prim2.att, prim1.att_kind, pdip_tol)
     st = int(out["status"][0])
@@ -483,15 +499,15 @@ def _single(kind, prim1, prim2, pdip_tol, ctx):
 
 
 def proximity(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
-    out = _single(0, prim1, prim2, pdip_tol, ctx)
+    out = _single(0, prim1, prim2, pdip_tol, ctx, verbose)
     return float(out["alpha"][0]), out["x"][0].copy()
 
 
 def proximity_gradient(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
-    out = _single(1, prim1, prim2, pdip_tol, ctx)
+    out = _single(1, prim1, prim2, pdip_tol, ctx, verbose)
     return float(out["alpha"][0]), out["grad"][0].copy()
 
 
 def proximity_jacobian(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
-    out = _single(2, prim1, prim2, pdip_tol, ctx)
+    out = _single(2, prim1, prim2, pdip_tol, ctx, verbose)
     return float(out["alpha"][0]), out["x"][0].copy(), out["J"][0].copy()

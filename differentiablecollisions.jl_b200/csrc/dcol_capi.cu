@@ -29,7 +29,7 @@ cudaError_t launch_persistent_v0(int grid, int block, size_t smem, cudaStream_t 
 cudaError_t launch_persistent_v1(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
 cudaError_t launch_persistent_v2(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter);
 cudaError_t launch_solve_socp(int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h, double tol, int max_iters,
-                              double* x, double* s, double* z, int32_t* status, int32_t* iters, cudaStream_t st);        // dcol_socp.cu
+                              double* x, double* s, double* z, int32_t* status, int32_t* iters, double* trace, cudaStream_t st);   // dcol_socp.cu
 int socp_limit(int which);
 static const void* persistent_kernel_ptr(int var) {
   return var == 2 ? persistent_kernel_ptr_v2() : (var == 1 ? persistent_kernel_ptr_v1() : persistent_kernel_ptr_v0());
@@ -2035,8 +2035,8 @@ int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta,
 }
 
 // Generic batched conic solve (dcol_socp.cu): the reference's solve_socp on n problems of common dimensions.
-int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
-                    double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters) {
+static int solve_socp_impl(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
+                           double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters, double* trace) {
   if (!ctx) return -1;
   ctx->err.clear();
   const int ns = n_ort + d1 + d2;
@@ -2050,9 +2050,10 @@ int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2,
   cudaStream_t S = ctx->stream();
   const double *dc_ = c, *dG = G, *dh = h; double *dx = x, *ds = s, *dz = z; int32_t *dst = status, *dit = iters;
   const size_t bc = align256(sizeof(double) * nx * (size_t)n), bG = align256(sizeof(double) * (size_t)ns * nx * (size_t)n), bh = align256(sizeof(double) * ns * (size_t)n),
-               bi = align256(sizeof(int32_t) * (size_t)n);
+               bi = align256(sizeof(int32_t) * (size_t)n), bt = trace ? align256(sizeof(double) * DCOL_TRACE_ROWS * DCOL_TRACE_COLS * (size_t)n) : 0;
+  double* dtr = trace;
   if (mem == DCOL_MEM_HOST) {
-    CK(ctx->d_wrench.need(2 * bc + bG + 3 * bh + 2 * bi));
+    CK(ctx->d_wrench.need(2 * bc + bG + 3 * bh + 2 * bi + bt));
     char* w = (char*)ctx->d_wrench.p;
     CK(cudaMemcpyAsync(w, c, sizeof(double) * nx * (size_t)n, cudaMemcpyHostToDevice, S));
     CK(cudaMemcpyAsync(w + bc, G, sizeof(double) * (size_t)ns * nx * (size_t)n, cudaMemcpyHostToDevice, S));
@@ -2060,8 +2061,12 @@ int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2,
     dc_ = (const double*)w; dG = (const double*)(w + bc); dh = (const double*)(w + bc + bG);
     dx = (double*)(w + bc + bG + bh); ds = (double*)(w + 2 * bc + bG + bh); dz = (double*)(w + 2 * bc + bG + 2 * bh);
     dst = (int32_t*)(w + 2 * bc + bG + 3 * bh); dit = (int32_t*)(w + 2 * bc + bG + 3 * bh + bi);
+    if (trace) {                                  // rows past a problem's last iteration keep the caller's values
+      dtr = (double*)(w + 2 * bc + bG + 3 * bh + 2 * bi);
+      CK(cudaMemcpyAsync(dtr, trace, sizeof(double) * DCOL_TRACE_ROWS * DCOL_TRACE_COLS * (size_t)n, cudaMemcpyHostToDevice, S));
+    }
   }
-  CK(launch_solve_socp(n, nx, n_ort, d1, d2, dc_, dG, dh, pdip_tol, ctx->max_iters, dx, ds, dz, dst, dit, S));
+  CK(launch_solve_socp(n, nx, n_ort, d1, d2, dc_, dG, dh, pdip_tol, ctx->max_iters, dx, ds, dz, dst, dit, dtr, S));
   ctx->launches++;
   if (mem == DCOL_MEM_HOST) {
     CK(cudaMemcpyAsync(x, dx, sizeof(double) * nx * (size_t)n, cudaMemcpyDeviceToHost, S));
@@ -2069,9 +2074,19 @@ int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2,
     CK(cudaMemcpyAsync(z, dz, sizeof(double) * ns * (size_t)n, cudaMemcpyDeviceToHost, S));
     if (status) CK(cudaMemcpyAsync(status, dst, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, S));
     if (iters) CK(cudaMemcpyAsync(iters, dit, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, S));
+    if (trace) CK(cudaMemcpyAsync(trace, dtr, sizeof(double) * DCOL_TRACE_ROWS * DCOL_TRACE_COLS * (size_t)n, cudaMemcpyDeviceToHost, S));
   }
   CK(cudaStreamSynchronize(S));
   return 0;
+}
+int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
+                    double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters) {
+  return solve_socp_impl(ctx, n, nx, n_ort, d1, d2, c, G, h, pdip_tol, mem, x, s, z, status, iters, nullptr);
+}
+int dcol_solve_socp_trace(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
+                          double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters, double* trace) {
+  if (ctx && !trace) { ctx->err = "dcol_solve_socp_trace: NULL trace"; return -1; }
+  return solve_socp_impl(ctx, n, nx, n_ort, d1, d2, c, G, h, pdip_tol, mem, x, s, z, status, iters, trace);
 }
 
 // ---- asynchronous submissions (host buffers): up to three in flight; inputs of submission k+1 cross PCIe while
@@ -2099,6 +2114,30 @@ int dcol_wait(dcol_ctx* ctx, int ticket) {
     if (ctx->done_ticket[h] == ticket) { if (ctx->done_result[h]) ctx->err = ctx->done_err[h]; return ctx->done_result[h]; }
   ctx->err = "dcol_wait: unknown ticket (the outcomes of the last 16 submissions are kept)";
   return -1;
+}
+
+// Self-test of the host copy engine (no GPU needed; run by the CPU test suite): `rounds` batches of slices with ragged
+// sizes and offsets between two buffers of `bytes` bytes on `threads` threads; returns 0 if every byte arrived.
+int dcol_host_copy_selftest(int threads, int64_t bytes, int rounds) {
+  if (threads < 1 || threads > 64 || bytes < 1 || rounds < 1) return -1;
+  std::vector<unsigned char> src((size_t)bytes), dst((size_t)bytes);
+  uint64_t x = 0x9e3779b97f4a7c15ull;
+  auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  HostCopier cp;
+  cp.start(threads - 1);
+  for (int r = 0; r < rounds; r++) {
+    for (size_t i = 0; i < src.size(); i++) src[i] = (unsigned char)rnd();
+    std::fill(dst.begin(), dst.end(), (unsigned char)0);
+    std::vector<CopyJob> jobs;
+    for (size_t o = 0; o < src.size();) {      // ragged pieces: 1 byte .. 3 MB, cut into slices by add()
+      const size_t len = std::min<size_t>(src.size() - o, 1 + (size_t)(rnd() % ((r & 1) ? 4096 : (3u << 20))));
+      HostCopier::add(jobs, dst.data() + o, src.data() + o, len);
+      o += len;
+    }
+    cp.run(jobs);
+    if (!jobs.empty() || memcmp(src.data(), dst.data(), src.size()) != 0) return 1 + r;
+  }
+  return 0;
 }
 
 // ---- device groups: one context per listed device, contiguous index slices, one host thread per member and call

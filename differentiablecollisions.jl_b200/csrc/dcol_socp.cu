@@ -151,7 +151,7 @@ __device__ inline void chol_solve(double (*U)[G_MAXX], int n, const double* b, d
 
 __global__ void k_solve_socp(int64_t n, ConeDims K, const double* __restrict__ cs, const double* __restrict__ Gs, const double* __restrict__ hs,
                              double tol, int max_iters, double* __restrict__ xs, double* __restrict__ ss, double* __restrict__ zs,
-                             int32_t* __restrict__ status, int32_t* __restrict__ iters) {
+                             int32_t* __restrict__ status, int32_t* __restrict__ iters, double* __restrict__ trace) {
   const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
   const int nx = K.nx, ns = K.ns;
@@ -238,6 +238,20 @@ __global__ void k_solve_socp(int64_t n, ConeDims K, const double* __restrict__ c
     for (int j = 0; j < nx; j++) x[j] += al * dx[j];
     for (int k = 0; k < ns; k++) { s[k] += al * ds[k]; z[k] += al * dz[k]; }
     it = iter;
+    if (trace) {
+      // the row the reference prints per iteration with verbose = true (static_solver2.jl:179-183):
+      // c'x, s'z/(n_ort + 1), |G x + s - h|, |s o z + sigma mu e|, step
+      double* tr = trace + (p * DCOL_TRACE_ROWS + (iter - 1)) * DCOL_TRACE_COLS;
+      double obj = 0.0, gap = 0.0, pres = 0.0, cent = 0.0;
+      for (int j = 0; j < nx; j++) obj += c[j] * x[j];
+      Gx(x, t1);
+      for (int k = 0; k < ns; k++) { const double r = t1[k] + s[k] - h[k]; pres += r * r; gap += s[k] * z[k]; }
+      cone_prod(K, s, z, t2);
+      for (int i = 0; i < K.n_ort; i++) t2[i] += sig * mu;
+      { int o = K.n_ort; for (int b = 0; b < 2; b++) if (K.d[b] > 0) { t2[o] += sig * mu; o += K.d[b]; } }
+      for (int k = 0; k < ns; k++) cent += t2[k] * t2[k];
+      if (iter <= DCOL_TRACE_ROWS) { tr[0] = obj; tr[1] = gap / (K.n_ort + 1); tr[2] = sqrt(pres); tr[3] = sqrt(cent); tr[4] = al; }
+    }
   }
   for (int j = 0; j < nx; j++) xs[p * nx + j] = x[j];
   for (int k = 0; k < ns; k++) { ss[p * ns + k] = s[k]; zs[p * ns + k] = z[k]; }
@@ -246,9 +260,9 @@ __global__ void k_solve_socp(int64_t n, ConeDims K, const double* __restrict__ c
 }
 
 cudaError_t launch_solve_socp(int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h, double tol, int max_iters,
-                              double* x, double* s, double* z, int32_t* status, int32_t* iters, cudaStream_t st) {
+                              double* x, double* s, double* z, int32_t* status, int32_t* iters, double* trace, cudaStream_t st) {
   ConeDims K; K.nx = nx; K.n_ort = n_ort; K.d[0] = d1; K.d[1] = d2; K.ns = n_ort + d1 + d2;
-  k_solve_socp<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, K, c, G, h, tol, max_iters, x, s, z, status, iters);
+  k_solve_socp<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(n, K, c, G, h, tol, max_iters, x, s, z, status, iters, trace);
   return cudaGetLastError();
 }
 int socp_limit(int which) { return which == 0 ? G_MAXX : (which == 1 ? G_MAXS : G_MAXD); }

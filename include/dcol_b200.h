@@ -197,6 +197,14 @@ int dcol_host_unregister(dcol_ctx* ctx, void* ptr);
  * test/solver_tests.jl fixture runs through it); the proximity entry points above never form G and are the fast path. */
 int dcol_solve_socp(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
                     double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters);
+/* The same solve with the per-iteration record the reference prints under verbose = true (static_solver2.jl:117-120,
+ * 179-183): trace[(p * DCOL_TRACE_ROWS + it) * DCOL_TRACE_COLS + k], it = 0 .. iters[p] - 1, k = {c'x, s'z/(n_ort + 1),
+ * |G x + s - h|, |s o z + sigma mu e|, step length}; rows past iters[p] are left untouched.  `trace` lives where the
+ * other arrays live (mem).  The single-pair front ends build the pair's (c, G, h) on the host and print this table. */
+#define DCOL_TRACE_ROWS 50
+#define DCOL_TRACE_COLS 5
+int dcol_solve_socp_trace(dcol_ctx* ctx, int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h,
+                          double pdip_tol, int mem, double* x, double* s, double* z, int32_t* status, int32_t* iters, double* trace);
 
 /* ---- warm start -------------------------------------------------------------------
  * Opt-in, NOT in the reference (every reference solve starts from `initialize`, static_solver2.jl:86-103) and excluded
@@ -236,6 +244,10 @@ double  dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds);
 /* measurement knob: host-pointer calls issue their host<->device copies (same staging, streams, chunking) but no kernels;
  * gives the copy-only bound of the end-to-end path */
 int     dcol_set_copy_only(dcol_ctx* ctx, int on);
+
+/* Self-test of the copy threads behind host-pointer calls on pageable memory (no GPU needed): `rounds` batches of ragged
+ * slices between two buffers of `bytes` bytes on `threads` threads; 0 if every byte arrived. */
+int dcol_host_copy_selftest(int threads, int64_t bytes, int rounds);
 
 /* ---- device groups: one process, several GPUs ------------------------------------------------
  * The reference's callers are single-process Julia programs; a group lets such a caller use every GPU of the box

@@ -397,18 +397,45 @@ unpin!(a::Array) = (_check(ccall((:dcol_host_unregister, _lib[]), Cint, (Ptr{Cvo
     solve_socp(c, G, h, idx_ort, idx_soc1, idx_soc2; pdip_tol = 1e-4) -> (x, s, z)
 
 Same call as the reference's `solve_socp` (`src/solvers/coneqp/static_solver2.jl:106-191`); rows of `G`, `h` must be
-ordered `[idx_ort; idx_soc1; idx_soc2]` as `combine_problem_matrices` produces them.  Runs `dcol_solve_socp` on one problem.
+ordered `[idx_ort; idx_soc1; idx_soc2]` as `combine_problem_matrices` produces them.  Runs `dcol_solve_socp` on one problem;
+`verbose = true` runs `dcol_solve_socp_trace` and prints the reference's per-iteration table.  The single-pair calls below
+accept `verbose` and ignore it (the fast kernels never form `G`): pass the pair's `combine_problem_matrices(...)` here
+for the table.
 """
+# "%W.De" without a dependency on Printf: mantissa with D decimals, two-digit exponent, right-aligned in W characters
+function _e(v::Float64, w::Int, d::Int)
+    (isfinite(v) && v != 0) || return lpad(string(v), w)
+    ex = floor(Int, log10(abs(v))); m = round(v / 10.0^ex; digits = d)
+    abs(m) >= 10 && (m /= 10; ex += 1)
+    ms = string(m); nd = d - (length(ms) - findfirst('.', ms))
+    return lpad(ms * "0"^nd * "e" * (ex < 0 ? "-" : "+") * lpad(abs(ex), 2, "0"), w)
+end
+
 function solve_socp(c::AbstractVector, G::AbstractMatrix, h::AbstractVector, idx_ort, idx_soc1, idx_soc2; pdip_tol = 1e-4, verbose = false)
     ns, nx = size(G)
     Gr = Matrix{Float64}(transpose(G))                               # row-major ns x nx for the C side
     x = Vector{Float64}(undef, nx); s = Vector{Float64}(undef, ns); z = Vector{Float64}(undef, ns)
     status = Int32[0]; iters = Int32[0]
+    if verbose                                                       # static_solver2.jl:117-120, 179-183
+        trace = fill(NaN, 5, 50)                                     # DCOL_TRACE_COLS x DCOL_TRACE_ROWS, one column per iteration
+        _check(ccall((:dcol_solve_socp_trace, _lib[]), Cint,
+                     (Ptr{Cvoid}, Int64, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+                     _ctx[], 1, nx, length(idx_ort), length(idx_soc1), length(idx_soc2), collect(Float64, c), Gr, collect(Float64, h),
+                     Float64(pdip_tol), MEM_HOST, x, s, z, status, iters, trace))
+        println("iter     objv        μ       |Gx+s-h|      |s∘z|      α")
+        println("---------------------------------------------------------")
+        for k in 1:min(iters[1], 50)
+            println(lpad(k, 3), "   ", _e(trace[1, k], 10, 3), "  ", _e(trace[2, k], 9, 2), "  ", _e(trace[3, k], 9, 2), "  ",
+                    _e(trace[4, k], 9, 2), "  ", trace[5, k] < 0 ? "" : " ", string(round(trace[5, k]; digits = 4)))
+        end
+    else
     _check(ccall((:dcol_solve_socp, _lib[]), Cint,
                  (Ptr{Cvoid}, Int64, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
                   Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
                  _ctx[], 1, nx, length(idx_ort), length(idx_soc1), length(idx_soc2), collect(Float64, c), Gr, collect(Float64, h),
                  Float64(pdip_tol), MEM_HOST, x, s, z, status, iters))
+    end
     status[1] == 1 && error("pdip failed")                           # static_solver2.jl:188
     status[1] == 0 || throw(DomainError(status[1], "numerical breakdown in the conic solver"))
     return x, s, z

@@ -1,6 +1,7 @@
 #!/bin/bash
+# final pass of round 2, session 3: parity table, then the measurement session (scripts/r02_profile.sh)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02f_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02f_tests.log
-timeout 600 python scripts/gpu_configs.py > gpurun_out/r02f_configs.txt 2>&1
-tail -15 gpurun_out/r02f_tests.log; cat gpurun_out/r02f_configs.txt
+timeout 1500 python scripts/parity_table.py 100000 > gpurun_out/r02f_parity.log 2>&1
+bash scripts/r02_profile.sh r02f
+tail -30 gpurun_out/r02f_parity.log

@@ -83,3 +83,16 @@ def test_mass_properties_host_helper():
     assert m == pytest.approx(math.pi * rad**2 * 2.0 / 3) and I[0, 0] == pytest.approx(0.3 * m * rad**2)
     with pytest.raises(TypeError):
         dc.mass_properties(dc.Sphere(1.0))
+
+
+@pytest.mark.parametrize("threads", [1, 2, 7])
+def test_host_copy_threads(threads):
+    """The copy engine behind host-pointer calls on pageable memory (HostCopier, dcol_capi.cu) needs no GPU: ragged slices,
+    many batches (workers go from spinning to sleeping and back in between), every byte checked."""
+    lib = _capi.load()
+    assert lib.dcol_host_copy_selftest(threads, 9 * 1024 * 1024 + 13, 12) == 0
+    assert lib.dcol_host_copy_selftest(threads, 1, 3) == 0
+    import time
+    time.sleep(0.01)                                   # longer than the workers' spin window
+    assert lib.dcol_host_copy_selftest(threads, 300_001, 6) == 0
+    assert lib.dcol_host_copy_selftest(0, 10, 1) == -1

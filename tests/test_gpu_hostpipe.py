@@ -104,3 +104,44 @@ def test_pageable_pipeline_reports_bad_shape_index():
         assert (on._batch(0, s1, s2, r1, a1, r2, a2, 0, 1e-6)["status"] == 0).all()      # the context stays usable
     finally:
         on.close()
+
+
+def test_operator_results_through_the_pipeline():
+    """Operators that solve into device scratch (culled scene, scene wrench, planar constraint rows) return their results
+    to pageable memory in slabs through the same staging area (results_to_host): bit-identical to the driver's copies;
+    a pinned-memory budget too small for the call falls back to the driver path."""
+    on, off = _ctx(True), _ctx(False)
+    try:
+        t, shape, r, att = scene_bodies(1300, 0, spread=3.0)             # 844 350 pairs: 100 MB of gradient rows
+        for c in (on, off):
+            c.set_shape_arrays(*t.arrays())
+            c.scene_set_cull(1.5)
+        a, b = on.scene_allpairs(1, shape, r, att, 0), off.scene_allpairs(1, shape, r, att, 0)
+        _same(a, b)
+        assert (a["status"] == 3).sum() > 0 and (a["status"] == 0).sum() > 0
+        lam = util.rng(3).uniform(0, 1, a["alpha"].shape[0])
+        _same(on.scene_wrench(shape, r, att, lam, 0, per_pair=True), off.scene_wrench(shape, r, att, lam, 0, per_pair=True))
+        for c in (on, off):
+            c.scene_set_cull(0.0)
+        # planar constraint rows: 250 000 states x 3 obstacles (6 MB + 18 MB + 3 MB)
+        veh = dc.create_rect_prism(2.5, 0.15, 0.01)[0]
+        obs = [dc.create_rect_prism(3.0, 3.0, 0.02)[0], dc.create_rect_prism(4.0, 1.0, 0.02)[0], dc.create_rect_prism(1.0, 3.0, 0.02)[0]]
+        tb = dc.ShapeTable(); sv = tb.add(veh); so = np.array([tb.add(x) for x in obs], np.int32)
+        g = util.rng(9)
+        xyt = np.stack([g.uniform(-4, 4, 250000), g.uniform(-4, 4, 250000), g.uniform(-3, 3, 250000)], axis=1)
+        r2 = np.array([[-1.5, 1.5, 0.0], [2.0, -2.5, 0.0], [3.0, 2.5, 0.0]]); p2 = np.zeros((3, 3))
+        for c in (on, off):
+            c.set_shape_arrays(*tb.arrays())
+        _same(on.se2_constraints(xyt, sv, so, r2, p2), off.se2_constraints(xyt, sv, so, r2, p2))
+        # no pinned memory to spare (DCOL_PIN_MAX_MB): the calls still work, through the driver's pageable copies
+        os.environ["DCOL_PIN_MAX_MB"] = "1"
+        try:
+            _same(on.se2_constraints(xyt, sv, so, r2, p2), off.se2_constraints(xyt, sv, so, r2, p2))
+            tm, s1, s2, r1, a1, rr2, a2 = util.mixed_batch(120000, 0, seed=2)
+            for c in (on, off):
+                c.set_shape_arrays(*tm.arrays())
+            _same(on._batch(0, s1, s2, r1, a1, rr2, a2, 0, 1e-6), off._batch(0, s1, s2, r1, a1, rr2, a2, 0, 1e-6))
+        finally:
+            os.environ.pop("DCOL_PIN_MAX_MB", None)
+    finally:
+        on.close(); off.close()

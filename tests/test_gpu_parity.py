@@ -543,3 +543,41 @@ def test_generic_socp_entry_on_the_reference_fixture(ctx, oracle):
     # dimensions out of range are an API error
     with pytest.raises(RuntimeError):
         ctx.solve_socp(np.zeros(20), np.zeros((30, 20)), np.zeros(30), 30, 0, 0)
+
+
+def test_verbose_trace(ctx, capsys):
+    """verbose = true (static_solver2.jl:117-120, 179-183): dcol_solve_socp_trace records, per iteration, the five numbers
+    the reference prints.  The last row describes the returned iterate, so it can be recomputed from (x, s, z); rows past
+    the last iteration are untouched; the single-pair front ends print the table and return the fast path's values."""
+    d = json.load(open(os.path.join(util.GOLDEN, "example_socp_2.json")))
+    Gm = np.array(d["G"], float); h = np.array(d["h"], float); c = np.array(d["c"], float)
+    x, s, z, st, it, tr = ctx.solve_socp(c, Gm, h, d["n_ort"], d["n_soc1"], d["n_soc2"], pdip_tol=1e-8, trace=True)
+    x0, s0, z0, st0, it0 = ctx.solve_socp(c, Gm, h, d["n_ort"], d["n_soc1"], d["n_soc2"], pdip_tol=1e-8)
+    assert st == 0 and it == it0 and np.array_equal(x, x0) and np.array_equal(s, s0) and np.array_equal(z, z0)
+    assert np.isfinite(tr[:it]).all() and np.isnan(tr[it:]).all()
+    last = tr[it - 1]
+    assert last[0] == pytest.approx(c @ x, rel=1e-13)
+    assert last[1] == pytest.approx(s @ z / (d["n_ort"] + 1), rel=1e-9)          # the reference divides by n_ort + 1 here (:181)
+    assert last[2] == pytest.approx(np.linalg.norm(Gm @ x + s - h), abs=1e-12)
+    assert (tr[:it, 4] > 0).all() and (tr[:it, 4] <= 1).all() and (np.diff(tr[:it, 1]) < 0).all()
+    # a batch: every problem its own rows
+    caps = dc.Capsule(0.3, 1.2); cone = dc.Cone(2.0, np.deg2rad(22))
+    r1, a1, r2, a2 = util.random_poses(70, 0, 11)
+    Gs, hs = [], []
+    for k in range(70):
+        caps.r, caps.q, cone.r, cone.q = r1[k], a1[k], r2[k], a2[k]
+        cc, Gk, hk, n_ort, d1, d2 = dc.pair_problem(caps, cone)
+        Gs.append(Gk); hs.append(hk)
+    X, S, Z, stt, its, T = ctx.solve_socp(cc, np.array(Gs), np.array(hs), n_ort, d1, d2, pdip_tol=1e-6, trace=True)
+    assert (stt == 0).all() and len(set(its.tolist())) > 1
+    for k in range(70):
+        assert np.isfinite(T[k, :its[k]]).all() and np.isnan(T[k, its[k]:]).all()
+        assert T[k, its[k] - 1, 0] == pytest.approx(X[k, 3], rel=1e-13)
+    # the front end: header, one row per iteration, objective of the last row = alpha of the fast path
+    capsys.readouterr()
+    alpha, xw = dc.proximity(caps, cone, pdip_tol=1e-6, verbose=True, ctx=ctx)
+    out = capsys.readouterr().out.strip().split("\n")
+    assert out[0].startswith("iter     objv") and set(out[1]) == {"-"} and len(out) == 2 + its[69]
+    assert int(out[-1].split()[0]) == its[69] and float(out[-1].split()[1]) == pytest.approx(alpha, rel=2e-3)
+    a2_, g = dc.proximity_gradient(caps, cone, verbose=True, ctx=ctx)
+    assert len(capsys.readouterr().out.strip().split("\n")) == len(out) and a2_ == pytest.approx(alpha, rel=1e-9)

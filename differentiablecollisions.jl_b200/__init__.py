@@ -15,4 +15,4 @@ from .api import (  # noqa: F401
 )
 from .problem_matrices import problem_matrices, combine_problem_matrices, pair_problem  # noqa: F401
 from . import flops_model  # noqa: F401
-from .sharding import shard, shard_bounds, gather_rows, bind_to_gpu_numa_node, bind_disjoint_cpus  # noqa: F401
+from .sharding import shard, shard_bounds, gather_rows, scene_wrench_sharded, bind_to_gpu_numa_node, bind_disjoint_cpus  # noqa: F401

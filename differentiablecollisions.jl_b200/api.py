@@ -24,6 +24,22 @@ from .shapes import ShapeTable
 MEM_HOST, MEM_DEVICE = 0, 1
 
 
+def _scene_arrays(shape, r, att, att_kind):
+    shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(-1)
+    nb = shape.shape[0]
+    na = 4 if att_kind == ATT_QUAT else 3
+    return (shape, np.ascontiguousarray(r, dtype=np.float64).reshape(nb, 3), np.ascontiguousarray(att, dtype=np.float64).reshape(nb, na),
+            nb, 6 + 2 * na)
+
+
+def _pair_range(lib, nb, pair_range):
+    n = int(lib.dcol_scene_pair_count(nb))
+    k0, k1 = (0, n) if pair_range is None else (int(pair_range[0]), int(pair_range[1]))
+    if not 0 <= k0 <= k1 <= n:
+        raise ValueError(f"pair_range must satisfy 0 <= k0 <= k1 <= {n}")
+    return k0, k1
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -289,40 +305,36 @@ class Context:
         alpha* > alpha_cut are answered without the conic solve (alpha = a lower bound > alpha_cut, status 3); 0 = off."""
         self._check(self._lib.dcol_scene_set_cull(self._h, float(alpha_cut)))
 
-    def scene_allpairs(self, kind, shape, r, att, att_kind=ATT_QUAT, pdip_tol=1e-6):
-        """All i<j pairs of a scene in `combinations` order (`dcol_scene_allpairs`); pair list generated on the device."""
+    def scene_allpairs(self, kind, shape, r, att, att_kind=ATT_QUAT, pdip_tol=1e-6, pair_range=None):
+        """All i<j pairs of a scene in `combinations` order (`dcol_scene_allpairs`); pair list generated on the device.
+        `pair_range=(k0, k1)`: only that slice of the enumeration (`dcol_scene_allpairs_range`, one shard of SURVEY.md 8e)."""
         if self._table_version is not None:
             self.sync_shapes()
-        shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(-1)
-        nb = shape.shape[0]
-        na = 4 if att_kind == ATT_QUAT else 3
-        nt = 6 + 2 * na
-        r = np.ascontiguousarray(r, dtype=np.float64).reshape(nb, 3); att = np.ascontiguousarray(att, dtype=np.float64).reshape(nb, na)
-        n = int(self._lib.dcol_scene_pair_count(nb))
-        out, x, deriv = self._alloc_out(kind, n, nt)
-        self._check(self._lib.dcol_scene_allpairs(self._h, int(kind), nb, _ptr(shape), _ptr(r), _ptr(att), int(att_kind), float(pdip_tol),
-                                                  MEM_HOST, _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
+        shape, r, att, nb, nt = _scene_arrays(shape, r, att, att_kind)
+        k0, k1 = _pair_range(self._lib, nb, pair_range)
+        out, x, deriv = self._alloc_out(kind, k1 - k0, nt)
+        self._check(self._lib.dcol_scene_allpairs_range(self._h, int(kind), nb, k0, k1, _ptr(shape), _ptr(r), _ptr(att), int(att_kind), float(pdip_tol),
+                                                        MEM_HOST, _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
         return self._finish(out, kind, x, deriv)
 
-    def scene_wrench(self, shape, r, att, lam, att_kind=ATT_QUAT, pdip_tol=1e-6, per_pair=True):
+    def scene_wrench(self, shape, r, att, lam, att_kind=ATT_QUAT, pdip_tol=1e-6, per_pair=True, pair_range=None):
         """`dcol_scene_wrench`: alpha of all i<j pairs and, per body, sum_k lam[k] * [d alpha_k/d r_b ; G(q_b)' d alpha_k/d q_b]
         (the accumulation loop of examples/contact_physics/ncp_contact_simulation.jl:133-139); the gradient rows stay on
-        the device.  per_pair=False skips the alpha / status / iters arrays."""
+        the device.  per_pair=False skips the alpha / status / iters arrays.  `pair_range=(k0, k1)`: the partial sums of
+        that slice of the pairs (`dcol_scene_wrench_range`; `lam` holds the slice's k1 - k0 weights)."""
         if self._table_version is not None:
             self.sync_shapes()
-        shape = np.ascontiguousarray(shape, dtype=np.int32).reshape(-1)
-        nb = shape.shape[0]
-        na = 4 if att_kind == ATT_QUAT else 3
-        r = np.ascontiguousarray(r, dtype=np.float64).reshape(nb, 3); att = np.ascontiguousarray(att, dtype=np.float64).reshape(nb, na)
-        n = int(self._lib.dcol_scene_pair_count(nb))
+        shape, r, att, nb, _ = _scene_arrays(shape, r, att, att_kind)
+        k0, k1 = _pair_range(self._lib, nb, pair_range)
+        n = k1 - k0
         lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1)
         if lam.shape[0] != n:
             raise ValueError(f"scene_wrench: lam must have one entry per pair ({n})")
         out = {"wrench": np.empty((nb, 6))}
         if per_pair:
             out.update(alpha=np.empty(n), status=np.empty(n, dtype=np.int32), iters=np.empty(n, dtype=np.int32))
-        self._check(self._lib.dcol_scene_wrench(self._h, nb, _ptr(shape), _ptr(r), _ptr(att), _ptr(lam), int(att_kind), float(pdip_tol),
-                                                MEM_HOST, _ptr(out.get("alpha")), _ptr(out["wrench"]), _ptr(out.get("status")), _ptr(out.get("iters"))))
+        self._check(self._lib.dcol_scene_wrench_range(self._h, nb, k0, k1, _ptr(shape), _ptr(r), _ptr(att), _ptr(lam), int(att_kind), float(pdip_tol),
+                                                      MEM_HOST, _ptr(out.get("alpha")), _ptr(out["wrench"]), _ptr(out.get("status")), _ptr(out.get("iters"))))
         return out
 
     def se2_constraints(self, xytheta, vehicle_shape, obs_shape, r_obs, p_obs, pdip_tol=1e-6):
@@ -455,6 +467,39 @@ class Group:
             out["grad"] = deriv
         elif kind == 2:
             out["J"] = deriv.transpose(0, 2, 1)
+        return out
+
+    def scene_set_cull(self, alpha_cut: float = 0.0):
+        """Broad phase of the group's scene operators: set on every member (`dcol_scene_set_cull`)."""
+        for i in range(len(self)):
+            if self._lib.dcol_scene_set_cull(self._lib.dcol_group_ctx(self._h, i), float(alpha_cut)) != 0:
+                raise RuntimeError("dcol_scene_set_cull failed")
+
+    def scene_allpairs(self, kind, shape, r, att, att_kind=ATT_QUAT, pdip_tol=1e-6):
+        """`dcol_group_scene_allpairs`: member i solves the i-th slice of the i<j enumeration; rows as on one device."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        shape, r, att, nb, nt = _scene_arrays(shape, r, att, att_kind)
+        n = int(self._lib.dcol_scene_pair_count(nb))
+        out, x, deriv = Context._alloc_out(None, kind, n, nt)
+        self._check(self._lib.dcol_group_scene_allpairs(self._h, int(kind), nb, _ptr(shape), _ptr(r), _ptr(att), int(att_kind), float(pdip_tol),
+                                                        _ptr(out["alpha"]), _ptr(x), _ptr(deriv), _ptr(out["status"]), _ptr(out["iters"])))
+        return Context._finish(out, kind, x, deriv)
+
+    def scene_wrench(self, shape, r, att, lam, att_kind=ATT_QUAT, pdip_tol=1e-6, per_pair=True):
+        """`dcol_group_scene_wrench`: the members' per-body partial sums added in member order."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        shape, r, att, nb, _ = _scene_arrays(shape, r, att, att_kind)
+        n = int(self._lib.dcol_scene_pair_count(nb))
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1)
+        if lam.shape[0] != n:
+            raise ValueError(f"scene_wrench: lam must have one entry per pair ({n})")
+        out = {"wrench": np.empty((nb, 6))}
+        if per_pair:
+            out.update(alpha=np.empty(n), status=np.empty(n, dtype=np.int32), iters=np.empty(n, dtype=np.int32))
+        self._check(self._lib.dcol_group_scene_wrench(self._h, nb, _ptr(shape), _ptr(r), _ptr(att), _ptr(lam), int(att_kind), float(pdip_tol),
+                                                      _ptr(out.get("alpha")), _ptr(out["wrench"]), _ptr(out.get("status")), _ptr(out.get("iters"))))
         return out
 
     def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6):

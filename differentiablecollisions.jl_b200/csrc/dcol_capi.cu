@@ -534,11 +534,13 @@ __device__ __forceinline__ void pair_of_index(int n_bodies, int64_t k, int64_t& 
   while ((i + 1) * (2 * (int64_t)n_bodies - i - 2) / 2 <= k) i++;
   j = k - i * (2 * (int64_t)n_bodies - i - 1) / 2 + i + 1;
 }
-__global__ void k_allpairs(int n_bodies, int64_t n_pairs, const int32_t* __restrict__ shape,
+// The n_pairs pairs from index k0 on (a slice of the enumeration: one member of a device group, one rank); row k of the
+// outputs belongs to pair k0 + k.
+__global__ void k_allpairs(int n_bodies, int64_t k0, int64_t n_pairs, const int32_t* __restrict__ shape,
                            int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ p1, int32_t* __restrict__ p2) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_pairs; k += (int64_t)gridDim.x * blockDim.x) {
     int64_t i, j;
-    pair_of_index(n_bodies, k, i, j);
+    pair_of_index(n_bodies, k0 + k, i, j);
     s1[k] = shape[i]; s2[k] = shape[j]; p1[k] = (int32_t)i; p2[k] = (int32_t)j;
   }
 }
@@ -563,7 +565,7 @@ __global__ void k_body_centres(int n_bodies, const int32_t* __restrict__ shape, 
   }
   centre[3 * b] = c[0]; centre[3 * b + 1] = c[1]; centre[3 * b + 2] = c[2];
 }
-__global__ void k_allpairs_cull(int n_bodies, int64_t n_pairs, const int32_t* __restrict__ shape, int n_shapes, const double* __restrict__ brad,
+__global__ void k_allpairs_cull(int n_bodies, int64_t k0, int64_t n_pairs, const int32_t* __restrict__ shape, int n_shapes, const double* __restrict__ brad,
                                 const double* __restrict__ centre, double alpha_cut, int nd,
                                 int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ p1, int32_t* __restrict__ p2,
                                 int32_t* __restrict__ oidx, int* __restrict__ count,
@@ -576,7 +578,7 @@ __global__ void k_allpairs_cull(int n_bodies, int64_t n_pairs, const int32_t* __
     bool keep = false;
     int64_t i = 0, j = 0; int si = 0, sj = 0;
     if (k < n_pairs) {
-      pair_of_index(n_bodies, k, i, j);
+      pair_of_index(n_bodies, k0 + k, i, j);
       si = shape[i]; sj = shape[j];
       keep = true;
       if ((unsigned)si < (unsigned)n_shapes && (unsigned)sj < (unsigned)n_shapes) {
@@ -613,8 +615,10 @@ __global__ void k_allpairs_cull(int n_bodies, int64_t n_pairs, const int32_t* __
 // (variational_utils.jl:24-26), identity for MRPs.  One block per body, no atomics: the pairs (b, j), j > b are the
 // contiguous run starting at k_b = b(2N-b-1)/2 (body b is side 1), the pairs (i, b), i < b sit at k_i + (b-i-1)
 // (body b is side 2).  Fixed summation order, so the result is reproducible.
-__global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, const double* __restrict__ lambda, const int32_t* __restrict__ culled,
-                               const double* __restrict__ att, int att_kind, double* __restrict__ out) {
+// With a slice [k0, k1) of the pair enumeration (grad / lambda / culled hold rows k0 .. k1-1), out[b] is the slice's part of
+// the sum; the parts of all slices add up to the whole (dcol_group_scene_wrench, sharded ranks).
+__global__ void k_scene_wrench(int n_bodies, int64_t k0, int64_t k1, const double* __restrict__ grad, const double* __restrict__ lambda,
+                               const int32_t* __restrict__ culled, const double* __restrict__ att, int att_kind, double* __restrict__ out) {
   const int b = blockIdx.x;
   const int na = (att_kind == 0) ? 4 : 3, nt = 6 + 2 * na, ns = 3 + na;
   const int64_t N = n_bodies;
@@ -624,6 +628,8 @@ __global__ void k_scene_wrench(int n_bodies, const double* __restrict__ grad, co
     int64_t k; int side;
     if (j > b) { k = (int64_t)b * (2 * N - b - 1) / 2 + (j - b - 1); side = 0; }
     else       { k = (int64_t)j * (2 * N - j - 1) / 2 + (b - j - 1); side = 1; }
+    if (k < k0 || k >= k1) continue;                             // another slice's pair
+    k -= k0;
     if (culled && culled[k] == DCOL_STATUS_CULLED) continue;     // far pair: its gradient row was never computed
     const double w = lambda[k];
     const double* g = grad + k * nt + side * ns;
@@ -1792,7 +1798,7 @@ int dcol_scene_set_cull(dcol_ctx* ctx, double alpha_cut) {
 }
 
 // centres, cull kernel, survivor count: fills the compact pair list (s1, s2, p1, p2, oidx) and returns its length in *n_keep
-static int scene_cull(dcol_ctx* ctx, cudaStream_t S, int n_bodies, int64_t np, const int32_t* d_shape, const double* d_r, const double* d_att,
+static int scene_cull(dcol_ctx* ctx, cudaStream_t S, int n_bodies, int64_t k0, int64_t np, const int32_t* d_shape, const double* d_r, const double* d_att,
                       int att_kind, int nd, int32_t* s1, int32_t* s2, int32_t* p1, int32_t* p2, int32_t* oidx,
                       double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters, int64_t* n_keep) {
   if (!ctx->h_count) CK(cudaHostAlloc((void**)&ctx->h_count, 2 * sizeof(int), cudaHostAllocDefault));
@@ -1802,7 +1808,7 @@ static int scene_cull(dcol_ctx* ctx, cudaStream_t S, int n_bodies, int64_t np, c
   CK(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), S));
   k_body_centres<<<(n_bodies + 127) / 128, 128, 0, S>>>(n_bodies, d_shape, (const DevShape*)ctx->d_shapes.p, ctx->n_shapes, d_r, d_att, att_kind,
                                                         d_centre, d_count + 1);
-  k_allpairs_cull<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, ctx->n_shapes, (const double*)ctx->d_brad.p,
+  k_allpairs_cull<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, k0, np, d_shape, ctx->n_shapes, (const double*)ctx->d_brad.p,
                                                                                        d_centre, ctx->cull_alpha, nd, s1, s2, p1, p2, oidx, d_count,
                                                                                        alpha, x, deriv, status, iters);
   CK(cudaGetLastError());
@@ -1818,12 +1824,21 @@ int64_t dcol_scene_pair_count(int n_bodies) { return n_bodies < 2 ? 0 : (int64_t
 int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* shape, const double* r, const double* att,
                         int att_kind, double pdip_tol, int mem,
                         double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  return dcol_scene_allpairs_range(ctx, query, n_bodies, 0, dcol_scene_pair_count(n_bodies), shape, r, att, att_kind, pdip_tol, mem,
+                                   alpha, x, deriv, status, iters);
+}
+
+int dcol_scene_allpairs_range(dcol_ctx* ctx, int query, int n_bodies, int64_t k_begin, int64_t k_end,
+                              const int32_t* shape, const double* r, const double* att,
+                              int att_kind, double pdip_tol, int mem,
+                              double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
   if (check_query_kind(ctx, query)) return -1;
   ctx->err.clear();
   if (n_bodies < 0 || !shape || !r || !att) { ctx->err = "dcol_scene_allpairs: bad arguments"; return -1; }
+  if (k_begin < 0 || k_end < k_begin || k_end > dcol_scene_pair_count(n_bodies)) { ctx->err = "dcol_scene_allpairs_range: need 0 <= k_begin <= k_end <= N(N-1)/2"; return -1; }
   if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { ctx->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
   if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
-  const int64_t np = dcol_scene_pair_count(n_bodies);
+  const int64_t np = k_end - k_begin;
   if (np == 0) return 0;
   if (np > 0x7fffffff) { ctx->err = "dcol_scene_allpairs: too many pairs for one call"; return -1; }
   CK(cudaSetDevice(ctx->device));
@@ -1861,7 +1876,7 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
     }
     if (!q_alpha || (query != Q_GRAD && !q_x) || (nd && !q_der)) { ctx->err = "dcol_scene_allpairs: NULL output pointer"; return -1; }
     int64_t n_keep = 0;
-    { int rc = scene_cull(ctx, S, n_bodies, np, d_shape, d_r, d_att, att_kind, nd, s1, s2, p1, p2, oidx, q_alpha, q_x, q_der, q_st, q_it, &n_keep); if (rc) return rc; }
+    { int rc = scene_cull(ctx, S, n_bodies, k_begin, np, d_shape, d_r, d_att, att_kind, nd, s1, s2, p1, p2, oidx, q_alpha, q_x, q_der, q_st, q_it, &n_keep); if (rc) return rc; }
     if (ctx->h_count[1]) { ctx->err = "dcol: shape index out of range in shape"; return -1; }
     if (n_keep > 0) {
       int rc = run_query(ctx, query, n_keep, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE, q_alpha, q_x, q_der, q_st, q_it,
@@ -1879,7 +1894,7 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
     }
     return 0;
   }
-  k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
+  k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, k_begin, np, d_shape, s1, s2, p1, p2);
   CK(cudaGetLastError());
   ctx->launches++;
   return run_query(ctx, query, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, mem, alpha, x, deriv, status, iters,
@@ -1890,12 +1905,21 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
 int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const double* r, const double* att, const double* lambda,
                       int att_kind, double pdip_tol, int mem,
                       double* alpha, double* wrench, int32_t* status, int32_t* iters) {
+  return dcol_scene_wrench_range(ctx, n_bodies, 0, dcol_scene_pair_count(n_bodies), shape, r, att, lambda, att_kind, pdip_tol, mem,
+                                 alpha, wrench, status, iters);
+}
+
+int dcol_scene_wrench_range(dcol_ctx* ctx, int n_bodies, int64_t k_begin, int64_t k_end,
+                            const int32_t* shape, const double* r, const double* att, const double* lambda,
+                            int att_kind, double pdip_tol, int mem,
+                            double* alpha, double* wrench, int32_t* status, int32_t* iters) {
   if (!ctx) return -1;
   ctx->err.clear();
   if (n_bodies < 0 || !shape || !r || !att || !lambda || !wrench) { ctx->err = "dcol_scene_wrench: bad arguments"; return -1; }
   if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { ctx->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
   if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
-  const int64_t np = dcol_scene_pair_count(n_bodies);
+  if (k_begin < 0 || k_end < k_begin || k_end > dcol_scene_pair_count(n_bodies)) { ctx->err = "dcol_scene_wrench_range: need 0 <= k_begin <= k_end <= N(N-1)/2"; return -1; }
+  const int64_t np = k_end - k_begin;
   if (np > 0x7fffffff) { ctx->err = "dcol_scene_wrench: too many pairs for one call"; return -1; }
   CK(cudaSetDevice(ctx->device));
   { int rc = drain_all(ctx); if (rc) return rc; }
@@ -1940,13 +1964,13 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
   int rc = 0;
   if (cull) {
     int64_t n_keep = 0;
-    rc = scene_cull(ctx, S, n_bodies, np, d_shape, d_r, d_att, att_kind, nt, s1, s2, p1, p2, oidx, q_alpha, nullptr, nullptr, q_status, q_iters, &n_keep);
+    rc = scene_cull(ctx, S, n_bodies, k_begin, np, d_shape, d_r, d_att, att_kind, nt, s1, s2, p1, p2, oidx, q_alpha, nullptr, nullptr, q_status, q_iters, &n_keep);
     if (rc) return rc;
     if (ctx->h_count[1]) { ctx->err = "dcol: shape index out of range in shape"; return -1; }
     if (n_keep > 0) rc = run_query(ctx, Q_GRAD, n_keep, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE,
                                    q_alpha, nullptr, d_grad, q_status, q_iters, p1, p2, n_bodies, n_bodies, DCOL_MEM_DEVICE, 0, false, oidx);
   } else {
-    k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, np, d_shape, s1, s2, p1, p2);
+    k_allpairs<<<(int)std::min<int64_t>((np + 255) / 256, 148 * 16), 256, 0, S>>>(n_bodies, k_begin, np, d_shape, s1, s2, p1, p2);
     CK(cudaGetLastError());
     ctx->launches++;
     rc = run_query(ctx, Q_GRAD, np, s1, s2, d_r, d_att, d_r, d_att, att_kind, pdip_tol, DCOL_MEM_DEVICE,
@@ -1954,7 +1978,7 @@ int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const d
   }
   if (rc) return rc;
   double* o = host ? d_out : wrench;
-  k_scene_wrench<<<n_bodies, 128, 0, S>>>(n_bodies, d_grad, d_lam, cull ? q_status : nullptr, d_att, att_kind, o);
+  k_scene_wrench<<<n_bodies, 128, 0, S>>>(n_bodies, k_begin, k_end, d_grad, d_lam, cull ? q_status : nullptr, d_att, att_kind, o);
   CK(cudaGetLastError());
   ctx->launches++;
   if (host) {
@@ -2224,6 +2248,78 @@ int dcol_group_query(dcol_group* g, int query, int64_t n, const int32_t* shape1,
   for (int i = 0; i < m; i++) {
     g->last_ms = std::max(g->last_ms, g->members[i]->last_ms);
     if (rc[i]) { g->err = "member " + std::to_string(i) + " (device " + std::to_string(g->members[i]->device) + "): " + g->members[i]->err; return rc[i]; }
+  }
+  return 0;
+}
+
+// Runs f(member, begin, end) on every member's contiguous slice of [0, n), one host thread per member.
+extern "C++" {
+template <class F>
+static int group_slices(dcol_group* g, int64_t n, F&& f) {
+  const int m = (int)g->members.size();
+  std::vector<int> rc(m, 0);
+  auto slice = [&](int i) {
+    const int64_t base = n / m, rem = n % m;
+    const int64_t b = i * base + std::min<int64_t>(i, rem), e = b + base + (i < rem ? 1 : 0);
+    rc[i] = f(i, b, e);
+  };
+  if (m == 1) slice(0);
+  else {
+    std::vector<std::thread> th;
+    for (int i = 1; i < m; i++) th.emplace_back(slice, i);
+    slice(0);
+    for (std::thread& t : th) t.join();
+  }
+  g->last_ms = -1.0;
+  for (int i = 0; i < m; i++) {
+    g->last_ms = std::max(g->last_ms, g->members[i]->last_ms);
+    if (rc[i]) { g->err = "member " + std::to_string(i) + " (device " + std::to_string(g->members[i]->device) + "): " + g->members[i]->err; return rc[i]; }
+  }
+  return 0;
+}
+}  // extern "C++"
+
+// All-pairs scene over the group: the body arrays go to every member, member i solves the i-th
+// contiguous slice of the i < j enumeration and writes its rows of the caller's (host) arrays.
+int dcol_group_scene_allpairs(dcol_group* g, int query, int n_bodies, const int32_t* shape, const double* r, const double* att,
+                              int att_kind, double pdip_tol,
+                              double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters) {
+  if (!g) return -1;
+  g->err.clear();
+  if (query != Q_PROX && query != Q_GRAD && query != Q_JAC) { g->err = "dcol_group_scene_allpairs: query must be 0 (proximity), 1 (gradient) or 2 (jacobian)"; return -1; }
+  if (att_kind != DCOL_ATT_QUAT && att_kind != DCOL_ATT_MRP) { g->err = "dcol: att_kind must be 0 (quaternion) or 1 (MRP)"; return -1; }
+  const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3, nt = 6 + 2 * na;
+  const int64_t dsz = (query == Q_GRAD) ? nt : (query == Q_JAC ? 4 * nt : 0);
+  auto off = [](auto* p, int64_t k) { return p ? p + k : p; };
+  return group_slices(g, dcol_scene_pair_count(n_bodies), [&](int i, int64_t b, int64_t e) {
+    if (e == b) return 0;
+    return dcol_scene_allpairs_range(g->members[i], query, n_bodies, b, e, shape, r, att, att_kind, pdip_tol, DCOL_MEM_HOST,
+                                     off(alpha, b), off(x, 3 * b), off(deriv, dsz * b), off(status, b), off(iters, b));
+  });
+}
+
+// Contact-scene accumulation over the group: every member reduces the pairs of its slice to per-body partial sums on its
+// device; the partial sums (n_bodies x 6 per member) are added on the host in member order -- the exchange step of
+// this operator.  The result differs from the one-device call by the summation order only.
+int dcol_group_scene_wrench(dcol_group* g, int n_bodies, const int32_t* shape, const double* r, const double* att, const double* lambda,
+                            int att_kind, double pdip_tol,
+                            double* alpha, double* wrench, int32_t* status, int32_t* iters) {
+  if (!g) return -1;
+  g->err.clear();
+  if (n_bodies < 0 || !wrench || !lambda) { g->err = "dcol_group_scene_wrench: bad arguments"; return -1; }
+  const int m = (int)g->members.size();
+  std::vector<double> part((size_t)m * 6 * (size_t)std::max(n_bodies, 0), 0.0);
+  auto off = [](auto* p, int64_t k) { return p ? p + k : p; };
+  const int rc = group_slices(g, dcol_scene_pair_count(n_bodies), [&](int i, int64_t b, int64_t e) {
+    if (e == b) return 0;
+    return dcol_scene_wrench_range(g->members[i], n_bodies, b, e, shape, r, att, lambda + b, att_kind, pdip_tol, DCOL_MEM_HOST,
+                                   off(alpha, b), part.data() + (size_t)i * 6 * n_bodies, off(status, b), off(iters, b));
+  });
+  if (rc) return rc;
+  for (int64_t k = 0; k < 6 * (int64_t)n_bodies; k++) {
+    double a = 0.0;
+    for (int i = 0; i < m; i++) a += part[(size_t)i * 6 * n_bodies + k];
+    wrench[k] = a;
   }
   return 0;
 }

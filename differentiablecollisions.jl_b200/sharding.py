@@ -44,6 +44,28 @@ def gather_rows(local, n_total: int, rank: int, world: int, group=None):
     return torch.cat([parts[r][: bounds[r][1] - bounds[r][0]] for r in range(world)], dim=0)
 
 
+def scene_wrench_sharded(ctx, rank: int, world: int, shape, r, att, lam, att_kind=0, pdip_tol=1e-6, group=None, device=None, per_pair=True):
+    """The contact-scene accumulation (`dcol_scene_wrench`, examples/contact_physics/ncp_contact_simulation.jl:133-139) over
+    `world` ranks: every rank holds the body arrays and the full weight vector `lam`, solves its contiguous slice of the
+    i<j enumeration on its own GPU (`dcol_scene_wrench_range`) and contributes per-body partial sums; ONE all-reduce (sum)
+    of the n_bodies x 6 partial sums is the exchange step of this operator (NCCL over NVLink when `device` is a CUDA
+    device, gloo on CPU tensors).  Returns (wrench on every rank, this rank's per-pair dict (alpha / status / iters of its slice unless per_pair=False), (k0, k1))."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    nb = int(np.asarray(shape).reshape(-1).shape[0])
+    k0, k1 = shard(nb * (nb - 1) // 2, rank, world)
+    lam = np.asarray(lam, dtype=np.float64).reshape(-1)
+    out = ctx.scene_wrench(shape, r, att, lam[k0:k1], att_kind, pdip_tol, per_pair=per_pair, pair_range=(k0, k1))
+    w = torch.from_numpy(out["wrench"])
+    if world > 1:
+        if device is not None:
+            w = w.to(device)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM, group=group)
+        w = w.cpu()
+    return w.numpy(), out, (k0, k1)
+
+
 def bind_to_gpu_numa_node(device_index: int) -> dict:
     """Best effort: pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers
     allocated afterwards are local to the GPU's PCIe root (matters when 8 ranks stream from host memory at once).

@@ -127,6 +127,14 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
                         int att_kind, double pdip_tol, int mem,
                         double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
 
+/* A slice [k_begin, k_end) of the same enumeration (the all-pairs scene shards by giving every GPU
+ * the body arrays and one contiguous slice of the pair indices).  Outputs have k_end - k_begin rows; row k belongs to
+ * pair k_begin + k.  Results are bit-identical to the corresponding rows of the whole call. */
+int dcol_scene_allpairs_range(dcol_ctx* ctx, int query, int n_bodies, int64_t k_begin, int64_t k_end,
+                              const int32_t* shape, const double* r, const double* att,
+                              int att_kind, double pdip_tol, int mem,
+                              double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
+
 /* Contact-scene accumulation: the loop of examples/contact_physics/ncp_contact_simulation.jl:133-139 as one call.  For
  * all pairs k = (i, j), i < j (order as above) with weights lambda[k] (the contact impulses of the caller's NCP):
  *     alpha[k]  = proximity_gradient(P_i, P_j)[1]
@@ -140,6 +148,14 @@ int dcol_scene_allpairs(dcol_ctx* ctx, int query, int n_bodies, const int32_t* s
 int dcol_scene_wrench(dcol_ctx* ctx, int n_bodies, const int32_t* shape, const double* r, const double* att, const double* lambda,
                       int att_kind, double pdip_tol, int mem,
                       double* alpha, double* wrench, int32_t* status, int32_t* iters);
+/* The part of that sum that comes from the pairs k_begin <= k < k_end: lambda, alpha, status, iters have k_end - k_begin
+ * rows, wrench is the full n_bodies*6 partial sum.  The partial sums of a partition of the pairs add up to the whole
+ * (the one exchange step of a sharded scene: dcol_group_scene_wrench adds them on the host, ranks under torchrun
+ * all-reduce them over NCCL -- dcol_b200.sharding.scene_wrench_sharded). */
+int dcol_scene_wrench_range(dcol_ctx* ctx, int n_bodies, int64_t k_begin, int64_t k_end,
+                            const int32_t* shape, const double* r, const double* att, const double* lambda,
+                            int att_kind, double pdip_tol, int mem,
+                            double* alpha, double* wrench, int32_t* status, int32_t* iters);
 
 /* Broad phase of the two scene operators above (opt-in: the reference's contact example,
  * examples/contact_physics/ncp_contact_simulation.jl:86-89,133-139, solves every pair).  Every primitive scales about its
@@ -271,7 +287,18 @@ int  dcol_group_query(dcol_group* g, int query, int64_t n, const int32_t* shape1
                       const double* r1, const double* att1, const double* r2, const double* att2,
                       int att_kind, double pdip_tol,
                       double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
-/* device time (ms) of the solver launches of the last dcol_group_query: the maximum over the members */
+/* The scene operators over the group (BASELINE config 4): the body arrays go to every member, member
+ * i takes the i-th contiguous slice of the i < j enumeration.  Per-pair rows land in the caller's (host) arrays and are
+ * bit-identical to the one-device call; the per-body wrench is the sum, in member order, of the members' partial sums
+ * (n_bodies x 6 each), so it equals the one-device result up to the order of summation.  A broad phase is set per
+ * member: dcol_scene_set_cull(dcol_group_ctx(g, i), alpha_cut). */
+int  dcol_group_scene_allpairs(dcol_group* g, int query, int n_bodies, const int32_t* shape, const double* r, const double* att,
+                               int att_kind, double pdip_tol,
+                               double* alpha, double* x, double* deriv, int32_t* status, int32_t* iters);
+int  dcol_group_scene_wrench(dcol_group* g, int n_bodies, const int32_t* shape, const double* r, const double* att, const double* lambda,
+                             int att_kind, double pdip_tol,
+                             double* alpha, double* wrench, int32_t* status, int32_t* iters);
+/* device time (ms) of the solver launches of the last group call: the maximum over the members */
 double dcol_group_last_kernel_ms(const dcol_group* g);
 
 #ifdef __cplusplus

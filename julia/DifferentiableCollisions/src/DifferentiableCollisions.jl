@@ -211,7 +211,7 @@ function __init__()
     _ctx[] = h[]
     atexit(() -> ccall((:dcol_destroy, _lib[]), Cvoid, (Ptr{Cvoid},), _ctx[]))
     # DCOL_B200_DEVICES=0,1,2,...: the batched queries (proximity_batch, ...) are cut into one index slice per listed GPU
-    # and run concurrently from this process (dcol_group_query); single-pair calls and the operators stay on _ctx
+    # and run concurrently from this process (dcol_group_query); single-pair calls and dcol_se2_constraints stay on _ctx
     devs = Cint[parse(Cint, d) for d in split(get(ENV, "DCOL_B200_DEVICES", ""), ','; keepempty = false)]
     if length(devs) > 1
         g = Ref{Ptr{Cvoid}}(C_NULL)
@@ -291,6 +291,15 @@ function scene_allpairs(kind::Integer, shape::Vector{Int32}, r::Matrix{Float64},
     α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
     x = Matrix{Float64}(undef, 3, kind == 1 ? 0 : n)
     deriv = kind == 0 ? Float64[] : (kind == 1 ? Matrix{Float64}(undef, nt, n) : Array{Float64}(undef, 4, nt, n))
+    if _grp[] != C_NULL      # several GPUs (DCOL_B200_DEVICES): every member solves one slice of the pair enumeration
+        rc = ccall((:dcol_group_scene_allpairs, _lib[]), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                   _grp[], kind, nb, shape, r, att, na == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol),
+                   α, kind == 1 ? C_NULL : x, kind == 0 ? C_NULL : deriv, status, iters)
+        rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_group_last_error, _lib[]), Cstring, (Ptr{Cvoid},), _grp[])))
+        return BatchResult(α, x, deriv, status, iters)
+    end
     _check(ccall((:dcol_scene_allpairs, _lib[]), Cint,
                  (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
                   Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
@@ -313,6 +322,14 @@ function scene_wrench(shape::Vector{Int32}, r::Matrix{Float64}, att::Matrix{Floa
     length(λ) == n || error("scene_wrench: λ must have one entry per pair ($n)")
     α = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); iters = Vector{Int32}(undef, n)
     wrench = Matrix{Float64}(undef, 6, nb)
+    if _grp[] != C_NULL      # per-body partial sums of the members' pair slices, added in member order
+        rc = ccall((:dcol_group_scene_wrench, _lib[]), Cint,
+                   (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                   _grp[], nb, shape, r, att, λ, na == 4 ? ATT_QUAT : ATT_MRP, Float64(pdip_tol), α, wrench, status, iters)
+        rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_group_last_error, _lib[]), Cstring, (Ptr{Cvoid},), _grp[])))
+        return α, wrench, status, iters
+    end
     _check(ccall((:dcol_scene_wrench, _lib[]), Cint,
                  (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
                   Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
@@ -442,7 +459,15 @@ function solve_socp(c::AbstractVector, G::AbstractMatrix, h::AbstractVector, idx
 end
 
 "`scene_set_cull!(α_cut)`: opt-in broad phase of `scene_allpairs` / `scene_wrench` (`dcol_scene_set_cull`); pairs proven to have α > α_cut come back with status 3 and a lower bound of α.  0 switches it off."
-scene_set_cull!(α_cut::Real) = (_check(ccall((:dcol_scene_set_cull, _lib[]), Cint, (Ptr{Cvoid}, Float64), _ctx[], Float64(α_cut))); nothing)
+function scene_set_cull!(α_cut::Real)
+    _check(ccall((:dcol_scene_set_cull, _lib[]), Cint, (Ptr{Cvoid}, Float64), _ctx[], Float64(α_cut)))
+    if _grp[] != C_NULL
+        for i in 0:(ccall((:dcol_group_size, _lib[]), Cint, (Ptr{Cvoid},), _grp[]) - 1)
+            ccall((:dcol_scene_set_cull, _lib[]), Cint, (Ptr{Cvoid}, Float64), ccall((:dcol_group_ctx, _lib[]), Ptr{Cvoid}, (Ptr{Cvoid}, Cint), _grp[], i), Float64(α_cut))
+        end
+    end
+    nothing
+end
 
 "`set_mu_output!(μ)`: the following host-pointer queries also return the final duality measure per pair in `μ` (a `Vector{Float64}` the caller keeps alive); `nothing` switches it off."
 set_mu_output!(μ::Union{Vector{Float64},Nothing}) =

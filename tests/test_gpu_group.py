@@ -66,3 +66,57 @@ def test_group_shape_table_and_errors(ctx):
         g.close()
     with pytest.raises(RuntimeError, match="device"):
         dc.Group([4096])
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+def test_scene_slices_and_group_scene(ctx, att_kind):
+    """SURVEY.md 8e for the all-pairs scene: every device gets the body arrays and one contiguous slice of the i<j
+    enumeration (dcol_scene_allpairs_range / dcol_scene_wrench_range).  Slices are bit-identical to the rows of the whole
+    call, with and without the broad phase; the per-body partial sums of a partition add up to the whole; the group
+    operators do exactly that over their members."""
+    from test_gpu_operators import scene_bodies
+    nb = 211
+    t, shape, r, att = scene_bodies(nb, att_kind, spread=3.0)
+    n = nb * (nb - 1) // 2
+    lam = util.rng(5).uniform(0.0, 2.0, n)
+    cuts = [0, 1, 5000, 5001, 17000, n]
+    g = dc.Group(_devices(3))
+    try:
+        ctx.set_shape_arrays(*t.arrays()); g.set_shape_arrays(*t.arrays())
+        for cull in (0.0, 1.5):
+            ctx.scene_set_cull(cull); g.scene_set_cull(cull)
+            for kind in (0, 1, 2):
+                whole = ctx.scene_allpairs(kind, shape, r, att, att_kind)
+                if cull:
+                    assert (whole["status"] == 3).any() and (whole["status"] == 0).any()
+                for k0, k1 in zip(cuts[:-1], cuts[1:]):
+                    part = ctx.scene_allpairs(kind, shape, r, att, att_kind, pair_range=(k0, k1))
+                    _same(part, {k: v[k0:k1] for k, v in whole.items()})
+                _same(g.scene_allpairs(kind, shape, r, att, att_kind), whole)
+            w = ctx.scene_wrench(shape, r, att, lam, att_kind)
+            acc = np.zeros((nb, 6))
+            for k0, k1 in zip(cuts[:-1], cuts[1:]):
+                p = ctx.scene_wrench(shape, r, att, lam[k0:k1], att_kind, pair_range=(k0, k1))
+                for k in ("alpha", "status", "iters"):
+                    assert np.array_equal(p[k], w[k][k0:k1]), k
+                acc += p["wrench"]
+            scale = np.abs(w["wrench"]).max()
+            assert np.abs(acc - w["wrench"]).max() < 1e-12 * scale          # same terms, another order of summation
+            gw = g.scene_wrench(shape, r, att, lam, att_kind)
+            for k in ("alpha", "status", "iters"):
+                assert np.array_equal(gw[k], w[k]), k
+            assert np.abs(gw["wrench"] - w["wrench"]).max() < 1e-12 * scale
+            assert np.array_equal(g.scene_wrench(shape, r, att, lam, att_kind, per_pair=False)["wrench"], gw["wrench"])   # reproducible
+        empty = ctx.scene_wrench(shape, r, att, np.zeros(0), att_kind, pair_range=(7, 7))
+        assert (empty["wrench"] == 0).all() and empty["alpha"].shape == (0,)
+        with pytest.raises(ValueError):
+            ctx.scene_allpairs(0, shape, r, att, att_kind, pair_range=(5, n + 1))
+        # the C entry checks the range itself
+        import ctypes as C
+        a = np.empty(4); s = np.empty(4, np.int32)
+        rc = ctx._lib.dcol_scene_allpairs_range(ctx._h, 0, nb, n - 1, n + 3, shape.ctypes.data, r.ctypes.data, att.ctypes.data, att_kind, 1e-6, 0,
+                                                a.ctypes.data, np.empty((4, 3)).ctypes.data, None, s.ctypes.data, None)
+        assert rc == -1 and b"k_begin" in ctx._lib.dcol_last_error(ctx._h)
+    finally:
+        ctx.scene_set_cull(0.0)
+        g.close()

@@ -20,6 +20,7 @@ torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of 
   e2e.copy_bound : the same end-to-end loop with the kernels switched off (dcol_set_copy_only): what the host can feed
   scene        : the same proximity workload on the reference's contact-example shapes (8-face fixture polytope,
                  Capsule(0.2, 5.0)): kernel time, roofline fraction, mean iterations
+  large_batch  : the same workload at 8 M pairs per GPU in one call (fixed part of a step amortised): kernel ms per 1 M pairs
   latency      : wall time of single-pair and config-1 (10k cube-cube) calls through the Python wrapper
 
 `--impl reference` times the reference's CPU implementation of the path; Julia is not in the image, so
@@ -53,6 +54,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="proximity pairs per GPU per step (config 2)")
     ap.add_argument("--jac-pairs", type=int, default=2_000_000, help="proximity_jacobian pairs per GPU per step (config 3)")
     ap.add_argument("--no-jacobian", action="store_true")
+    ap.add_argument("--no-large", action="store_true", help="skip the 8x larger batch (large_batch object)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="cube", choices=["cube", "scene"])
     ap.add_argument("--profile", action="store_true",
@@ -369,6 +371,9 @@ def main():
     prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234, e2e=not args.profile)
     other = "scene" if args.variant == "cube" else "cube"
     prox2 = None if args.profile else run_config(0, dc.ATT_QUAT, args.pairs, max(3, args.steps // 4), args.warmup, 1234, variant=other, e2e=False)
+    # the same workload at 8 M pairs per GPU: what the solver does once the fixed part of a step (first tiles, class-pair
+    # transitions of the tile queue, the tail of the last tiles and the resume launches: ~0.14 ms) is amortised
+    big = None if (args.profile or args.no_large) else run_config(0, dc.ATT_QUAT, 8 * args.pairs, 3, 3, 1234, e2e=False)
     jac = None
     if not args.no_jacobian:
         jac = run_config(2, dc.ATT_MRP, args.jac_pairs, max(2, args.steps // 2), args.warmup, 4321, e2e=not args.profile)
@@ -476,6 +481,14 @@ def main():
                                       "roofline_frac": r2["frac"], "achieved_tflops": r2["achieved"],
                                       "algorithmic_flops_per_pair": r2["algorithmic_flops_per_pair"],
                                       "mean_iters": prox2["mean_iters"], "max_iters": prox2["max_iters"], "failed_pairs": prox2["failed"]}
+        if big:
+            rb = roof(big, "proximity_large")
+            line["large_batch"] = {"what": "same workload, %d pairs per GPU in one call (the fixed part of a step amortised)" % big["n"],
+                                   "value": world * big["n"] * big["steps"] / (big["dev_ms"] * 1e-3), "unit": UNIT,
+                                   "ms_per_step": big["dev_ms"] / big["steps"], "kernel_ms_per_step": big["kernel_ms"],
+                                   "kernel_ms_per_1M_pairs": big["kernel_ms"] / (big["n"] / 1e6),
+                                   "roofline_frac": rb["frac"], "achieved_tflops": rb["achieved"], "mean_iters": big["mean_iters"],
+                                   "failed_pairs": big["failed"]}
         if latency:
             line["latency"] = latency
         if prox.get("gather"):

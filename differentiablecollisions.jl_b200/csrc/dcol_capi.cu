@@ -1084,9 +1084,6 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
     // Row capacities of the shared-memory tiers.  Up to 16 rows per pair two 4-warp CTAs fit an SM (the register limit's
     // 8 warps); the <= 8 and <= 16 row tiers stay separate launches all the same: the smaller row store leaves the SM a
     // larger L1 for the spilled registers (measured -1 % proximity, -2.5 % Jacobian against one merged tier).
-    // Row capacities of the shared-memory tiers.  Up to 16 rows per pair two 4-warp CTAs fit an SM (the register limit's
-    // 8 warps); the <= 8 and <= 16 row tiers stay separate launches all the same: the smaller row store leaves the SM a
-    // larger L1 for the spilled registers (measured -1 % proximity, -2.5 % Jacobian against one merged tier).
     const int cap_max = (MAX_SMEM - 1024) / (NFIELD * (int)sizeof(double) * 32) - 8;
     std::vector<int> tier_cap = {8, 16, 32, 64, 128};
     if (const char* e = getenv("DCOL_TIERS")) {          // tuning knob: comma-separated row capacities
@@ -1639,6 +1636,7 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     const bool one_launch = small && ctx->has_small;
     const int n_launch = one_launch ? 1 : nt_tiers;
     if (n_launch > 1) CK(cudaEventRecord(ctx->ev_join[NSIDE - 1], SC));
+    // (tiers in ascending row capacity; launching the heavier tier first was measured 0.5-1 % slower, profiles/r02_variants.txt)
     for (int t = 0; t < n_launch && !ctx->copy_only; t++) {
       const dcol_ctx::Tier& TR = one_launch ? ctx->small_tier : ctx->tiers[t];
       cudaStream_t st = (n_launch == 1) ? SC : ctx->side[t % NSIDE];

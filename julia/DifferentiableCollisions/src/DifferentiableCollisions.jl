@@ -415,9 +415,8 @@ unpin!(a::Array) = (_check(ccall((:dcol_host_unregister, _lib[]), Cint, (Ptr{Cvo
 
 Same call as the reference's `solve_socp` (`src/solvers/coneqp/static_solver2.jl:106-191`); rows of `G`, `h` must be
 ordered `[idx_ort; idx_soc1; idx_soc2]` as `combine_problem_matrices` produces them.  Runs `dcol_solve_socp` on one problem;
-`verbose = true` runs `dcol_solve_socp_trace` and prints the reference's per-iteration table.  The single-pair calls below
-accept `verbose` and ignore it (the fast kernels never form `G`): pass the pair's `combine_problem_matrices(...)` here
-for the table.
+`verbose = true` runs `dcol_solve_socp_trace` and prints the reference's per-iteration table; the single-pair calls below
+do that on the pair's dense problem (`pair_problem`) when called with `verbose = true`.
 """
 # "%W.De" without a dependency on Printf: mantissa with D decimals, two-digit exponent, right-aligned in W characters
 function _e(v::Float64, w::Int, d::Int)
@@ -480,9 +479,64 @@ set_warm_start!(state::Ptr{Float64}, capacity_pairs::Integer; mu_save = 1e-2) =
 
 
 # ---------------------------------------------------------------------------------------------
+# dense conic form of one pair (host side; only `verbose = true` and users of `solve_socp` need it: the batched
+# kernels never form G).  Same blocks as src/problem_matrices.jl:30-191 and src/combine_problem_matrices.jl:15-86,
+# with plain `Matrix` / `Vector` instead of static arrays: rows `h - G*y` in the orthant, then in a second-order
+# cone; `y = [x; α; extra variables of primitive 1; extra variables of primitive 2]`.
+# ---------------------------------------------------------------------------------------------
+_dcm(P::AbstractPrimitive) = Matrix(dcm_from_q(P.q))
+_dcm(P::AbstractPrimitiveMRP) = Matrix(dcm_from_mrp(P.p))
+function _ball_block(R, r, E)                    # SOC rows [R α; x - r - E e]
+    G = zeros(4, 4 + size(E, 2)); G[1, 4] = -R
+    for i in 1:3; G[1 + i, i] = -1.0; end
+    G[2:4, 5:end] .= E
+    return G, vcat(0.0, -r)
+end
+function problem_matrices(P::AnyPrimitive)
+    Qn = _dcm(P); r = Vector(P.r) + Qn * Vector(P.r_offset); Q = Qn * Matrix(P.Q_offset)
+    t = shape_type(P); bx = Q[:, 1]
+    if t == 0                                                        # polytope: A Q'(x - r) <= α b
+        AQt = Matrix(P.A) * Q'
+        return hcat(AQt, -Vector(P.b)), AQt * r, zeros(0, 4), zeros(0)
+    elseif t == 4                                                    # sphere
+        G, h = _ball_block(P.R, r, zeros(3, 0)); return zeros(0, 4), zeros(0), G, h
+    elseif t == 1 || t == 2                                          # capsule / cylinder: axis point r + γ bx, |γ| <= α L/2
+        G, h = _ball_block(P.R, r, reshape(bx, 3, 1))
+        Go = [0 0 0 -P.L/2 1.0; 0 0 0 -P.L/2 -1.0]; ho = zeros(2)
+        if t == 2                                                    # the two end planes
+            Go = vcat(Go, hcat(-bx', -P.L / 2, 0.0), hcat(bx', -P.L / 2, 0.0)); ho = [0.0, 0.0, -dot(bx, r), dot(bx, r)]
+        end
+        return Go, ho, G, h
+    elseif t == 3                                                    # cone
+        tb = tan(P.β); EQt = Diagonal([tb, 1.0, 1.0]) * Q'
+        return hcat(bx', -P.H / 4), [dot(bx, r)], hcat(-EQt, [-tb * 3 * P.H / 4, 0.0, 0.0]), -EQt * r
+    elseif t == 6                                                    # padded polygon: in-plane point r + Q[:,1:2] e, A e <= α b
+        nh = size(P.A, 1); G, h = _ball_block(P.R, r, Q[:, 1:2])
+        return hcat(zeros(nh, 3), -Vector(P.b), Matrix(P.A)), zeros(nh), G, h
+    else                                                             # ellipsoid: |U Q'(x - r)| <= α
+        UQt = Matrix(P.U) * Q'; G = zeros(4, 4); G[1, 4] = -1.0; G[2:4, 1:3] .= -UQt
+        return zeros(0, 4), zeros(0), G, vcat(0.0, -UQt * r)
+    end
+end
+function combine_problem_matrices(Go1, ho1, Gs1, hs1, Go2, ho2, Gs2, hs2)
+    e1 = max(size(Go1, 2), size(Gs1, 2)) - 4; e2 = max(size(Go2, 2), size(Gs2, 2)) - 4; nx = 4 + e1 + e2
+    function widen(B, first, ne)
+        out = zeros(size(B, 1), nx); out[:, 1:4] .= B[:, 1:4]; out[:, first:first+ne-1] .= B[:, 5:4+ne]; out
+    end
+    G = vcat(widen(Go1, 5, e1), widen(Go2, 5 + e1, e2), widen(Gs1, 5, e1), widen(Gs2, 5 + e1, e2))
+    h = vcat(ho1, ho2, hs1, hs2); c = zeros(nx); c[4] = 1.0
+    no = size(Go1, 1) + size(Go2, 1); d1 = size(Gs1, 1); d2 = size(Gs2, 1)
+    return c, G, h, collect(1:no), collect(no+1:no+d1), collect(no+d1+1:no+d1+d2)
+end
+pair_problem(P1::AnyPrimitive, P2::AnyPrimitive) = combine_problem_matrices(problem_matrices(P1)..., problem_matrices(P2)...)
+
+# ---------------------------------------------------------------------------------------------
 # single-pair drop-in calls: a batch of one through the same entry points
 # ---------------------------------------------------------------------------------------------
-function _single(sym, P1, P2, pdip_tol)
+function _single(sym, P1, P2, pdip_tol, verbose = false)
+    # verbose (static_solver2.jl:117-120, 179-183): the iteration table comes from the pair's dense problem solved by
+    # dcol_solve_socp_trace; the values returned below are the fast path's
+    verbose && solve_socp(pair_problem(P1, P2)...; pdip_tol = pdip_tol, verbose = true)
     set_shapes!(ShapeTable([P1, P2]))
     col(v) = reshape(collect(Float64, v), :, 1)
     res = _query(sym, Int32[0], Int32[1], col(P1.r), col(att(P1)), col(P2.r), col(att(P2)), att_kind(P1), Float64(pdip_tol))
@@ -494,15 +548,15 @@ end
 for (PT, nt) in ((:AbstractPrimitive, 14), (:AbstractPrimitiveMRP, 12))
     @eval begin
         function proximity(prim1::$PT, prim2::$PT; pdip_tol::Float64 = 1e-6, verbose::Bool = false)
-            res = _single(:dcol_proximity, prim1, prim2, pdip_tol)
+            res = _single(:dcol_proximity, prim1, prim2, pdip_tol, verbose)
             return res.α[1], SVector{3}(res.x[:, 1])
         end
         function proximity_gradient(prim1::$PT, prim2::$PT; pdip_tol::Float64 = 1e-6, verbose::Bool = false)
-            res = _single(:dcol_proximity_gradient, prim1, prim2, pdip_tol)
+            res = _single(:dcol_proximity_gradient, prim1, prim2, pdip_tol, verbose)
             return res.α[1], SVector{$nt}(res.deriv[:, 1])
         end
         function proximity_jacobian(prim1::$PT, prim2::$PT; pdip_tol::Float64 = 1e-6, verbose::Bool = false)
-            res = _single(:dcol_proximity_jacobian, prim1, prim2, pdip_tol)
+            res = _single(:dcol_proximity_jacobian, prim1, prim2, pdip_tol, verbose)
             return res.α[1], SVector{3}(res.x[:, 1]), SMatrix{4,$nt}(res.deriv[:, :, 1])
         end
     end

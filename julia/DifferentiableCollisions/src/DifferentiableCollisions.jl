@@ -192,7 +192,26 @@ end
 
 _check(rc) = rc == 0 || error("dcol_b200: " * unsafe_string(ccall((:dcol_last_error, _lib[]), Cstring, (Ptr{Cvoid},), _ctx[])))
 
+# Registry behind the single-pair calls: primitives with identical geometry share one shape id, and the device table
+# is uploaded again only when a shape was added or a caller's own table replaced it (the reference's examples call
+# `proximity` in their inner loops with the same handful of shapes: no upload per call).
+const _reg = ShapeTable(Cint[], Int64[], Float64[])
+const _reg_ids = Dict{Tuple{Cint,Vector{Float64}},Int32}()
+const _reg_on_device = Ref(false)
+function _registered!(P)::Int32
+    key = (shape_type(P), shape_params(P))
+    id = get(_reg_ids, key, Int32(-1))
+    if id < 0
+        id = Int32(length(_reg.types))
+        push!(_reg.types, key[1]); push!(_reg.offs, length(_reg.params)); append!(_reg.params, key[2])
+        _reg_ids[key] = id
+        _reg_on_device[] = false
+    end
+    return id
+end
+
 function set_shapes!(t::ShapeTable)
+    _reg_on_device[] = (t === _reg)
     _check(ccall((:dcol_set_shapes, _lib[]), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Int64}, Ptr{Float64}, Int64),
                  _ctx[], length(t.types), t.types, t.offs, t.params, length(t.params)))
     if _grp[] != C_NULL
@@ -537,9 +556,10 @@ function _single(sym, P1, P2, pdip_tol, verbose = false)
     # verbose (static_solver2.jl:117-120, 179-183): the iteration table comes from the pair's dense problem solved by
     # dcol_solve_socp_trace; the values returned below are the fast path's
     verbose && solve_socp(pair_problem(P1, P2)...; pdip_tol = pdip_tol, verbose = true)
-    set_shapes!(ShapeTable([P1, P2]))
+    s1 = _registered!(P1); s2 = _registered!(P2)
+    _reg_on_device[] || set_shapes!(_reg)
     col(v) = reshape(collect(Float64, v), :, 1)
-    res = _query(sym, Int32[0], Int32[1], col(P1.r), col(att(P1)), col(P2.r), col(att(P2)), att_kind(P1), Float64(pdip_tol))
+    res = _query(sym, Int32[s1], Int32[s2], col(P1.r), col(att(P1)), col(P2.r), col(att(P2)), att_kind(P1), Float64(pdip_tol))
     res.status[1] == 1 && error("pdip failed")                        # static_solver2.jl:188
     res.status[1] == 0 || throw(DomainError(res.status[1], "numerical breakdown in the conic solver"))
     return res

@@ -62,6 +62,7 @@ class Context:
         self.device = int(device)
         self.table = ShapeTable()
         self._table_version = -1
+        self._one_bufs = {}          # preallocated arrays and pointers of the single-pair calls, per attitude kind
 
     def close(self):
         if getattr(self, "_h", None):
@@ -217,6 +218,33 @@ class Context:
     def set_max_iters(self, k: int = 50):
         """Testing knob (dcol_set_max_iters): iteration cap of the solver, 50 in the reference and by default."""
         self._check(self._lib.dcol_set_max_iters(self._h, int(k)))
+
+    def _one(self, kind, s1, s2, prim1, prim2, pdip_tol):
+        """One pair through preallocated buffers (the single-pair drop-in calls sit in the inner loops of the reference's
+        examples: no array allocation, conversion or pointer construction per call).  Same entry points as `_batch`."""
+        att_kind = prim1.att_kind
+        b = self._one_bufs.get(att_kind)
+        if b is None:
+            na = 4 if att_kind == ATT_QUAT else 3
+            nt = 6 + 2 * na
+            a = {"s1": np.empty(1, np.int32), "s2": np.empty(1, np.int32), "r1": np.empty((1, 3)), "a1": np.empty((1, na)),
+                 "r2": np.empty((1, 3)), "a2": np.empty((1, na)), "alpha": np.empty(1), "x": np.empty((1, 3)),
+                 "grad": np.empty((1, nt)), "J": np.empty((1, nt, 4)), "status": np.empty(1, np.int32), "iters": np.empty(1, np.int32)}
+            b = self._one_bufs[att_kind] = (a, {k: _ptr(v) for k, v in a.items()})
+        a, q = b
+        a["s1"][0] = s1; a["s2"][0] = s2
+        a["r1"][0] = prim1.r; a["a1"][0] = prim1.att; a["r2"][0] = prim2.r; a["a2"][0] = prim2.att
+        if self._table_version is not None:
+            self.sync_shapes()
+        args = (self._h, 1, q["s1"], q["s2"], q["r1"], q["a1"], q["r2"], q["a2"], att_kind, float(pdip_tol), MEM_HOST)
+        if kind == 0:
+            rc = self._lib.dcol_proximity(*args, q["alpha"], q["x"], q["status"], q["iters"])
+        elif kind == 1:
+            rc = self._lib.dcol_proximity_gradient(*args, q["alpha"], q["grad"], q["status"], q["iters"])
+        else:
+            rc = self._lib.dcol_proximity_jacobian(*args, q["alpha"], q["x"], q["J"], q["status"], q["iters"])
+        self._check(rc)
+        return a
 
     def _batch(self, kind, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out=None, want_mu=False):
         shape1 = np.ascontiguousarray(shape1, dtype=np.int32).reshape(-1)
@@ -534,7 +562,7 @@ def _single(kind, prim1, prim2, pdip_tol, ctx, verbose=False):
         # dcol_solve_socp_trace on the GPU: the same iterates up to round-off; the values returned below are the fast path's.
         ctx.solve_socp(*pair_problem(prim1, prim2), pdip_tol=pdip_tol, verbose=True)
     s1, s2 = ctx.add_shape(prim1), ctx.add_shape(prim2)
-    out = ctx._batch(kind, [s1], [s2], prim1.r, prim1.att, prim2.r, prim2.att, prim1.att_kind, pdip_tol)
+    out = ctx._one(kind, s1, s2, prim1, prim2, pdip_tol)
     st = int(out["status"][0])
     if st == 1:
         raise RuntimeError("pdip failed")
@@ -555,4 +583,4 @@ def proximity_gradient(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = Fal
 
 def proximity_jacobian(prim1, prim2, pdip_tol: float = 1e-6, verbose: bool = False, ctx: Context | None = None):
     out = _single(2, prim1, prim2, pdip_tol, ctx, verbose)
-    return float(out["alpha"][0]), out["x"][0].copy(), out["J"][0].copy()
+    return float(out["alpha"][0]), out["x"][0].copy(), out["J"][0].T.copy()      # (4, nt) from the column-major C layout

@@ -20,6 +20,10 @@ TYPE_NAMES = ["polytope", "capsule", "cylinder", "cone", "sphere", "ellipsoid", 
 ATT_QUAT, ATT_MRP = 0, 1
 
 
+def _bytes(x):
+    return x.tobytes() if type(x) is np.ndarray and x.dtype == np.float64 else np.asarray(x, dtype=np.float64).tobytes()
+
+
 def _vec(x, n):
     a = np.asarray(x, dtype=np.float64).reshape(-1)
     if a.shape[0] != n:
@@ -54,7 +58,11 @@ class AbstractPrimitive:
                                np.asarray(self.Q_offset, dtype=np.float64).reshape(9)])
 
     def shape_key(self):
-        return (self.shape_type, self.packed().tobytes())
+        """Identity of the geometry (shape-table de-duplication); cheaper than packing: this sits in every single-pair call."""
+        return (self.shape_type,) + self._geom_key() + (_bytes(self.r_offset), _bytes(self.Q_offset))
+
+    def _geom_key(self):
+        return (self.shape_params().tobytes(),)
 
 
 class AbstractPrimitiveMRP(AbstractPrimitive):
@@ -76,6 +84,9 @@ class _PolytopeBase:
     def shape_params(self):
         return np.concatenate([[float(self.A.shape[0])], self.A.reshape(-1), self.b])
 
+    def _geom_key(self):
+        return (_bytes(self.A), _bytes(self.b))
+
 
 class _CapsuleBase:
     shape_type = CAPSULE
@@ -86,6 +97,9 @@ class _CapsuleBase:
 
     def shape_params(self):
         return np.array([self.R, self.L])
+
+    def _geom_key(self):
+        return (float(self.R), float(self.L))
 
 
 class _CylinderBase(_CapsuleBase):
@@ -106,6 +120,9 @@ class _ConeBase:
     def shape_params(self):
         return np.array([self.H, self.beta])
 
+    def _geom_key(self):
+        return (float(self.H), float(self.beta))
+
 
 class _SphereBase:
     shape_type = SPHERE
@@ -116,6 +133,9 @@ class _SphereBase:
 
     def shape_params(self):
         return np.array([self.R])
+
+    def _geom_key(self):
+        return (float(self.R),)
 
 
 class _PolygonBase:
@@ -131,6 +151,9 @@ class _PolygonBase:
 
     def shape_params(self):
         return np.concatenate([[float(self.A.shape[0])], self.A.reshape(-1), self.b, [self.R]])
+
+    def _geom_key(self):
+        return (_bytes(self.A), _bytes(self.b), float(self.R))
 
 
 class _EllipsoidBase:

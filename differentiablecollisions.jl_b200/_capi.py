@@ -49,6 +49,8 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_se2_constraints": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcol_se3_constraints": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcol_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "dcol_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcol_solve_socp": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

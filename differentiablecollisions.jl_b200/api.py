@@ -379,6 +379,25 @@ class Context:
                                                    float(pdip_tol), MEM_HOST, _ptr(c), _ptr(Jc), _ptr(status)))
         return {"c": c, "Jc": Jc, "status": status}
 
+    def se3_constraints(self, states, vehicle_shape, obs_shape, r_obs, p_obs, r_col=0, p_col=6, pdip_tol=1e-6):
+        """`dcol_se3_constraints`: `ineq_con_x` / `ineq_con_x_jac` of examples/trajectory_optimization/cone_through_wall.jl:56-68
+        and cluttered_hallway_quadrotor.jl:83-104 for a batch of states (n, stride) whose columns r_col.. / p_col.. hold the
+        vehicle's position / MRP, against K obstacles: c = 1 - alpha (n, K) and the non-zero blocks of the constraint
+        Jacobian rows, Jc[..., :3] = -d alpha/d r, Jc[..., 3:] = -d alpha/d p (n, K, 6)."""
+        if self._table_version is not None:
+            self.sync_shapes()
+        X = np.ascontiguousarray(states, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("states must be (n, stride)")
+        n, stride = X.shape
+        obs_shape = np.ascontiguousarray(obs_shape, dtype=np.int32).reshape(-1)
+        K = obs_shape.shape[0]
+        r_obs = np.ascontiguousarray(r_obs, dtype=np.float64).reshape(K, 3); p_obs = np.ascontiguousarray(p_obs, dtype=np.float64).reshape(K, 3)
+        c = np.empty((n, K)); Jc = np.empty((n, K, 6)); status = np.empty((n, K), dtype=np.int32)
+        self._check(self._lib.dcol_se3_constraints(self._h, n, _ptr(X), int(stride), int(r_col), int(p_col), int(vehicle_shape), K, _ptr(obs_shape),
+                                                   _ptr(r_obs), _ptr(p_obs), float(pdip_tol), MEM_HOST, _ptr(c), _ptr(Jc), _ptr(status)))
+        return {"c": c, "Jc": Jc, "status": status}
+
     def proximity_batch(self, shape1, shape2, r1, att1, r2, att2, att_kind=ATT_QUAT, pdip_tol=1e-6, out=None):
         return self._batch(0, shape1, shape2, r1, att1, r2, att2, att_kind, pdip_tol, out)
 

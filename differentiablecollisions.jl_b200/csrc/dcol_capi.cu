@@ -689,6 +689,34 @@ __global__ void k_se2_rows(int64_t np, int n_obs, const double* __restrict__ xyt
   }
 }
 
+// Rigid vehicle against static obstacles (examples/trajectory_optimization/cone_through_wall.jl:56-68,
+// cluttered_hallway_quadrotor.jl:83-104): every state row holds the vehicle's position at columns r_col.. and its MRP at
+// p_col.. (the examples' 12-state [r; v; p; omega]: r_col 0, p_col 6); pair k = state * n_obs + obstacle.
+__global__ void k_se3_pairs(int64_t n_states, int n_obs, const double* __restrict__ X, int stride, int r_col, int p_col, int32_t vehicle,
+                            const int32_t* __restrict__ obs_shape, double* __restrict__ r1, double* __restrict__ p1,
+                            int32_t* __restrict__ s1, int32_t* __restrict__ s2, int32_t* __restrict__ i1, int32_t* __restrict__ i2) {
+  const int64_t np = n_states * n_obs;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = k / n_obs; const int o = (int)(k - s * n_obs);
+    s1[k] = vehicle; s2[k] = obs_shape[o]; i1[k] = (int32_t)s; i2[k] = o;
+    if (o == 0) {
+      const double* x = X + (int64_t)stride * s;
+#pragma unroll
+      for (int a = 0; a < 3; a++) { r1[3 * s + a] = x[r_col + a]; p1[3 * s + a] = x[p_col + a]; }
+    }
+  }
+}
+// c = 1 - alpha ; the non-zero columns of the examples' constraint Jacobian rows: -d alpha/d r1, -d alpha/d p1
+__global__ void k_se3_rows(int64_t np, const double* __restrict__ alpha, const double* __restrict__ grad, double* __restrict__ c, double* __restrict__ Jc) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+    const double* g = grad + 12 * k;
+    c[k] = 1.0 - alpha[k];
+    if (Jc) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) Jc[6 * k + a] = -g[a]; }
+  }
+}
+
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure): 8 independent
 // chains per thread, 16 rounds per loop trip (128 DFMA against 3 loop instructions).  Under ncu the pipe reads 98 %
 // active; the round-1 probe (8 DFMA per trip as written, 32 after the compiler's unrolling) read 91 % and understated the
@@ -2049,6 +2077,73 @@ int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta,
     std::vector<CopyJob> items;
     items.push_back({(char*)c, (const char*)d_c, sizeof(double) * (size_t)np});
     if (Jc) items.push_back({(char*)Jc, (const char*)d_J, sizeof(double) * 3 * (size_t)np});
+    if (status) items.push_back({(char*)status, (const char*)d_status, sizeof(int32_t) * (size_t)np});
+    return results_to_host(ctx, S, items);
+  }
+  CK(cudaStreamSynchronize(S));
+  return 0;
+}
+
+int dcol_se3_constraints(dcol_ctx* ctx, int64_t n_states, const double* states, int state_stride, int r_col, int p_col,
+                         int32_t vehicle_shape, int n_obs, const int32_t* obs_shape, const double* r_obs, const double* p_obs,
+                         double pdip_tol, int mem, double* c, double* Jc, int32_t* status) {
+  if (!ctx) return -1;
+  ctx->err.clear();
+  if (n_states < 0 || n_obs < 0 || !states || !obs_shape || !r_obs || !p_obs || !c) { ctx->err = "dcol_se3_constraints: bad arguments"; return -1; }
+  if (state_stride < 6 || r_col < 0 || p_col < 0 || r_col + 3 > state_stride || p_col + 3 > state_stride ||
+      (r_col < p_col + 3 && p_col < r_col + 3)) { ctx->err = "dcol_se3_constraints: position and MRP columns must be disjoint triples inside a state row"; return -1; }
+  if (mem != DCOL_MEM_HOST && mem != DCOL_MEM_DEVICE) { ctx->err = "dcol: mem must be 0 (host) or 1 (device)"; return -1; }
+  const int64_t np = n_states * (int64_t)n_obs;
+  if (np == 0) return 0;
+  if (np > 0x7fffffff) { ctx->err = "dcol_se3_constraints: too many pairs for one call"; return -1; }
+  CK(cudaSetDevice(ctx->device));
+  { int rc = drain_all(ctx); if (rc) return rc; }
+  cudaStream_t S = ctx->stream();
+  const bool host = (mem == DCOL_MEM_HOST);
+  // device scratch: gradient rows | alpha | c | status | vehicle poses (r, p) | (host mode) states, Jc
+  const size_t w0 = align256(sizeof(double) * 12 * (size_t)np), w1 = align256(sizeof(double) * (size_t)np),
+               w2 = align256(sizeof(int32_t) * (size_t)np), w3 = align256(sizeof(double) * 3 * (size_t)n_states),
+               w4 = align256(sizeof(double) * (size_t)state_stride * (size_t)n_states), w5 = align256(sizeof(double) * 6 * (size_t)np);
+  CK(ctx->d_wrench.need(w0 + 2 * w1 + w2 + 2 * w3 + (host ? w4 + w5 : 0)));
+  char* wb = (char*)ctx->d_wrench.p;
+  double* d_grad = (double*)wb;
+  double* d_alpha = (double*)(wb + w0);
+  double* d_c = (double*)(wb + w0 + w1);
+  int32_t* d_status = (int32_t*)(wb + w0 + 2 * w1);
+  double* d_r1 = (double*)(wb + w0 + 2 * w1 + w2);
+  double* d_p1 = (double*)(wb + w0 + 2 * w1 + w2 + w3);
+  double* d_X = (double*)(wb + w0 + 2 * w1 + w2 + 2 * w3);
+  double* d_J = (double*)(wb + w0 + 2 * w1 + w2 + 2 * w3 + w4);
+  const double* x_dev = states; const int32_t* os_dev = obs_shape; const double* ro_dev = r_obs; const double* po_dev = p_obs;
+  if (host) {
+    size_t b0 = align256(sizeof(int32_t) * n_obs), b1 = align256(sizeof(double) * 3 * n_obs);
+    CK(ctx->d_scene.need(b0 + 2 * b1));
+    char* d = (char*)ctx->d_scene.p;
+    CK(cudaMemcpyAsync(d, obs_shape, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0, r_obs, sizeof(double) * 3 * n_obs, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d + b0 + b1, p_obs, sizeof(double) * 3 * n_obs, cudaMemcpyHostToDevice, S));
+    CK(cudaMemcpyAsync(d_X, states, sizeof(double) * (size_t)state_stride * (size_t)n_states, cudaMemcpyHostToDevice, S));
+    os_dev = (const int32_t*)d; ro_dev = (const double*)(d + b0); po_dev = (const double*)(d + b0 + b1); x_dev = d_X;
+  }
+  CK(ctx->d_pairs.need(sizeof(int32_t) * 4 * (size_t)np));
+  int32_t* s1 = (int32_t*)ctx->d_pairs.p; int32_t* s2 = s1 + np; int32_t* i1 = s2 + np; int32_t* i2 = i1 + np;
+  const int blocks = (int)std::min<int64_t>((np + 255) / 256, 148 * 16);
+  k_se3_pairs<<<blocks, 256, 0, S>>>(n_states, n_obs, x_dev, state_stride, r_col, p_col, vehicle_shape, os_dev, d_r1, d_p1, s1, s2, i1, i2);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  int32_t* q_status = host ? (status ? d_status : nullptr) : status;
+  int rc = run_query(ctx, Q_GRAD, np, s1, s2, d_r1, d_p1, ro_dev, po_dev, DCOL_ATT_MRP, pdip_tol, DCOL_MEM_DEVICE,
+                     d_alpha, nullptr, d_grad, q_status, nullptr, i1, i2, n_states, n_obs, DCOL_MEM_DEVICE);
+  if (rc) return rc;
+  double* o_c = host ? d_c : c;
+  double* o_J = host ? (Jc ? d_J : nullptr) : Jc;
+  k_se3_rows<<<blocks, 256, 0, S>>>(np, d_alpha, d_grad, o_c, o_J);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (host) {
+    std::vector<CopyJob> items;
+    items.push_back({(char*)c, (const char*)d_c, sizeof(double) * (size_t)np});
+    if (Jc) items.push_back({(char*)Jc, (const char*)d_J, sizeof(double) * 6 * (size_t)np});
     if (status) items.push_back({(char*)status, (const char*)d_status, sizeof(int32_t) * (size_t)np});
     return results_to_host(ctx, S, items);
   }

@@ -180,6 +180,20 @@ int dcol_se2_constraints(dcol_ctx* ctx, int64_t n_states, const double* xytheta,
                          int n_obs, const int32_t* obs_shape, const double* r_obs, const double* p_obs,
                          double pdip_tol, int mem, double* c, double* Jc, int32_t* status);
 
+/* Rigid vehicle against static obstacles: the same constraint functions in the 3-D trajectory examples
+ * (examples/trajectory_optimization/cone_through_wall.jl:56-68, cluttered_hallway_quadrotor.jl:83-104, ineq_con_x /
+ * ineq_con_x_jac).  Row s of `states` (state_stride doubles per row) holds the vehicle's position in columns
+ * r_col .. r_col+2 and its MRP in columns p_col .. p_col+2 (the examples' state [r; v; p; omega]: stride 12, r_col 0,
+ * p_col 6); for every obstacle o (shape ids, poses r_obs / p_obs, MRP):
+ *     c [s*n_obs + o]          = 1 - alpha(vehicle(s), obstacle o)
+ *     Jc[(s*n_obs + o)*6 + m]  = -(d alpha / d r1)_m  for m < 3,   -(d alpha / d p1)_{m-3}  for m >= 3
+ * i.e. the non-zero blocks (columns r_col.., p_col..) of the examples' constraint Jacobian rows
+ * [-J[1:3]' 0 -J[4:6]' 0].  One proximity_gradient query on the device between a gather and a row kernel.
+ * states f64[n_states*state_stride]; c f64[n_states*n_obs]; Jc f64[n_states*n_obs*6] (may be NULL); status as above. */
+int dcol_se3_constraints(dcol_ctx* ctx, int64_t n_states, const double* states, int state_stride, int r_col, int p_col,
+                         int32_t vehicle_shape, int n_obs, const int32_t* obs_shape, const double* r_obs, const double* p_obs,
+                         double pdip_tol, int mem, double* c, double* Jc, int32_t* status);
+
 /* ---- asynchronous submissions (host buffers) -------------------------------------------------------------
  * dcol_submit enqueues one query (query: 0 proximity, 1 gradient, 2 jacobian; buffers as in the synchronous
  * calls, all HOST memory, pinned for the copies to overlap) and returns a ticket >= 0 without waiting; dcol_wait

@@ -376,6 +376,27 @@ function se2_constraints(xyθ::Matrix{Float64}, vehicle_shape::Integer, obs_shap
 end
 
 """
+    se3_constraints(X, vehicle_shape, obs_shape, r_obs, p_obs; r_rows = 1:3, p_rows = 7:9, pdip_tol) -> (c, Jc, status)
+
+`ineq_con_x` / `ineq_con_x_jac` of the 3-D trajectory examples (cone through a wall, quadrotor in a cluttered hallway) for a
+batch of states: column `s` of `X` (nx×n; the examples' state `[r; v; p; ω]`) holds the vehicle's position in rows `r_rows`
+and its MRP in rows `p_rows`; `c[o, s] = 1 - α` against obstacle `o`, `Jc[1:3, o, s] = -∂α/∂r`, `Jc[4:6, o, s] = -∂α/∂p` (the
+non-zero blocks of the examples' rows `[-J[1:3]' 0 -J[4:6]' 0]`).  Shape ids are 0-based.
+"""
+function se3_constraints(X::Matrix{Float64}, vehicle_shape::Integer, obs_shape::Vector{Int32}, r_obs::Matrix{Float64},
+                         p_obs::Matrix{Float64}; r_rows = 1:3, p_rows = 7:9, pdip_tol = 1e-6)
+    nx, n = size(X); K = length(obs_shape)
+    (length(r_rows) == 3 && length(p_rows) == 3) || error("se3_constraints: r_rows and p_rows must be three consecutive rows each")
+    c = Matrix{Float64}(undef, K, n); Jc = Array{Float64}(undef, 6, K, n); status = Matrix{Int32}(undef, K, n)
+    _check(ccall((:dcol_se3_constraints, _lib[]), Cint,
+                 (Ptr{Cvoid}, Int64, Ptr{Float64}, Cint, Cint, Cint, Int32, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Float64, Cint,
+                  Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                 _ctx[], n, X, nx, first(r_rows) - 1, first(p_rows) - 1, vehicle_shape, K, obs_shape, r_obs, p_obs, Float64(pdip_tol), MEM_HOST,
+                 c, Jc, status))
+    return c, Jc, status
+end
+
+"""
     query_indexed(kind, shape1, shape2, pose1, pose2, r1, att1, r2, att2; pdip_tol) -> BatchResult
 
 Pose-table query: pair k uses column `pose1[k]+1` of `(r1, att1)` and `pose2[k]+1` of `(r2, att2)` (0-based indices, as in C).

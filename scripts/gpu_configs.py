@@ -70,3 +70,25 @@ print(f"config 5  piano-mover batch, {B*N*K} box-box MRP jacobians: call {w*1e3:
 xyt = np.stack([r1[:, 0], r1[:, 1], theta], axis=1)
 w5, k5, o5 = timed(lambda: ctx.se2_constraints(xyt, sv, np.array(so, np.int32), r2, p2), 3)
 print(f"config 5f same batch through dcol_se2_constraints (c and dc/d(x,y,theta) per pair): call {w5*1e3:8.3f} ms  kernels {k5:7.3f} ms  {B*N*K/w5/1e6:8.2f} Mpairs/s")
+# 5g: the quadrotor of cluttered_hallway_quadrotor.jl (a sphere, state [r; v; p; omega]) against its 11 obstacles (:139-153):
+# 1024 rollouts x 100 knots x 11 obstacles through dcol_se3_constraints, and the same pairs as plain gradient rows
+A1, b1, A2, b2 = util.load_polytopes()
+veh = dc.SphereMRP(0.25)
+bot = dc.create_rect_prism(20, 5.0, 0.2)[0]; top = dc.create_rect_prism(20, 5.0, 0.2)[0]
+obs = [dc.CylinderMRP(0.6, 3.0), dc.CapsuleMRP(0.2, 5.0), dc.SphereMRP(0.8), dc.ConeMRP(2.0, np.deg2rad(22)), dc.PolytopeMRP(A2, b2),
+       dc.PolygonMRP(*dc.create_n_sided(5, 0.6), 0.2), dc.CylinderMRP(1.1, 2.3), dc.CapsuleMRP(0.8, 1.0), dc.SphereMRP(0.5), bot, top]
+K = len(obs)
+t = dc.ShapeTable(); sv = t.add(veh); so = np.array([t.add(x) for x in obs], np.int32)
+ctx.set_shape_arrays(*t.arrays())
+g = util.rng(19)
+r_obs = np.zeros((K, 3)); r_obs[:9, 0] = np.linspace(-5, 5, 9); r_obs[:9, 1] = g.standard_normal(9); r_obs[:9, 2] = 3 + g.standard_normal(9)
+r_obs[9] = [0, 0, 0.9]; r_obs[10] = [0, 0, 6.0]
+q = g.standard_normal((K, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True); q = np.where(q[:, :1] < 0, -q, q)
+p_obs = q[:, 1:] / (1 + q[:, :1]); p_obs[9:] = 0.0
+X = np.zeros((B * N, 12))
+X[:, 0] = g.uniform(-8, 8, B * N); X[:, 1] = g.uniform(-2, 2, B * N); X[:, 2] = g.uniform(1.5, 5.5, B * N); X[:, 6:9] = 0.1 * g.standard_normal((B * N, 3))
+w6, k6, o6 = timed(lambda: ctx.se3_constraints(X, sv, so, r_obs, p_obs), 3)
+print(f"config 5g quadrotor hallway batch, {B*N*K} pairs through dcol_se3_constraints (c and the two 1x3 Jacobian blocks per pair): call {w6*1e3:8.3f} ms  kernels {k6:7.3f} ms  {B*N*K/w6/1e6:8.2f} Mpairs/s  (failed {int((o6['status'] != 0).sum())})")
+i1 = np.repeat(np.arange(B * N, dtype=np.int32), K); i2 = np.tile(np.arange(K, dtype=np.int32), B * N)
+w7, k7, o7 = timed(lambda: ctx.query_indexed(1, np.full(B * N * K, sv, np.int32), so[i2], i1, i2, np.ascontiguousarray(X[:, 0:3]), np.ascontiguousarray(X[:, 6:9]), r_obs, p_obs, dc.ATT_MRP), 3)
+print(f"config 5h same pairs through dcol_query_indexed (gradient rows, 13 numbers per pair): call {w7*1e3:8.3f} ms  kernels {k7:7.3f} ms  identical c: {np.array_equal(1 - o7['alpha'], o6['c'].reshape(-1))}")

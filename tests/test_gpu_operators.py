@@ -256,6 +256,64 @@ def test_se2_constraints_match_the_example_formulas(ctx, oracle):
     assert np.array_equal(again["c"], out["c"][:10])
 
 
+def test_se3_constraints_match_the_example_formulas(ctx, oracle):
+    """dcol_se3_constraints against ineq_con_x / ineq_con_x_jac of cone_through_wall.jl:56-68 and
+    cluttered_hallway_quadrotor.jl:83-104 (state [r; v; p; omega], rows [-J[1:3]' 0 -J[4:6]' 0]) evaluated on the host from
+    per-pair proximity_gradient results: the same kernels on the same poses, so bit-identical; against the oracle; and
+    against central finite differences of c in the six pose columns."""
+    n = 2500
+    g = util.rng(29)
+    # the cone of cone_through_wall.jl against its four walls (:96-110), and the quadrotor sphere against the hallway set
+    for veh, obs, r_obs, p_obs in (
+            (dc.ConeMRP(2.0, np.deg2rad(22)),
+             [dc.create_rect_prism(10.0, 10.0, 1.0)[0], dc.create_rect_prism(10.0, 10.0, 1.0)[0], dc.create_rect_prism(4.1, 4.1, 1.1)[0], dc.create_rect_prism(4.1, 4.1, 1.1)[0]],
+             np.array([[-6, 0, 5.0], [6, 0, 5.0], [0, 0, 2.05], [0, 0, 7.96]]), np.tile(dc.mrp_from_q([np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0]), (4, 1))),
+            (dc.SphereMRP(0.25),
+             [dc.CylinderMRP(0.6, 3.0), dc.CapsuleMRP(0.2, 5.0), dc.ConeMRP(2.0, np.deg2rad(22)), dc.PolygonMRP(*dc.create_n_sided(5, 0.6), 0.2), dc.create_rect_prism(20, 5.0, 0.2)[0]],
+             np.array([[-5, 0.3, 3.2], [-2.5, -0.4, 2.1], [0, 0.8, 3.9], [2.5, 0.1, 2.7], [0, 0, 0.9]]), 0.3 * g.standard_normal((5, 3)))):
+        K = len(obs)
+        t = dc.ShapeTable(); sv = t.add(veh); so = np.array([t.add(o) for o in obs], np.int32)
+        ctx.set_shape_arrays(*t.arrays())
+        X = np.zeros((n, 12))
+        X[:, 0:3] = np.array([0.0, 0.0, 4.0]) + g.uniform(-7, 7, (n, 3)) * np.array([1.0, 1.0, 0.5])
+        X[:, 3:6] = g.standard_normal((n, 3)); X[:, 9:12] = g.standard_normal((n, 3))       # velocities: ignored by the constraint
+        q = g.standard_normal((n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True); q = np.where(q[:, :1] < 0, -q, q)
+        X[:, 6:9] = q[:, 1:] / (1 + q[:, :1])
+        out = ctx.se3_constraints(X, sv, so, r_obs, p_obs)
+        assert out["c"].shape == (n, K) and out["Jc"].shape == (n, K, 6)
+        i1 = np.repeat(np.arange(n), K); i2 = np.tile(np.arange(K), n)
+        args = (np.full(n * K, sv, np.int32), so[i2], X[i1, 0:3], X[i1, 6:9], r_obs[i2], p_obs[i2])
+        e = ctx._batch(1, *args, dc.ATT_MRP, 1e-6)
+        assert np.array_equal(out["status"].reshape(-1), e["status"]) and (e["status"] == 0).all()
+        assert np.array_equal(out["c"].reshape(-1), 1 - e["alpha"])
+        assert np.array_equal(out["Jc"].reshape(-1, 6), -e["grad"][:, :6])
+        o = oracle.query(1, t.arrays(), *args, dc.ATT_MRP, 1e-6)
+        assert np.abs(out["c"].reshape(-1) - (1 - o["alpha"])).max() < 1e-6 * max(1.0, np.abs(o["alpha"]).max())
+        err = np.abs(out["Jc"].reshape(-1, 6) + o["grad"][:, :6]).max(axis=1) / np.maximum(1.0, np.abs(o["grad"]).max(axis=1))
+        assert np.quantile(err, 0.99) < 1e-5
+        # another state layout: [p; r] in a 7-column row (the columns are arguments, not a convention)
+        Y = np.concatenate([X[:, 6:9], X[:, 0:3], np.ones((n, 1))], axis=1)
+        alt = ctx.se3_constraints(Y, sv, so, r_obs, p_obs, r_col=3, p_col=0)
+        assert np.array_equal(alt["c"], out["c"]) and np.array_equal(alt["Jc"], out["Jc"])
+        m = 150; eps = 1e-6
+        Jt = ctx.se3_constraints(X[:m], sv, so, r_obs, p_obs, pdip_tol=1e-10)["Jc"]
+        fd = np.zeros((m, K, 6))
+        for a, col in enumerate((0, 1, 2, 6, 7, 8)):
+            d = np.zeros(12); d[col] = eps
+            fd[:, :, a] = (ctx.se3_constraints(X[:m] + d, sv, so, r_obs, p_obs, pdip_tol=1e-10)["c"]
+                           - ctx.se3_constraints(X[:m] - d, sv, so, r_obs, p_obs, pdip_tol=1e-10)["c"]) / (2 * eps)
+        ef = np.abs(fd - Jt).max(axis=2) / np.maximum(1.0, np.abs(Jt).max(axis=2))
+        assert np.median(ef) < 1e-5 and (ef < 1e-3).mean() > 0.95
+    assert ctx.se3_constraints(np.zeros((0, 12)), sv, so, r_obs, p_obs)["c"].shape == (0, K)
+    with pytest.raises(RuntimeError, match="disjoint"):
+        ctx.se3_constraints(X[:4], sv, so, r_obs, p_obs, r_col=0, p_col=2)
+    with pytest.raises(RuntimeError, match="disjoint"):
+        ctx.se3_constraints(X[:4], sv, so, r_obs, p_obs, r_col=10, p_col=0)
+    with pytest.raises(RuntimeError, match="shape index out of range"):
+        ctx.se3_constraints(X[:4], 999, so, r_obs, p_obs)
+    assert np.array_equal(ctx.se3_constraints(X[:4], sv, so, r_obs, p_obs)["c"], out["c"][:4])
+
+
 @pytest.mark.parametrize("att_kind", [0, 1])
 @pytest.mark.parametrize("kind", [0, 1, 2])
 def test_scene_cull_keeps_near_pairs_bit_identical(ctx, att_kind, kind):

@@ -718,9 +718,9 @@ __global__ void k_se3_rows(int64_t np, const double* __restrict__ alpha, const d
 }
 
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure): 8 independent
-// chains per thread, 16 rounds per loop trip (128 DFMA against 3 loop instructions).  Under ncu the pipe reads 98 %
-// active; the round-1 probe (8 DFMA per trip as written, 32 after the compiler's unrolling) read 91 % and understated the
-// peak by as much (33.8 instead of 36.5 TFLOP/s; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2).
+// chains per thread, 16 rounds per loop trip (128 DFMA against 3 loop instructions).  Under ncu the FP64 pipe reads 92 %
+// active at 1.96 GHz (profiles/r02z_k_dfma_ncu.txt), so the 34.1 TFLOP/s it measures understate the pipe's own peak
+// (37.1 = nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz) by that much; bench.py reports the fraction of both.
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
 #pragma unroll 1

@@ -13,7 +13,7 @@ torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of 
   e2e   : same metric through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
   roofline     : FP64 CUDA-core roofline of the solver kernels (algorithmic FLOPs from the frozen
                  flops_model with each pair's actual iteration count / kernel time from CUDA events
-                 inside the library); peak = DFMA micro-benchmark run in the same process, because
+                 inside the library); peak = DFMA micro-benchmark (pipe peak, two-source form) run in the same process, because
                  MEASURED_PEAKS.json carries no FP64 figure.  "hbm" sub-object: pose-in/result-out bytes.
   cpu_baseline : the C++ oracle (restatement of the Julia reference) on all host threads, bounded sample; rebuilt on the box
                  it runs on with -O3 -march=native, flags and thread count in `sample`
@@ -368,6 +368,7 @@ def main():
     tp0 = time.time()
     fp64_peak = ctx.measure_fp64_tflops(0.02 if args.profile else 0.6)
     peak_clocks = peak_sampler.stop(tp0, time.time()) if peak_sampler else None
+    fp64_peak3 = ctx.measure_fp64_tflops(0.02 if args.profile else 0.2, three_source=True)
     prox = run_config(0, dc.ATT_QUAT, args.pairs, args.steps, args.warmup, 1234, e2e=not args.profile)
     other = "scene" if args.variant == "cube" else "cube"
     prox2 = None if args.profile else run_config(0, dc.ATT_QUAT, args.pairs, max(3, args.steps // 4), args.warmup, 1234, variant=other, e2e=False)
@@ -448,9 +449,13 @@ def main():
             ach = r["flops"] / (r["kernel_ms"] * 1e-3) / 1e12
             gbs = (r["in_bytes"] + r["out_bytes"]) / (r["kernel_ms"] * 1e-3) / 1e9
             return {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                    "peak_source": "DFMA-only kernel launched back to back for 0.6 s in this process, median launch (MEASURED_PEAKS.json has "
-                                   "no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)",
+                    "peak_source": "DFMA-only kernel x = fma(x, a, x) launched back to back for 0.6 s in this process, median launch: the FP64 "
+                                   "pipe ~100 % busy under ncu (MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz "
+                                   "= 37.2 TFLOP/s)",
                     "peak_clocks": peak_clocks, "frac_of_nominal_37.2": ach / 37.2,
+                    "peak_three_source_dfma": fp64_peak3, "frac_of_three_source_peak": ach / fp64_peak3,
+                    "peak_three_source_note": "x = fma(x, a, b) with three distinct 64-bit register sources keeps the pipe 92 % busy whatever the "
+                                              "unrolling or CTA shape (profiles/r02z_k_dfma_ncu.txt); earlier bench lines of this repo used this figure",
                     "traffic": traffic.get(key, {}).get("dram_bytes_per_step") if traffic.get(key, {}).get("pairs") == r["n"] else None,
                     "traffic_source": traffic.get(key, {}).get("source"),
                     "kernel_ms_per_step": r["kernel_ms"], "algorithmic_flops_per_pair": r["flops"] / r["n"],

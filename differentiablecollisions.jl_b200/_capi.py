@@ -65,6 +65,7 @@ SYMBOLS = {
     "dcol_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops": (C.c_double, [C.c_void_p]),
     "dcol_measure_fp64_tflops_for": (C.c_double, [C.c_void_p, C.c_double]),
+    "dcol_measure_fp64_tflops_mode": (C.c_double, [C.c_void_p, C.c_double, C.c_int]),
     "dcol_set_copy_only": (C.c_int, [C.c_void_p, C.c_int]),
     "dcol_host_copy_selftest": (C.c_int, [C.c_int, C.c_int64, C.c_int]),
     "dcol_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]),

@@ -718,17 +718,27 @@ __global__ void k_se3_rows(int64_t np, const double* __restrict__ alpha, const d
 }
 
 // FP64 FMA throughput micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure): 8 independent
-// chains per thread, 16 rounds per loop trip (128 DFMA against 3 loop instructions).  Under ncu the FP64 pipe reads 92 %
-// active at 1.96 GHz (profiles/r02z_k_dfma_ncu.txt), so the 34.1 TFLOP/s it measures understate the pipe's own peak
-// (37.1 = nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz) by that much; bench.py reports the fraction of both.
+// chains per thread, 16 rounds per loop trip (128 DFMA against 3 loop instructions).  Measured on B200 with ncu
+// (profiles/r02z_k_dfma_ncu.txt, scripts/dfma_probe.cu):
+//   TWO_SRC  x = fma(x, a, x)   two distinct 64-bit register sources:   37.0 TFLOP/s, FP64 pipe ~100 % busy -- the pipe's peak
+//                                                                       (nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)
+//   !TWO_SRC x = fma(x, a, b)   three distinct sources:                 34.1 TFLOP/s, pipe 92 % busy -- whatever the chain count,
+//                                                                       unrolling or CTA shape: the third 64-bit operand read
+// The roofline uses the first (higher) figure; the second is what a stream of general DFMAs can reach.
+template <bool TWO_SRC>
 __global__ void k_dfma(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
 #pragma unroll 1
   for (int i = 0; i < iters; i += 16) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+      if (TWO_SRC) {
+        x0 = fma(x0, a, x0); x1 = fma(x1, a, x1); x2 = fma(x2, a, x2); x3 = fma(x3, a, x3);
+        x4 = fma(x4, a, x4); x5 = fma(x5, a, x5); x6 = fma(x6, a, x6); x7 = fma(x7, a, x7);
+      } else {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+      }
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
@@ -1211,7 +1221,8 @@ int dcol_set_shapes(dcol_ctx* ctx, int n_shapes, const int32_t* type, const int6
 
 // DFMA throughput of the device: `seconds` of back-to-back launches of an FMA-only kernel (8 independent chains per
 // thread, 8 CTAs of 256 threads per SM), median launch.  bench.py samples the SM clock while this runs.
-double dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds) {
+// three_source = 0: x = fma(x, a, x), the pipe's peak; 1: x = fma(x, a, b), a stream of general DFMAs (k_dfma above).
+double dcol_measure_fp64_tflops_mode(dcol_ctx* ctx, double seconds, int three_source) {
   if (!ctx) return -1.0;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
   cudaDeviceProp prop;
@@ -1220,13 +1231,18 @@ double dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds) {
   double* d = nullptr;
   if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
   cudaStream_t s = ctx->stream();
-  k_dfma<<<blocks, threads, 0, s>>>(d, 2000, 1.0000001, 1e-9);   // warm-up (iteration counts are multiples of 16)
+  // (iteration counts are multiples of 16; x grows by (1 + 1e-9) per step in the two-source form: no overflow)
+  auto launch = [&](int it) {
+    if (three_source) k_dfma<false><<<blocks, threads, 0, s>>>(d, it, 1.0000001, 1e-9);
+    else k_dfma<true><<<blocks, threads, 0, s>>>(d, it, 1e-9, 0.0);
+  };
+  launch(2000);
   cudaStreamSynchronize(s);
   std::vector<float> ms_all;
   double total = 0.0;
   while (total < seconds * 1e3 && ms_all.size() < 4000) {
     cudaEventRecord(ctx->ev_k0, s);
-    k_dfma<<<blocks, threads, 0, s>>>(d, iters, 1.0000001, 1e-9);
+    launch(iters);
     cudaEventRecord(ctx->ev_k1, s);
     cudaEventSynchronize(ctx->ev_k1);
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1);
@@ -1239,6 +1255,7 @@ double dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds) {
   double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
   return flops / (med * 1e-3) / 1e12;
 }
+double dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds) { return dcol_measure_fp64_tflops_mode(ctx, seconds, 0); }
 double dcol_measure_fp64_tflops(dcol_ctx* ctx) { return dcol_measure_fp64_tflops_for(ctx, 0.6); }
 
 }  // extern "C"

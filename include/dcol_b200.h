@@ -271,6 +271,9 @@ double  dcol_last_kernel_ms(const dcol_ctx* ctx);
  * (0.6 s for the short form), median launch; the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry) */
 double  dcol_measure_fp64_tflops(dcol_ctx* ctx);
 double  dcol_measure_fp64_tflops_for(dcol_ctx* ctx, double seconds);
+/* three_source = 0: x = fma(x, a, x), the FP64 pipe's peak (what the two calls above return); 1: x = fma(x, a, b), three
+ * distinct 64-bit register sources per DFMA -- 92 % of the former on B200 (profiles/r02z_k_dfma_ncu.txt) */
+double  dcol_measure_fp64_tflops_mode(dcol_ctx* ctx, double seconds, int three_source);
 /* measurement knob: host-pointer calls issue their host<->device copies (same staging, streams, chunking) but no kernels;
  * gives the copy-only bound of the end-to-end path */
 int     dcol_set_copy_only(dcol_ctx* ctx, int on);

@@ -56,6 +56,9 @@ __device__ __forceinline__ void dispatch_c2(int c2, const QueryParams* p, const 
 template <int VAR>
 __global__ void DCOL_KERNEL_BOUNDS proximity_persistent(LaunchTable* __restrict__ tt, int* __restrict__ counter) {
   __shared__ int s_tile;
+  // Small batches launch this kernel with programmatic stream serialisation behind the preparation kernel: its blocks are
+  // already resident when that kernel ends and wait here for its tables (a no-op for ordinary launches).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int n_tiles = tt->n_tiles;
   const int tile_sz = blockDim.x;
   for (;;) {
@@ -95,7 +98,15 @@ __global__ void DCOL_KERNEL_BOUNDS proximity_persistent(LaunchTable* __restrict_
 #define DCOL_CAT2(a, b) a##b
 #define DCOL_CAT(a, b) DCOL_CAT2(a, b)
 const void* DCOL_CAT(persistent_kernel_ptr_v, DCOL_VAR)() { return (const void*)proximity_persistent<DCOL_VAR>; }
-cudaError_t DCOL_CAT(launch_persistent_v, DCOL_VAR)(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter) {
+cudaError_t DCOL_CAT(launch_persistent_v, DCOL_VAR)(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter, int early) {
+  if (early) {      // may start before the previous kernel of the stream has finished (it waits at griddepcontrol.wait)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, proximity_persistent<DCOL_VAR>, tt, counter);
+  }
   proximity_persistent<DCOL_VAR><<<grid, block, smem, st>>>(tt, counter);
   return cudaGetLastError();
 }

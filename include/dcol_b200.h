@@ -265,7 +265,9 @@ int dcol_set_max_iters(dcol_ctx* ctx, int max_iters);
 int64_t dcol_launch_count(const dcol_ctx* ctx);
 /* device time (ms) of the solver launches (the persistent kernels with their fused derivative epilogues: first pass and
  * resume pass of every row tier) of the last query call, measured with CUDA events on the launching streams; the
- * binning / packing / un-permute kernels around them are not included; <0 if unavailable */
+ * binning / packing / un-permute kernels around them are not included -- except for batches of up to 4 096 pairs, whose
+ * single preparation kernel sits inside the bracket (nothing may stand between it and the solver launch, which becomes
+ * resident while it still runs); <0 if unavailable */
 double  dcol_last_kernel_ms(const dcol_ctx* ctx);
 /* measured FP64 FMA throughput of the device in TFLOP/s: DFMA-only kernel launched back to back for `seconds`
  * (0.6 s for the short form), median launch; the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry) */

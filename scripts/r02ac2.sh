@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02ac2_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02ac2_tests.log
+timeout 300 python scripts/gpu_mini.py 2>&1 | tail -1 > gpurun_out/r02ac2_mini.txt
+timeout 300 python scripts/gpu_mini.py 2>&1 | tail -1 >> gpurun_out/r02ac2_mini.txt
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02ac2_bench.json 2> gpurun_out/r02ac2_bench.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02ac2_bench_ref.json 2>> gpurun_out/r02ac2_bench.err
+tail -3 gpurun_out/r02ac2_tests.log; cat gpurun_out/r02ac2_mini.txt; python -c "
+import json; d=json.loads(open('gpurun_out/r02ac2_bench.json').read().strip().split('\n')[-1]); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel_ms_per_step'], d['e2e']['value'], d['jacobian']['value'], d['large_batch']['roofline_frac']); print(json.dumps(d['latency'], indent=0))"

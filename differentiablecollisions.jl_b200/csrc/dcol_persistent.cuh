@@ -94,6 +94,24 @@ __global__ void DCOL_KERNEL_BOUNDS proximity_persistent(LaunchTable* __restrict_
   }
 }
 
+// One pair whose packed record the host wrote itself (single-pair calls on host pointers, dcol_capi.cu): no binning pass
+// and no launch table, one launch in all.  Lane 0 owns the pair; the other lanes of the warp redo it for the barriers only.
+template <int VAR>
+__global__ void __launch_bounds__(32) proximity_single(QueryParams P, int cp) {
+  TileCtx tc;
+  tc.mode = 0; tc.spill_t = 0; tc.ov = nullptr; tc.ov_cap = 0; tc.ov_count = nullptr; tc.in = nullptr; tc.in_cap = 0;
+  tc.dup = threadIdx.x != 0;
+  const int c1 = cp / NCLS, c2 = cp - c1 * NCLS;
+  switch (c1) {
+    case 0: dispatch_c2<0, VAR>(c2, &P, &tc, 0); break;
+    case 1: dispatch_c2<1, VAR>(c2, &P, &tc, 0); break;
+    case 2: dispatch_c2<2, VAR>(c2, &P, &tc, 0); break;
+    case 3: dispatch_c2<3, VAR>(c2, &P, &tc, 0); break;
+    case 4: dispatch_c2<4, VAR>(c2, &P, &tc, 0); break;
+    case 5: dispatch_c2<5, VAR>(c2, &P, &tc, 0); break;
+  }
+}
+
 // host-side handles of this translation unit's kernel (dcol_capi.cu)
 #define DCOL_CAT2(a, b) a##b
 #define DCOL_CAT(a, b) DCOL_CAT2(a, b)
@@ -108,6 +126,14 @@ cudaError_t DCOL_CAT(launch_persistent_v, DCOL_VAR)(int grid, int block, size_t 
     return cudaLaunchKernelEx(&cfg, proximity_persistent<DCOL_VAR>, tt, counter);
   }
   proximity_persistent<DCOL_VAR><<<grid, block, smem, st>>>(tt, counter);
+  return cudaGetLastError();
+}
+cudaError_t DCOL_CAT(launch_single_v, DCOL_VAR)(size_t smem, cudaStream_t st, const QueryParams& P, int cp) {
+  if (smem > 48 * 1024) {      // (row stores of very large polytopes only)
+    cudaError_t e = cudaFuncSetAttribute(proximity_single<DCOL_VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  proximity_single<DCOL_VAR><<<1, 32, smem, st>>>(P, cp);
   return cudaGetLastError();
 }
 }  // namespace dcol

@@ -581,3 +581,32 @@ def test_verbose_trace(ctx, capsys):
     assert int(out[-1].split()[0]) == its[69] and float(out[-1].split()[1]) == pytest.approx(alpha, rel=2e-3)
     a2_, g = dc.proximity_gradient(caps, cone, verbose=True, ctx=ctx)
     assert len(capsys.readouterr().out.strip().split("\n")) == len(out) and a2_ == pytest.approx(alpha, rel=1e-9)
+
+
+@pytest.mark.parametrize("att_kind", [0, 1])
+def test_single_pair_one_launch_path(ctx, att_kind):
+    """One pair on host pointers runs as ONE launch on a record the host packs itself (proximity_single): bit-identical to
+    the same pair inside a two-pair batch (preparation kernel + persistent kernel) for all 49 ordered type pairs (both class
+    orders: the host applies the exchange the packing kernels apply), every query kind, shapes with offsets; and the same
+    error for a bad shape index."""
+    g = util.rng(41 + att_kind)
+    shapes = util.standard_shapes(att_kind, "scene")
+    for p in shapes:
+        p.r_offset = 0.2 * g.standard_normal(3); p.Q_offset = dc.dcm_from_q(g.standard_normal(4))
+    t = dc.ShapeTable(); ids = [t.add(p) for p in shapes]
+    ctx.set_shape_arrays(*t.arrays())
+    r1, a1, r2, a2 = util.random_poses(49, att_kind, seed=77)
+    k = 0
+    for i in ids:
+        for j in ids:
+            for kind in (0, 1, 2):
+                one = ctx._batch(kind, [i], [j], r1[k:k + 1], a1[k:k + 1], r2[k:k + 1], a2[k:k + 1], att_kind, 1e-6, want_mu=(kind == 0))
+                two = ctx._batch(kind, [i, i], [j, j], r1[[k, k]], a1[[k, k]], r2[[k, k]], a2[[k, k]], att_kind, 1e-6, want_mu=(kind == 0))
+                assert one["status"][0] == 0
+                for key in one:
+                    assert np.array_equal(one[key][0], two[key][0], equal_nan=True), (i, j, kind, key)
+            k += 1
+    with pytest.raises(RuntimeError, match="shape index out of range"):
+        ctx._batch(0, [len(ids)], [0], r1[:1], a1[:1], r2[:1], a2[:1], att_kind, 1e-6)
+    ok = ctx._batch(0, [0], [1], r1[:1], a1[:1], r2[:1], a2[:1], att_kind, 1e-6)          # the context stays usable
+    assert ok["status"][0] == 0

@@ -28,9 +28,9 @@ const void* persistent_kernel_ptr_v0(); const void* persistent_kernel_ptr_v1(); 
 cudaError_t launch_persistent_v0(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter, int early);
 cudaError_t launch_persistent_v1(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter, int early);
 cudaError_t launch_persistent_v2(int grid, int block, size_t smem, cudaStream_t st, LaunchTable* tt, int* counter, int early);
-cudaError_t launch_single_v0(size_t smem, cudaStream_t st, const QueryParams& P, int cp);
-cudaError_t launch_single_v1(size_t smem, cudaStream_t st, const QueryParams& P, int cp);
-cudaError_t launch_single_v2(size_t smem, cudaStream_t st, const QueryParams& P, int cp);
+cudaError_t launch_packed_v0(int block, size_t smem, cudaStream_t st, const QueryParams& P, const PackedGroups& G);
+cudaError_t launch_packed_v1(int block, size_t smem, cudaStream_t st, const QueryParams& P, const PackedGroups& G);
+cudaError_t launch_packed_v2(int block, size_t smem, cudaStream_t st, const QueryParams& P, const PackedGroups& G);
 cudaError_t launch_solve_socp(int64_t n, int nx, int n_ort, int d1, int d2, const double* c, const double* G, const double* h, double tol, int max_iters,
                               double* x, double* s, double* z, int32_t* status, int32_t* iters, double* trace, cudaStream_t st);   // dcol_socp.cu
 int socp_limit(int which);
@@ -1540,24 +1540,44 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     if (cudaHostGetDevicePointer(&dp, ctx->h_stage, 0) == cudaSuccess && dp) { di = (char*)dp; dout = (char*)dp + STAGE_MAX; zero_copy = true; }
     else (void)cudaGetLastError();
   }
-  // One pair on host pointers (the drop-in calls of the reference's examples): the host knows the two shapes' classes and
-  // writes the pair's packed record into the staging area itself; ONE launch (proximity_single) reads it from there and
-  // writes the results back the same way.  No preparation kernel, no launch table.
-  static const bool single_on = !(getenv("DCOL_SINGLE") && atoi(getenv("DCOL_SINGLE")) == 0);      // tuning knob
-  const PairRec* single_rec = nullptr; int single_cp = 0;
-  if (zero_copy && single_on && n == 1 && !indexed && !oidx && (ctx->has_small || nt_tiers == 1) && !ctx->copy_only && !ctx->warm) {
-    const int s1 = shape1[0], s2 = shape2[0];
-    if ((unsigned)s1 >= (unsigned)ctx->n_shapes || (unsigned)s2 >= (unsigned)ctx->n_shapes) { ctx->err = "dcol: shape index out of range in shape1/shape2"; return -1; }
-    const int c1 = ctx->h_shapes[s1].cls, c2 = ctx->h_shapes[s2].cls;
-    const bool swp = c1 > c2;
+  // A handful of pairs on host pointers (above all ONE pair: the drop-in calls of the reference's examples): the host knows
+  // the shapes' classes, so it packs the 128-byte records itself into the staging area -- grouped by class pair, with the
+  // exchange of the two primitives the packing kernels apply -- and ONE launch (proximity_packed: a block per class pair
+  // present) reads them from there and writes the results back the same way.  No preparation kernel, no launch table.
+  // Through the C ABI on B200: single pair 50 -> 38 us (profiles/r02_latency.txt).
+  static const int packed_max = getenv("DCOL_PACKED_MAX") ? std::min(DCOL_PACKED_MAX, atoi(getenv("DCOL_PACKED_MAX"))) : DCOL_PACKED_MAX;   // tuning knob; 0 = off
+  const PairRec* packed_recs = nullptr; PackedGroups packed; int packed_block = 32;
+  packed.n = 0;
+  if (zero_copy && n <= packed_max && !indexed && !oidx && (ctx->has_small || nt_tiers == 1) && !ctx->copy_only && !ctx->warm) {
+    int cpk[DCOL_PACKED_MAX], cnt[MAX_BINS] = {};
+    for (int64_t i = 0; i < n; i++) {
+      const int s1 = shape1[i], s2 = shape2[i];
+      if ((unsigned)s1 >= (unsigned)ctx->n_shapes || (unsigned)s2 >= (unsigned)ctx->n_shapes) { ctx->err = "dcol: shape index out of range in shape1/shape2"; return -1; }
+      const int c1 = ctx->h_shapes[s1].cls, c2 = ctx->h_shapes[s2].cls;
+      cpk[i] = std::min(c1, c2) * NCLS + std::max(c1, c2);
+      cnt[cpk[i]]++;
+    }
+    int first[MAX_BINS], g_of[MAX_BINS];
+    for (int cp = 0, at = 0; cp < MAX_BINS; cp++) if (cnt[cp]) {
+      g_of[cp] = packed.n; packed.cp[packed.n] = cp; packed.first[packed.n] = at; packed.count[packed.n] = cnt[cp];
+      first[cp] = at; at += cnt[cp]; packed.n++;
+      packed_block = std::max(packed_block, (cnt[cp] + 31) & ~31);
+    }
     PairRec* hr = (PairRec*)(ctx->h_stage + align256(b_in));
-    memset(hr, 0, sizeof(PairRec));
-    const double* ra = swp ? r2 : r1; const double* aa = swp ? att2 : att1; const double* rb = swp ? r1 : r2; const double* ab = swp ? att1 : att2;
-    for (int a = 0; a < 3; a++) { hr->r1[a] = ra[a]; hr->r2[a] = rb[a]; }
-    for (int a = 0; a < na; a++) { hr->a1[a] = aa[a]; hr->a2[a] = ab[a]; }
-    hr->s1 = swp ? s2 : s1; hr->s2 = swp ? s1 : s2; hr->pair = 0; hr->flags = swp ? DCOL_REC_SWAPPED : 0;
-    single_rec = (const PairRec*)(di + align256(b_in));
-    single_cp = std::min(c1, c2) * NCLS + std::max(c1, c2);
+    for (int64_t i = 0; i < n; i++) {
+      const int s1 = shape1[i], s2 = shape2[i];
+      const bool swp = ctx->h_shapes[s1].cls > ctx->h_shapes[s2].cls;
+      PairRec& R = hr[first[cpk[i]]++];
+      const double* ra = (swp ? r2 : r1) + 3 * i; const double* aa = (swp ? att2 : att1) + na * i;
+      const double* rb = (swp ? r1 : r2) + 3 * i; const double* ab = (swp ? att1 : att2) + na * i;
+      for (int a = 0; a < 3; a++) { R.r1[a] = ra[a]; R.r2[a] = rb[a]; }
+      R.a1[3] = 0.0; R.a2[3] = 0.0;
+      for (int a = 0; a < na; a++) { R.a1[a] = aa[a]; R.a2[a] = ab[a]; }
+      R.s1 = swp ? s2 : s1; R.s2 = swp ? s1 : s2; R.pair = (int32_t)i; R.flags = swp ? DCOL_REC_SWAPPED : 0;
+    }
+    (void)g_of;
+    // (a tier whose row store leaves room for fewer threads per block than the largest group needs keeps the general path)
+    if (packed_block <= (ctx->has_small ? ctx->small_tier : ctx->tiers[0]).block) packed_recs = (const PairRec*)(di + align256(b_in));
   }
   if (staged && !zero_copy) CK(cudaMemcpyAsync(di, ctx->h_stage, b_in, cudaMemcpyHostToDevice, S));
   if (indexed && in_mem == DCOL_MEM_HOST && !staged) {       // pose tables go up once, ahead of the first chunk's pair lists
@@ -1686,8 +1706,8 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
     bool t0_recorded = false;
     if (ctx->copy_only) {
       // measurement mode: the copies of this call with the same buffers, streams and chunking, and no kernels
-    } else if (single_rec) {
-      P.recs = single_rec;
+    } else if (packed_recs) {
+      P.recs = packed_recs;
       CK(cudaEventRecord(L.ev_t0[c], SC)); t0_recorded = true;
     } else if (small) {
       // one preparation launch (which also packs up to SMALL_FUSED pairs) and one solver launch over the merged tier
@@ -1736,10 +1756,10 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       // costs ~2 us of front-end time): single pair 49.5 -> 45.8 us (device pointers), 1 000 pairs 76 -> 71 us
       static const bool pdl = !(getenv("DCOL_PDL") && atoi(getenv("DCOL_PDL")) == 0);      // tuning knob
       const int early = (pdl && small && n_launch == 1 && nc <= SMALL_FUSED) ? 1 : 0;
-      if (single_rec) {
+      if (packed_recs) {
         P.row_pitch = TR.pitch;
-        const size_t sm1 = (size_t)TR.pitch * sizeof(double) * 32;
-        CK(jac == 2 ? launch_single_v2(sm1, st, P, single_cp) : (jac == 1 ? launch_single_v1(sm1, st, P, single_cp) : launch_single_v0(sm1, st, P, single_cp)));
+        const size_t smp = (size_t)TR.pitch * sizeof(double) * packed_block;
+        CK(jac == 2 ? launch_packed_v2(packed_block, smp, st, P, packed) : (jac == 1 ? launch_packed_v1(packed_block, smp, st, P, packed) : launch_packed_v0(packed_block, smp, st, P, packed)));
       } else
       CK(launch_persistent(jac, grid, TR.block, TR.smem, st, d_tab + t, d_counter + t, early));
       ctx->launches++;

@@ -117,6 +117,11 @@ struct LaunchTable {
   int in_cap[MAX_BINS];
 };
 
+// A handful of pairs whose records the HOST packed (host-pointer calls of up to DCOL_PACKED_MAX pairs): one block per
+// class pair present, records of a class pair contiguous.  Passed to the kernel by value.
+constexpr int DCOL_PACKED_MAX = 128;
+struct PackedGroups { int n; int cp[MAX_BINS]; int first[MAX_BINS]; int count[MAX_BINS]; };
+
 // what one tile needs to know beyond the query parameters
 struct TileCtx {
   int mode;                        // 0 first pass, 1 resume

@@ -94,21 +94,25 @@ __global__ void DCOL_KERNEL_BOUNDS proximity_persistent(LaunchTable* __restrict_
   }
 }
 
-// One pair whose packed record the host wrote itself (single-pair calls on host pointers, dcol_capi.cu): no binning pass
-// and no launch table, one launch in all.  Lane 0 owns the pair; the other lanes of the warp redo it for the barriers only.
+// A handful of pairs whose packed records the host wrote itself (host-pointer calls of up to DCOL_PACKED_MAX pairs, above all the
+// single-pair calls; dcol_capi.cu): no binning pass and no launch table, one launch in all.  One block per class pair
+// present; lanes past the group's last pair redo it for the barriers only.
 template <int VAR>
-__global__ void __launch_bounds__(32) proximity_single(QueryParams P, int cp) {
+__global__ void __launch_bounds__(DCOL_PACKED_MAX) proximity_packed(QueryParams P, PackedGroups G) {
+  const int g = blockIdx.x, cnt = G.count[g];
   TileCtx tc;
   tc.mode = 0; tc.spill_t = 0; tc.ov = nullptr; tc.ov_cap = 0; tc.ov_count = nullptr; tc.in = nullptr; tc.in_cap = 0;
-  tc.dup = threadIdx.x != 0;
+  tc.dup = (int)threadIdx.x >= cnt;
+  const int idx = G.first[g] + min((int)threadIdx.x, cnt - 1);
+  const int cp = G.cp[g];
   const int c1 = cp / NCLS, c2 = cp - c1 * NCLS;
   switch (c1) {
-    case 0: dispatch_c2<0, VAR>(c2, &P, &tc, 0); break;
-    case 1: dispatch_c2<1, VAR>(c2, &P, &tc, 0); break;
-    case 2: dispatch_c2<2, VAR>(c2, &P, &tc, 0); break;
-    case 3: dispatch_c2<3, VAR>(c2, &P, &tc, 0); break;
-    case 4: dispatch_c2<4, VAR>(c2, &P, &tc, 0); break;
-    case 5: dispatch_c2<5, VAR>(c2, &P, &tc, 0); break;
+    case 0: dispatch_c2<0, VAR>(c2, &P, &tc, idx); break;
+    case 1: dispatch_c2<1, VAR>(c2, &P, &tc, idx); break;
+    case 2: dispatch_c2<2, VAR>(c2, &P, &tc, idx); break;
+    case 3: dispatch_c2<3, VAR>(c2, &P, &tc, idx); break;
+    case 4: dispatch_c2<4, VAR>(c2, &P, &tc, idx); break;
+    case 5: dispatch_c2<5, VAR>(c2, &P, &tc, idx); break;
   }
 }
 
@@ -128,12 +132,12 @@ cudaError_t DCOL_CAT(launch_persistent_v, DCOL_VAR)(int grid, int block, size_t 
   proximity_persistent<DCOL_VAR><<<grid, block, smem, st>>>(tt, counter);
   return cudaGetLastError();
 }
-cudaError_t DCOL_CAT(launch_single_v, DCOL_VAR)(size_t smem, cudaStream_t st, const QueryParams& P, int cp) {
-  if (smem > 48 * 1024) {      // (row stores of very large polytopes only)
-    cudaError_t e = cudaFuncSetAttribute(proximity_single<DCOL_VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t DCOL_CAT(launch_packed_v, DCOL_VAR)(int block, size_t smem, cudaStream_t st, const QueryParams& P, const PackedGroups& G) {
+  if (smem > 48 * 1024) {      // (row stores of large polytopes only)
+    cudaError_t e = cudaFuncSetAttribute(proximity_packed<DCOL_VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  proximity_single<DCOL_VAR><<<1, 32, smem, st>>>(P, cp);
+  proximity_packed<DCOL_VAR><<<G.n, block, smem, st>>>(P, G);
   return cudaGetLastError();
 }
 }  // namespace dcol

@@ -606,7 +606,24 @@ def test_single_pair_one_launch_path(ctx, att_kind):
                 for key in one:
                     assert np.array_equal(one[key][0], two[key][0], equal_nan=True), (i, j, kind, key)
             k += 1
+    # a handful of pairs (up to 128 on host pointers): packed on the host as well, one block per class pair present --
+    # bit-identical to the same pairs inside a batch that takes the preparation-kernel path (129 pairs and more)
+    n = 300
+    tm, s1, s2, q1, b1, q2, b2 = util.mixed_batch(n, att_kind, seed=9, variant="scene", table=t)
+    ctx.set_shape_arrays(*t.arrays())
+    for kind in (0, 1, 2):
+        big = ctx._batch(kind, s1, s2, q1, b1, q2, b2, att_kind, 1e-6)
+        for m in (2, 3, 31, 32, 33, 78, 128):
+            sm = ctx._batch(kind, s1[:m], s2[:m], q1[:m], b1[:m], q2[:m], b2[:m], att_kind, 1e-6)
+            for key in sm:
+                assert np.array_equal(sm[key], big[key][:m], equal_nan=True), (kind, m, key)
+        one_class = ctx._batch(kind, np.full(128, s1[0]), np.full(128, s2[0]), q1[:128], b1[:128], q2[:128], b2[:128], att_kind, 1e-6)   # one group of 128
+        ref = ctx._batch(kind, np.full(n, s1[0]), np.full(n, s2[0]), q1, b1, q2, b2, att_kind, 1e-6)
+        for key in one_class:
+            assert np.array_equal(one_class[key], ref[key][:128], equal_nan=True), (kind, key)
     with pytest.raises(RuntimeError, match="shape index out of range"):
-        ctx._batch(0, [len(ids)], [0], r1[:1], a1[:1], r2[:1], a2[:1], att_kind, 1e-6)
+        ctx._batch(0, [0, len(ids) + 40, 1], [0, 1, 2], r1[:3], a1[:3], r2[:3], a2[:3], att_kind, 1e-6)
+    with pytest.raises(RuntimeError, match="shape index out of range"):
+        ctx._batch(0, [len(ids) + 40], [0], r1[:1], a1[:1], r2[:1], a2[:1], att_kind, 1e-6)
     ok = ctx._batch(0, [0], [1], r1[:1], a1[:1], r2[:1], a2[:1], att_kind, 1e-6)          # the context stays usable
     assert ok["status"][0] == 0

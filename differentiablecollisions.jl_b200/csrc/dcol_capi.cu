@@ -1961,6 +1961,23 @@ int dcol_scene_allpairs_range(dcol_ctx* ctx, int query, int n_bodies, int64_t k_
   { int rc = drain_all(ctx); if (rc) return rc; }      // context-level scratch (d_scene, d_pairs) is about to be rewritten
   cudaStream_t S = ctx->stream();
   const int na = (att_kind == DCOL_ATT_QUAT) ? 4 : 3;
+  // A handful of pairs on host arrays (the contact example's own scene: 13 bodies, 78 pairs): the host writes the pair
+  // list itself and the call takes the one-launch path of small host-pointer queries (same records, same results).
+  if (mem == DCOL_MEM_HOST && np <= DCOL_PACKED_MAX && ctx->cull_alpha <= 0.0) {
+    std::vector<int32_t> s1(np), s2(np);
+    std::vector<double> r1(3 * np), a1((size_t)na * np), r2(3 * np), a2((size_t)na * np);
+    int64_t i = 0, k = 0;
+    while ((i + 1) * (2 * (int64_t)n_bodies - i - 2) / 2 <= k_begin) i++;             // row of the first pair
+    int64_t j = k_begin - i * (2 * (int64_t)n_bodies - i - 1) / 2 + i + 1;
+    for (; k < np; k++) {
+      s1[k] = shape[i]; s2[k] = shape[j];
+      for (int a = 0; a < 3; a++) { r1[3 * k + a] = r[3 * i + a]; r2[3 * k + a] = r[3 * j + a]; }
+      for (int a = 0; a < na; a++) { a1[na * k + a] = att[na * i + a]; a2[na * k + a] = att[na * j + a]; }
+      if (++j == n_bodies) { i++; j = i + 1; }
+    }
+    return run_query(ctx, query, np, s1.data(), s2.data(), r1.data(), a1.data(), r2.data(), a2.data(), att_kind, pdip_tol, DCOL_MEM_HOST,
+                     alpha, x, deriv, status, iters);
+  }
   // body arrays on the device
   const int32_t* d_shape = shape; const double* d_r = r; const double* d_att = att;
   if (mem == DCOL_MEM_HOST) {

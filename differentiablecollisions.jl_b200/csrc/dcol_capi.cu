@@ -1557,9 +1557,9 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       cpk[i] = std::min(c1, c2) * NCLS + std::max(c1, c2);
       cnt[cpk[i]]++;
     }
-    int first[MAX_BINS], g_of[MAX_BINS];
+    int first[MAX_BINS];
     for (int cp = 0, at = 0; cp < MAX_BINS; cp++) if (cnt[cp]) {
-      g_of[cp] = packed.n; packed.cp[packed.n] = cp; packed.first[packed.n] = at; packed.count[packed.n] = cnt[cp];
+      packed.cp[packed.n] = cp; packed.first[packed.n] = at; packed.count[packed.n] = cnt[cp];
       first[cp] = at; at += cnt[cp]; packed.n++;
       packed_block = std::max(packed_block, (cnt[cp] + 31) & ~31);
     }
@@ -1575,7 +1575,6 @@ static int run_query(dcol_ctx* ctx, int query, int64_t n, const int32_t* shape1,
       for (int a = 0; a < na; a++) { R.a1[a] = aa[a]; R.a2[a] = ab[a]; }
       R.s1 = swp ? s2 : s1; R.s2 = swp ? s1 : s2; R.pair = (int32_t)i; R.flags = swp ? DCOL_REC_SWAPPED : 0;
     }
-    (void)g_of;
     // (a tier whose row store leaves room for fewer threads per block than the largest group needs keeps the general path)
     if (packed_block <= (ctx->has_small ? ctx->small_tier : ctx->tiers[0]).block) packed_recs = (const PairRec*)(di + align256(b_in));
   }

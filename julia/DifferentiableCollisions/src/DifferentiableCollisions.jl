@@ -7,7 +7,9 @@
 #   proximity_gradient   src/proximity_gradient.jl:80-111
 #   helpers           src/problem_matrices.jl:1-27, src/misc_primitive_constructors.jl:1-33
 # — and forwards every query through `ccall` to the C ABI of include/dcol_b200.h.  There is no Julia
-# numerics here and no CPU fallback: without the shared library and a CUDA device `__init__` throws.
+# solver here and no CPU fallback: without the shared library and a CUDA device `__init__` throws (the only
+# arithmetic on the Julia side packs shape tables and, for `verbose = true`, the dense (c, G, h) of one pair that
+# `dcol_solve_socp_trace` then solves on the GPU).
 #
 # NOTE: Julia is not installed in the build image, so this file is written against the C header and
 # has NOT been executed; the same ABI is exercised from Python (ctypes) by tests/ and bench.py.
